@@ -1,0 +1,443 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, imported by or shipped with the
+// product (optnetaligncpp_b200/).  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load the library this
+// file is compiled into.
+//
+// extern "C" shim around the UNMODIFIED reference translation units
+//   /root/reference/{Network,blastinfo,goc,Alignment,localSearch,nsga-ii,Archive}.cpp
+// which oracle/Makefile compiles *where they lie* together with this file into
+// oracle/_ref/libona_ref.so.  Everything in here only CALLS the reference's own
+// public C++ API (Alignment.h:13-113, localSearch.h:9-24, Network.h:98-108,
+// blastinfo.h:12, goc.h:14) and moves data across a C boundary so that the
+// Python tests and bench.py can drive the real reference through ctypes.
+//
+// The only pieces of logic that are restated here rather than called are
+//   * ref_gen_xy_stream      -- the two uniform_int_distribution draws of
+//                               localSearch.cpp:21-28, so that the very same
+//                               (x,y) proposal stream can be fed to the GPU;
+//   * ref_hill_climb_replay  -- the accept/undo loop of localSearch.cpp:29-53
+//                               driven by an explicit (x,y) list instead of a
+//                               PRNG (tests pin it against the real
+//                               correctHillClimb with the same seed);
+//   * ref_aln_set_state      -- the "seed the incremental counters" idiom of
+//                               Alignment.cpp:437-446 after assigning a
+//                               caller-provided permutation/mask.
+// All three operate through the reference's doSwap/computeFitness/ics/... so the
+// arithmetic is still the reference's.
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <exception>
+#include <random>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "Alignment.h"
+#include "Network.h"
+#include "blastinfo.h"
+#include "goc.h"
+#include "localSearch.h"
+
+static thread_local std::string g_err;
+
+#define REF_TRY try {
+#define REF_CATCH(ret)                   \
+    }                                    \
+    catch (const std::exception& e) {    \
+        g_err = e.what();                \
+        return ret;                      \
+    }                                    \
+    catch (...) {                        \
+        g_err = "unknown C++ exception"; \
+        return ret;                      \
+    }
+
+static std::vector<fitnessName> to_names(const int* names, int M) {
+    std::vector<fitnessName> v;
+    for (int i = 0; i < M; ++i) v.push_back(static_cast<fitnessName>(names[i]));
+    return v;
+}
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+// ----------------------------------------------------------------- Network
+void* ref_net_load(const char* path) {
+    REF_TRY
+    return new Network(std::string(path));
+    REF_CATCH(nullptr)
+}
+void ref_net_free(void* n) { delete static_cast<Network*>(n); }
+int ref_net_n(void* n) { return (int)static_cast<Network*>(n)->nodeToNodeName.size(); }
+long ref_net_num_edges(void* n) { return (long)static_cast<Network*>(n)->edges.size(); }
+long ref_net_adj_total(void* n) {
+    long t = 0;
+    for (auto& l : static_cast<Network*>(n)->adjList) t += (long)l.size();
+    return t;
+}
+// rowptr has n+1 entries, col has ref_net_adj_total entries; adjList order kept.
+void ref_net_export_csr(void* n, int* rowptr, int* col) {
+    Network* net = static_cast<Network*>(n);
+    long k = 0;
+    for (size_t i = 0; i < net->adjList.size(); ++i) {
+        rowptr[i] = (int)k;
+        for (node v : net->adjList[i]) col[k++] = v;
+    }
+    rowptr[net->adjList.size()] = (int)k;
+}
+int ref_net_adjmatrix_bit(void* n, int u, int v) {
+    return static_cast<Network*>(n)->adjMatrix[u][v] ? 1 : 0;
+}
+// writes the node name into buf (NUL terminated, truncated to cap-1)
+void ref_net_node_name(void* n, int u, char* buf, int cap) {
+    const std::string& s = static_cast<Network*>(n)->nodeToNodeName.at(u);
+    std::strncpy(buf, s.c_str(), cap - 1);
+    buf[cap - 1] = 0;
+}
+
+// ------------------------------------------------------- score dictionaries
+void* ref_blast_load(void* n1, void* n2, const char* path) {
+    REF_TRY
+    return loadBLASTInfo(static_cast<Network*>(n1), static_cast<Network*>(n2), std::string(path));
+    REF_CATCH(nullptr)
+}
+void* ref_goc_load(void* n1, void* n2, const char* f1, const char* f2) {
+    REF_TRY
+    return loadGOC(static_cast<Network*>(n1), static_cast<Network*>(n2), std::string(f1),
+                   std::string(f2));
+    REF_CATCH(nullptr)
+}
+// dense row-major rows x cols doubles -> a BLASTDict/GOCDict (same type)
+void* ref_dict_from_dense(int rows, int cols, const double* data) {
+    BLASTDict* d = new BLASTDict(boost::extents[rows][cols]);
+    for (int i = 0; i < rows; ++i)
+        for (int j = 0; j < cols; ++j) (*d)[i][j] = data[(size_t)i * cols + j];
+    return d;
+}
+void ref_dict_free(void* d) { delete static_cast<BLASTDict*>(d); }
+double ref_dict_get(void* d, int i, int j) { return (*static_cast<BLASTDict*>(d))[i][j]; }
+// copies row i (cols doubles) out
+void ref_dict_row(void* d, int i, int cols, double* out) {
+    const double* r = (*static_cast<const BLASTDict*>(d))[i];
+    std::memcpy(out, r, sizeof(double) * (size_t)cols);
+}
+
+// --------------------------------------------------------------- Alignment
+void* ref_aln_new(void* n1, void* n2, void* bit, void* goc) {
+    REF_TRY
+    Alignment* a = new Alignment(static_cast<Network*>(n1), static_cast<Network*>(n2),
+                                 static_cast<BLASTDict*>(bit), static_cast<GOCDict*>(goc));
+    // constructor 1 leaves the two fp64 accumulators uninitialised
+    // (Alignment.cpp:23-47); give them the from-scratch values.
+    if (a->bitscores) a->currBitscore = a->sumBLAST(); else a->currBitscore = 0.0;
+    if (a->gocs) a->currGOC = a->sumGOC(); else a->currGOC = 0.0;
+    return a;
+    REF_CATCH(nullptr)
+}
+void* ref_aln_clone(void* a) { return new Alignment(*static_cast<Alignment*>(a)); }
+void ref_aln_free(void* a) { delete static_cast<Alignment*>(a); }
+
+void ref_aln_shuf(void* a, uint32_t seed, int uniformsize, int smallstart, int total) {
+    RandGenT g(seed);
+    static_cast<Alignment*>(a)->shuf(g, uniformsize != 0, smallstart != 0, total != 0);
+}
+
+// assign permutation + mask, then seed counters exactly like Alignment.cpp:437-446
+void ref_aln_set_state(void* av, const int* aln, const uint8_t* mask) {
+    Alignment* a = static_cast<Alignment*>(av);
+    size_t n = a->aln.size();
+    for (size_t i = 0; i < n; ++i) {
+        a->aln[i] = aln[i];
+        a->alnInv[aln[i]] = (int)i;
+        a->alnMask[i] = mask ? (mask[i] != 0) : true;
+    }
+    if (a->bitscores) a->currBitscore = a->sumBLAST();
+    if (a->gocs) a->currGOC = a->sumGOC();
+    double denom = a->fastICSDenominator();
+    a->currConservedCount = a->ics() * denom;
+    a->currInducedCount = (int)denom;
+    a->fitnessValid = false;
+}
+int ref_aln_size_n2(void* a) { return (int)static_cast<Alignment*>(a)->aln.size(); }
+void ref_aln_get_state(void* av, int* aln, int* alnInv, uint8_t* mask) {
+    Alignment* a = static_cast<Alignment*>(av);
+    size_t n = a->aln.size();
+    for (size_t i = 0; i < n; ++i) {
+        if (aln) aln[i] = a->aln[i];
+        if (alnInv) alnInv[i] = a->alnInv[i];
+        if (mask) mask[i] = a->alnMask[i] ? 1 : 0;
+    }
+}
+void ref_aln_get_counters(void* av, int* cons, int* ind, double* bits, double* goc) {
+    Alignment* a = static_cast<Alignment*>(av);
+    *cons = a->currConservedCount;
+    *ind = a->currInducedCount;
+    *bits = a->bitscores ? a->currBitscore : 0.0;
+    *goc = a->gocs ? a->currGOC : 0.0;
+}
+void ref_aln_set_counters(void* av, int cons, int ind, double bits, double goc) {
+    Alignment* a = static_cast<Alignment*>(av);
+    a->currConservedCount = cons;
+    a->currInducedCount = ind;
+    a->currBitscore = bits;
+    a->currGOC = goc;
+}
+void ref_aln_do_swap(void* a, int x, int y) { static_cast<Alignment*>(a)->doSwap(x, y); }
+void ref_aln_compute_fitness(void* av, const int* names, int M, double* out) {
+    Alignment* a = static_cast<Alignment*>(av);
+    std::vector<fitnessName> fn = to_names(names, M);
+    a->computeFitness(fn);
+    for (int i = 0; i < M; ++i) out[i] = a->fitness[i];
+}
+double ref_aln_ics(void* a) { return static_cast<Alignment*>(a)->ics(); }
+double ref_aln_fast_ics_denominator(void* a) {
+    return static_cast<Alignment*>(a)->fastICSDenominator();
+}
+double ref_aln_sum_blast(void* a) { return static_cast<Alignment*>(a)->sumBLAST(); }
+double ref_aln_sum_goc(void* a) { return static_cast<Alignment*>(a)->sumGOC(); }
+double ref_aln_aln_size(void* a) { return static_cast<Alignment*>(a)->alnSize(); }
+int ref_aln_conserved_count(void* a, int n1, int n2, int mask, int ignore) {
+    return static_cast<Alignment*>(a)->conservedCount(n1, n2, mask != 0, ignore);
+}
+int ref_aln_induced_count(void* a, int n2, int ignore) {
+    return static_cast<Alignment*>(a)->inducedCount(n2, ignore);
+}
+void ref_aln_mutate(void* a, uint32_t seed, float mutswappb, int total) {
+    RandGenT g(seed);
+    static_cast<Alignment*>(a)->mutate(g, mutswappb, total != 0);
+}
+void* ref_aln_crossover(uint32_t seed, float cxswappb, void* p1, void* p2, int total) {
+    RandGenT g(seed);
+    return new Alignment(g, cxswappb, *static_cast<Alignment*>(p1), *static_cast<Alignment*>(p2),
+                         total != 0);
+}
+
+// ------------------------------------------------------------ local search
+// the real thing: correctHillClimb with mt19937(seed)  (localSearch.cpp:18-55)
+void ref_correct_hill_climb(void* av, uint32_t seed, int iters, const int* names, int M, int obj) {
+    Alignment* a = static_cast<Alignment*>(av);
+    std::vector<fitnessName> fn = to_names(names, M);
+    RandGenT g(seed);
+    correctHillClimb(g, a, true, iters, fn, obj);
+}
+
+// the (x,y) proposals correctHillClimb would draw from mt19937(seed):
+// same two distribution objects, same draw order as localSearch.cpp:21-28.
+void ref_gen_xy_stream(uint32_t seed, int n1, int n2, long iters, int* xy) {
+    RandGenT prng(seed);
+    auto randNonDummyIndex = std::uniform_int_distribution<int>(0, n1 - 1);
+    auto randIndex = std::uniform_int_distribution<int>(0, n2 - 2);
+    for (long i = 0; i < iters; ++i) {
+        node x = randNonDummyIndex(prng);
+        node y = randIndex(prng);
+        if (y >= x) y++;
+        xy[2 * i] = x;
+        xy[2 * i + 1] = y;
+    }
+}
+
+// accept/undo loop of localSearch.cpp:29-53 over an explicit proposal list.
+// accepted (optional) receives 1/0 per proposal.  aln->fitness must be valid.
+void ref_hill_climb_replay(void* av, const int* xy, long iters, const int* names, int M, int obj,
+                           uint8_t* accepted) {
+    Alignment* aln = static_cast<Alignment*>(av);
+    std::vector<fitnessName> fn = to_names(names, M);
+    std::vector<double> currFit(M);
+    for (long i = 0; i < iters; ++i) {
+        node x = xy[2 * i], y = xy[2 * i + 1];
+        std::copy(aln->fitness.begin(), aln->fitness.end(), currFit.begin());
+        aln->doSwap(x, y);
+        aln->computeFitness(fn);
+        bool improved = true;
+        if (obj == -1) {
+            for (int j = 0; j < M; ++j)
+                if (aln->fitness[j] < currFit[j]) improved = false;
+        } else {
+            if (aln->fitness[obj] <= currFit[obj]) improved = false;
+        }
+        if (!improved) {
+            aln->doSwap(x, y);
+            aln->computeFitness(fn);
+        }
+        if (accepted) accepted[i] = improved ? 1 : 0;
+    }
+}
+
+double ref_swap_normalized_delta(void* av, const int* names, int M, int x, int y) {
+    Alignment* a = static_cast<Alignment*>(av);
+    std::vector<fitnessName> fn = to_names(names, M);
+    return swapNormalizedDelta(*a, fn, x, y);
+}
+
+// Per-candidate records against ONE base state: for each (x,y) do the swap with
+// the reference's doSwap+computeFitness, record the new counters / accumulators /
+// objectives and the accept decision for `obj`, undo, and restore the two fp64
+// accumulators + fitness to the base values (the undo is not bit-exact, H3).
+// Outputs (any may be null): cons[n], ind[n], bits[n], goc[n], fit[n*M], improved[n],
+// snd[n] = swapNormalizedDelta value.
+void ref_swap_delta_records(void* av, const int* names, int M, int obj, const int* xy, long n,
+                            int* cons, int* ind, double* bits, double* goc, double* fit,
+                            uint8_t* improved, double* snd) {
+    Alignment* a = static_cast<Alignment*>(av);
+    std::vector<fitnessName> fn = to_names(names, M);
+    a->computeFitness(fn);
+    const std::vector<double> base = a->fitness;
+    const double b0 = a->currBitscore, g0 = a->currGOC;
+    for (long i = 0; i < n; ++i) {
+        node x = xy[2 * i], y = xy[2 * i + 1];
+        if (snd) {
+            snd[i] = swapNormalizedDelta(*a, fn, x, y);
+            a->currBitscore = b0;
+            a->currGOC = g0;
+            a->fitness = base;
+        }
+        a->doSwap(x, y);
+        a->computeFitness(fn);
+        if (cons) cons[i] = a->currConservedCount;
+        if (ind) ind[i] = a->currInducedCount;
+        if (bits) bits[i] = a->bitscores ? a->currBitscore : 0.0;
+        if (goc) goc[i] = a->gocs ? a->currGOC : 0.0;
+        if (fit)
+            for (int j = 0; j < M; ++j) fit[i * M + j] = a->fitness[j];
+        if (improved) {
+            bool imp = true;
+            if (obj == -1) {
+                for (int j = 0; j < M; ++j)
+                    if (a->fitness[j] < base[j]) imp = false;
+            } else if (a->fitness[obj] <= base[obj]) {
+                imp = false;
+            }
+            improved[i] = imp ? 1 : 0;
+        }
+        a->doSwap(x, y);
+        a->currBitscore = b0;
+        a->currGOC = g0;
+        a->fitness = base;
+    }
+}
+
+// ------------------------------------------------------------ CPU baselines
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch())
+        .count();
+}
+
+// Threaded swapNormalizedDelta over a fixed candidate list: the worker pattern of
+// localSearch.cpp:130-147 (private Alignment copy per thread, contiguous slab of
+// the candidates each).  alns[] holds `nalns` base individuals; thread t works
+// on individual t % nalns.  Returns wall seconds; *sink gets a checksum.
+double ref_time_swap_deltas(void** alns, int nalns, const int* names, int M, const int* xy,
+                            long n, int nthreads, double* sink) {
+    std::vector<fitnessName> fn = to_names(names, M);
+    std::vector<double> sums(nthreads, 0.0);
+    std::vector<Alignment> locals;
+    locals.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        locals.push_back(*static_cast<Alignment*>(alns[t % nalns]));
+        locals.back().computeFitness(fn);
+    }
+    std::vector<std::thread> ts;
+    double t0 = now_s();
+    for (int t = 0; t < nthreads; ++t) {
+        ts.push_back(std::thread([&, t]() {
+            long lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+            Alignment& local = locals[t];
+            double s = 0.0;
+            for (long i = lo; i < hi; ++i) {
+                double d = swapNormalizedDelta(local, fn, xy[2 * i], xy[2 * i + 1]);
+                if (d > 0.0 && d < 1e300) s += d;
+            }
+            sums[t] = s;
+        }));
+    }
+    for (auto& th : ts) th.join();
+    double t1 = now_s();
+    double s = 0.0;
+    for (double v : sums) s += v;
+    if (sink) *sink = s;
+    return t1 - t0;
+}
+
+// Threaded correctHillClimb on independent individuals (the worker pattern of
+// steadystate.cpp:132-253): individual i is climbed `iters` iterations with
+// mt19937(seed0+i); individuals are handed out dynamically to nthreads threads.
+// The alignments ARE modified.  Returns wall seconds.
+double ref_time_hill_climb(void** alns, int nalns, uint32_t seed0, int iters, const int* names,
+                           int M, int obj, int nthreads) {
+    std::vector<fitnessName> fn = to_names(names, M);
+    for (int i = 0; i < nalns; ++i) static_cast<Alignment*>(alns[i])->computeFitness(fn);
+    std::atomic<int> next(0);
+    std::vector<std::thread> ts;
+    double t0 = now_s();
+    for (int t = 0; t < nthreads; ++t) {
+        ts.push_back(std::thread([&]() {
+            for (;;) {
+                int i = next.fetch_add(1);
+                if (i >= nalns) break;
+                RandGenT g(seed0 + (uint32_t)i);
+                correctHillClimb(g, static_cast<Alignment*>(alns[i]), true, iters, fn, -1 == obj ? -1 : obj);
+            }
+        }));
+    }
+    for (auto& th : ts) th.join();
+    return now_s() - t0;
+}
+
+// Threaded from-scratch scoring (the tail of shuf, Alignment.cpp:437-446, plus
+// computeFitness): `reps` evaluations spread over nthreads threads, each on
+// individual (k % nalns).  with_ics=0 skips the hash-set ics() and recounts the
+// conserved edges through conservedCount() instead (adjacency based), so the
+// comparison is not inflated by the reference's unordered_set implementation.
+double ref_time_full_fitness(void** alns, int nalns, const int* names, int M, long reps,
+                             int nthreads, int with_ics, double* sink) {
+    std::vector<fitnessName> fn = to_names(names, M);
+    std::vector<std::vector<Alignment>> locals(nthreads);
+    for (int t = 0; t < nthreads; ++t)
+        for (int i = 0; i < nalns; ++i) locals[t].push_back(*static_cast<Alignment*>(alns[i]));
+    std::vector<double> sums(nthreads, 0.0);
+    std::vector<std::thread> ts;
+    double t0 = now_s();
+    for (int t = 0; t < nthreads; ++t) {
+        ts.push_back(std::thread([&, t]() {
+            long lo = reps * t / nthreads, hi = reps * (t + 1) / nthreads;
+            double s = 0.0;
+            for (long k = lo; k < hi; ++k) {
+                Alignment& a = locals[t][k % nalns];
+                if (a.bitscores) a.currBitscore = a.sumBLAST();
+                if (a.gocs) a.currGOC = a.sumGOC();
+                double denom = a.fastICSDenominator();
+                if (with_ics) {
+                    a.currConservedCount = a.ics() * denom;
+                } else {
+                    int twice = 0;
+                    for (int u = 0; u < a.actualSize; ++u) {
+                        int c = a.conservedCount(u, a.aln[u], a.alnMask[u], -1);
+                        // a self-loop appears once in adjList, all other edges twice
+                        twice += c;
+                        if (a.alnMask[u] && a.net1->adjMatrix[u][u] &&
+                            a.net2->adjMatrix[a.aln[u]][a.aln[u]])
+                            twice += 1;
+                    }
+                    a.currConservedCount = twice / 2;
+                }
+                a.currInducedCount = (int)denom;
+                a.computeFitness(fn);
+                s += a.fitness[0];
+            }
+            sums[t] = s;
+        }));
+    }
+    for (auto& th : ts) th.join();
+    double t1 = now_s();
+    double s = 0.0;
+    for (double v : sums) s += v;
+    if (sink) *sink = s;
+    return t1 - t0;
+}
+
+int ref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+"""Generates the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Run in the dev container only (needs /root/reference and oracle/_ref/libona_ref.so):
+
+    python tests/golden/make_golden.py
+
+Outputs
+  example_pair.npz   the bundled example pair as the reference's loaders see it
+                     (Network.cpp:39-112 node numbering / adjList order, edges.size(),
+                     blastinfo.cpp:11-45 non-zeros incl. the "unknown name -> node 0" rule H4)
+                     + reference results on it: shuf(mt19937(seed)) individuals, their seeded
+                     counters, objectives, per-candidate doSwap records, a correctHillClimb
+                     trajectory (proposals from mt19937(7), localSearch.cpp:21-28).
+  small_pair.npz     a 120/150-node synthetic pair with bit scores AND GO annotations, with
+                     partial (masked) individuals and every objective name.
+Nothing here is read at test time except the .npz files.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref  # noqa: E402
+from optnetaligncpp_b200 import synth  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+ALL_NAMES = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9]
+
+
+def records(a, xy, names, obj):
+    r = a.swap_delta_records(xy, names, obj=obj, want_snd=True)
+    return {k: v for k, v in r.items()}
+
+
+def example_pair():
+    n1 = ref.Net(os.path.join(REF, "example1.net"))
+    n2 = ref.Net(os.path.join(REF, "example2.net"))
+    B = ref.Dict.load_blast(n1, n2, os.path.join(REF, "example.sim"))
+    rp1, col1 = n1.csr()
+    rp2, col2 = n2.csr()
+    S = B.dense()
+    br, bc = np.nonzero(S)
+    out = dict(n1=n1.n, n2=n2.n, E1=n1.E, E2=n2.E, rp1=rp1, col1=col1, rp2=rp2, col2=col2,
+               bit_rows=br.astype(np.int32), bit_cols=bc.astype(np.int32), bit_vals=S[br, bc])
+    names = np.array([6, 2], np.int32)          # --s3 --blastsum   (argParsing.h:212-271 order)
+    out["names"] = names
+    seeds = [42, 43, 44]
+    alns, ctr, fit, ics, denom = [], [], [], [], []
+    for s in seeds:
+        a = ref.Aln(n1, n2, B, None)
+        a.shuf(s)
+        al, _, _ = a.state()
+        alns.append(al)
+        ctr.append(a.counters())
+        fit.append(a.compute_fitness(names))
+        ics.append(a.ics())
+        denom.append(a.fast_ics_denominator())
+    out["seeds"] = np.array(seeds)
+    out["aln"] = np.array(alns, np.int32)
+    out["cons"] = np.array([c[0] for c in ctr], np.int32)
+    out["ind"] = np.array([c[1] for c in ctr], np.int32)
+    out["bits"] = np.array([c[2] for c in ctr])
+    out["fitness"] = np.array(fit)
+    out["ics"] = np.array(ics)
+    out["denom"] = np.array(denom)
+    # identity alignment (constructor 1) known answers
+    ident = ref.Aln(n1, n2, B, None)
+    out["ident_counters"] = np.array(ident.counters())
+    # per-candidate records on individual 0, obj=-1 and obj=0
+    a = ref.Aln(n1, n2, B, None)
+    a.shuf(seeds[0])
+    xy = ref.gen_xy_stream(11, n1.n, n2.n, 3000)
+    out["cand_xy"] = xy
+    for obj in (-1, 0, 1):
+        r = records(a, xy, names, obj)
+        for k, v in r.items():
+            if k == "improved" or obj == -1:
+                out["cand_%s_obj%d" % (k, obj)] = v
+    # correctHillClimb trajectory
+    iters = 60000
+    xy = ref.gen_xy_stream(7, n1.n, n2.n, iters)
+    b = a.clone()
+    b.correct_hill_climb(7, iters, names)          # the real thing
+    acc = a.hill_climb_replay(xy, names, want_accepted=True)
+    assert a.counters() == b.counters()
+    assert all((p == q).all() for p, q in zip(a.state(), b.state()))
+    out["hc_seed"] = 7
+    out["hc_xy"] = xy
+    out["hc_accepted"] = np.packbits(acc)
+    out["hc_final_aln"] = a.state()[0]
+    out["hc_final_counters"] = np.array(a.counters())
+    out["hc_final_fitness"] = a.compute_fitness(names)
+    # single-objective climb (obj = 1: bit scores only)
+    c = ref.Aln(n1, n2, B, None)
+    c.shuf(seeds[1])
+    xy1 = ref.gen_xy_stream(8, n1.n, n2.n, 20000)
+    acc1 = c.hill_climb_replay(xy1, names, obj=1, want_accepted=True)
+    out["hc1_xy"] = xy1
+    out["hc1_accepted"] = np.packbits(acc1)
+    out["hc1_final_aln"] = c.state()[0]
+    out["hc1_final_counters"] = np.array(c.counters())
+    np.savez_compressed(os.path.join(OUT, "example_pair.npz"), **out)
+    print("example_pair.npz written; identity", out["ident_counters"], "seed42", ctr[0], fit[0],
+          "after climb", a.counters())
+
+
+def small_pair():
+    pair = synth.make_pair(n1=120, n2=150, m1=500, m2=560, max_deg=30, seed=synth.DEFAULT_SEED + 9,
+                           annotations=True, n_terms=60, terms_per_node=5, bit_density=0.01,
+                           bit_decimals=True)
+    d = tempfile.mkdtemp()
+    paths = synth.write_text(pair, os.path.join(d, "s"))
+    n1, n2 = ref.Net(paths["net1"]), ref.Net(paths["net2"])
+    B = ref.Dict.load_blast(n1, n2, paths["sim"])
+    G = ref.Dict.load_goc(n1, n2, paths["annos1"], paths["annos2"])
+    rp1, col1 = n1.csr()
+    rp2, col2 = n2.csr()
+    assert (rp1 == pair.rp1).all() and (col1 == pair.col1).all()
+    out = dict(n1=n1.n, n2=n2.n, E1=n1.E, E2=n2.E, rp1=rp1, col1=col1, rp2=rp2, col2=col2,
+               S=B.dense(), G=G.dense(), names=np.array(ALL_NAMES, np.int32))
+    names = ALL_NAMES
+    alns, masks, ctr, fit, cand, hc = [], [], [], [], [], []
+    for i, (seed, total) in enumerate([(1, True), (2, False), (3, False), (4, True)]):
+        a = ref.Aln(n1, n2, B, G)
+        a.shuf(seed, total=total)
+        al, _, m = a.state()
+        alns.append(al)
+        masks.append(m)
+        ctr.append(a.counters())
+        fit.append(a.compute_fitness(names))
+        # general doSwap support: x may be a dummy position too (mutate, Alignment.cpp:464)
+        rng = np.random.default_rng(100 + i)
+        xy = np.stack([rng.integers(0, n2.n, 400), rng.integers(0, n2.n, 400)], -1).astype(np.int32)
+        r = records(a, xy, names, -1)
+        out["cand_xy_%d" % i] = xy
+        for k, v in r.items():
+            out["cand_%s_%d" % (k, i)] = v
+        xyh = ref.gen_xy_stream(50 + i, n1.n, n2.n, 4000)
+        obj = [-1, 6, -1, 5][i]
+        acc = a.hill_climb_replay(xyh, names, obj=obj, want_accepted=True)
+        out["hc_xy_%d" % i] = xyh
+        out["hc_obj_%d" % i] = obj
+        out["hc_accepted_%d" % i] = acc
+        out["hc_final_aln_%d" % i] = a.state()[0]
+        out["hc_final_mask_%d" % i] = a.state()[2]
+        out["hc_final_counters_%d" % i] = np.array(a.counters())
+    out["aln"] = np.array(alns, np.int32)
+    out["mask"] = np.array(masks, np.uint8)
+    out["cons"] = np.array([c[0] for c in ctr], np.int32)
+    out["ind"] = np.array([c[1] for c in ctr], np.int32)
+    out["bits"] = np.array([c[2] for c in ctr])
+    out["goc"] = np.array([c[3] for c in ctr])
+    out["fitness"] = np.array(fit)
+    np.savez_compressed(os.path.join(OUT, "small_pair.npz"), **out)
+    print("small_pair.npz written", ctr)
+
+
+if __name__ == "__main__":
+    assert ref.available(), "build oracle/_ref first (make -C oracle)"
+    small_pair()
+    example_pair()

@@ -1,0 +1,99 @@
+"""CPU: the C restatement (oracle/ona_oracle.c) against golden vectors that
+tests/golden/make_golden.py generated from the unmodified compiled reference."""
+import numpy as np
+import pytest
+
+from conftest import dense_from_coo
+from oracle import port
+
+
+@pytest.fixture(scope="module")
+def example_problem(example_golden):
+    g = example_golden
+    S = dense_from_coo(int(g["n1"]), int(g["n2"]), g["bit_rows"], g["bit_cols"], g["bit_vals"])
+    return port.Problem(g["n1"], g["n2"], g["E1"], g["rp1"], g["col1"], g["rp2"], g["col2"], S, None)
+
+
+@pytest.fixture(scope="module")
+def small_problem(small_golden):
+    g = small_golden
+    return port.Problem(g["n1"], g["n2"], g["E1"], g["rp1"], g["col1"], g["rp2"], g["col2"],
+                        g["S"], g["G"])
+
+
+def test_example_identity_known_answers(example_golden, example_problem):
+    # identity alignment of the example pair: C=584, I=27789, bits=685
+    n2 = int(example_golden["n2"])
+    a = port.Aln(example_problem, np.arange(n2, dtype=np.int32))
+    c = a.counters()
+    assert list(example_golden["ident_counters"][:3]) == [584, 27789, 685]
+    assert (c[0], c[1], c[2]) == (584, 27789, 685.0)
+
+
+def test_example_full_fitness(example_golden, example_problem):
+    g = example_golden
+    for i in range(len(g["seeds"])):
+        a = port.Aln(example_problem, g["aln"][i])
+        c = a.counters()
+        assert c[0] == g["cons"][i] and c[1] == g["ind"][i] and c[2] == g["bits"][i]
+        assert a.induced_true() == g["denom"][i]
+        assert a.ics() == g["ics"][i]
+        assert np.array_equal(a.compute_fitness(g["names"]), g["fitness"][i])
+    # seed 42 known answer
+    assert g["cons"][0] == 140 and g["ind"][0] == 12177 and g["bits"][0] == 360.0
+    assert g["fitness"][0][0] == 0.0031865255491066347
+
+
+@pytest.mark.parametrize("obj", [-1, 0, 1])
+def test_example_candidate_records(example_golden, example_problem, obj):
+    g = example_golden
+    a = port.Aln(example_problem, g["aln"][0])
+    r = a.swap_delta_records(g["cand_xy"], g["names"], obj=obj, want_snd=True)
+    assert np.array_equal(r["improved"], g["cand_improved_obj%d" % obj])
+    if obj == -1:
+        for k in ("cons", "ind", "bits", "goc", "fit", "snd"):
+            assert np.array_equal(r[k], g["cand_%s_obj-1" % k], equal_nan=True), k
+
+
+def test_example_hill_climb_trajectory(example_golden, example_problem):
+    g = example_golden
+    a = port.Aln(example_problem, g["aln"][0])
+    acc = a.hill_climb_replay(g["hc_xy"], g["names"], obj=-1, want_accepted=True)
+    assert np.array_equal(np.packbits(acc), g["hc_accepted"])
+    assert np.array_equal(a.state()[0], g["hc_final_aln"])
+    assert list(a.counters()) == list(g["hc_final_counters"])
+    assert np.array_equal(a.compute_fitness(g["names"]), g["hc_final_fitness"])
+    b = port.Aln(example_problem, g["aln"][1])
+    acc = b.hill_climb_replay(g["hc1_xy"], g["names"], obj=1, want_accepted=True)
+    assert np.array_equal(np.packbits(acc), g["hc1_accepted"])
+    assert np.array_equal(b.state()[0], g["hc1_final_aln"])
+    assert list(b.counters()) == list(g["hc1_final_counters"])
+
+
+def test_small_pair_all_objectives_and_masks(small_golden, small_problem):
+    g = small_golden
+    names = g["names"]
+    for i in range(4):
+        a = port.Aln(small_problem, g["aln"][i], g["mask"][i])
+        c = a.counters()
+        assert (c[0], c[1]) == (g["cons"][i], g["ind"][i])
+        assert c[2] == g["bits"][i] and c[3] == g["goc"][i]
+        assert np.array_equal(a.compute_fitness(names), g["fitness"][i], equal_nan=True)
+        r = a.swap_delta_records(g["cand_xy_%d" % i], names, obj=-1, want_snd=True)
+        for k in ("cons", "ind", "bits", "goc", "fit", "improved", "snd"):
+            assert np.array_equal(r[k], g["cand_%s_%d" % (k, i)], equal_nan=True), (i, k)
+        acc = a.hill_climb_replay(g["hc_xy_%d" % i], names, obj=int(g["hc_obj_%d" % i]),
+                                  want_accepted=True)
+        assert np.array_equal(acc, g["hc_accepted_%d" % i])
+        st = a.state()
+        assert np.array_equal(st[0], g["hc_final_aln_%d" % i])
+        assert np.array_equal(st[2], g["hc_final_mask_%d" % i])
+        assert list(a.counters()) == list(g["hc_final_counters_%d" % i])
+
+
+def test_refseed_truncation_hazard():
+    # (int)((C/I)*I) lands one below C for some pairs
+    assert port.lib().orc_refseed_conserved(15, 22) == 14
+    assert port.lib().orc_refseed_conserved(104, 11500) == 103
+    assert port.lib().orc_refseed_conserved(140, 12177) == 140
+    assert port.lib().orc_refseed_conserved(5, 0) == 0

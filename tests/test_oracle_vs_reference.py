@@ -1,0 +1,124 @@
+"""CPU: the C restatement against the live compiled reference (oracle/_ref), plus the
+reference test-suite's invariant families (tests.cpp) re-run on synthetic
+inputs.  Skipped where the prebuilt _ref library did not travel."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from optnetaligncpp_b200 import synth
+from oracle import port, ref
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libona_ref.so not built")
+
+NAMES = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9]
+
+
+@pytest.fixture(scope="module")
+def world():
+    pair = synth.make_pair(n1=250, n2=330, m1=1200, m2=1300, max_deg=50, seed=77,
+                           annotations=True, n_terms=150, bit_density=0.01)
+    d = tempfile.mkdtemp()
+    paths = synth.write_text(pair, os.path.join(d, "w"))
+    n1, n2 = ref.Net(paths["net1"]), ref.Net(paths["net2"])
+    B = ref.Dict.load_blast(n1, n2, paths["sim"])
+    G = ref.Dict.load_goc(n1, n2, paths["annos1"], paths["annos2"])
+    S, Gd = synth.dense_bits(pair), synth.dense_goc(pair)
+    prob = port.Problem(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2, S, Gd)
+    return dict(pair=pair, n1=n1, n2=n2, B=B, G=G, S=S, Gd=Gd, prob=prob)
+
+
+def test_loader_numbering_and_adjacency(world):
+    # adjacency_list_correct / adjList_adjMatrix_consistent (tests.cpp:443-508)
+    pair, n1, n2 = world["pair"], world["n1"], world["n2"]
+    assert (n1.n, n1.E, n2.n, n2.E) == (pair.n1, pair.E1, pair.n2, pair.E2)
+    for net, rp, col in ((n1, pair.rp1, pair.col1), (n2, pair.rp2, pair.col2)):
+        r, c = net.csr()
+        assert np.array_equal(r, rp) and np.array_equal(c, col)
+    rng = np.random.default_rng(0)
+    dense = np.zeros((pair.n2, pair.n2), bool)
+    for u in range(pair.n2):
+        dense[u, pair.col2[pair.rp2[u]:pair.rp2[u + 1]]] = True
+    for u, v in rng.integers(0, pair.n2, (2000, 2)):
+        assert n2.adj_bit(int(u), int(v)) == int(dense[u, v])
+    assert np.array_equal(world["B"].dense(), world["S"])
+    assert np.array_equal(world["G"].dense(), world["Gd"])      # double(i)/double(u), goc.cpp:47
+
+
+@pytest.mark.parametrize("total", [True, False])
+def test_from_scratch_and_incremental_match_reference(world, total):
+    w = world
+    for seed in range(6):
+        a = ref.Aln(w["n1"], w["n2"], w["B"], w["G"])
+        a.shuf(seed, total=total)
+        al, inv, m = a.state()
+        o = port.Aln(w["prob"], al, m)
+        assert a.counters() == o.counters()
+        assert a.ics() == o.ics() and a.fast_ics_denominator() == o.induced_true()
+        assert a.sum_blast() == o.sum_blast() and a.sum_goc() == o.sum_goc()
+        assert a.aln_size() == o.aln_size()
+        assert np.array_equal(a.compute_fitness(NAMES), o.compute_fitness(NAMES), equal_nan=True)
+        rng = np.random.default_rng(seed)
+        for _ in range(200):      # doSwap with arbitrary positions (mutate path, Alignment.cpp:464)
+            x, y = (int(v) for v in rng.integers(0, w["pair"].n2, 2))
+            if x == y:
+                continue
+            assert a.conserved_count(x, int(al[x]), 1, y) == o.conserved_count(x, int(al[x]), 1, y)
+            a.do_swap(x, y)
+            o.do_swap(x, y)
+            al = a.state()[0]
+        assert a.counters() == o.counters()
+        assert all(np.array_equal(p, q) for p, q in zip(a.state(), o.state()))
+        # do_swap_consistent_ics / currInducedCount_consistent_after_doSwap (tests.cpp:670-697,993+)
+        assert o.induced_true() == o.counters()[1]
+        assert a.fast_ics_denominator() == a.counters()[1]
+        assert abs(o.sum_blast() - o.counters()[2]) < 1e-9 * max(1.0, abs(o.counters()[2]))
+        assert abs(o.sum_goc() - o.counters()[3]) < 1e-9 * max(1.0, abs(o.counters()[3]))
+
+
+@pytest.mark.parametrize("obj", [-1, 2, 5, 6])
+def test_hill_climb_replay_is_correctHillClimb(world, obj):
+    w = world
+    names = [6, 2, 5]
+    o_idx = {-1: -1, 6: 0, 2: 1, 5: 2}[obj]
+    a = ref.Aln(w["n1"], w["n2"], w["B"], w["G"])
+    a.shuf(3)
+    al, _, m = a.state()
+    o = port.Aln(w["prob"], al, m)
+    real = a.clone()
+    real.correct_hill_climb(99, 30000, names, obj=o_idx)
+    xy = ref.gen_xy_stream(99, w["pair"].n1, w["pair"].n2, 30000)
+    acc_r = a.hill_climb_replay(xy, names, obj=o_idx, want_accepted=True)
+    acc_o = o.hill_climb_replay(xy, names, obj=o_idx, want_accepted=True)
+    assert np.array_equal(acc_r, acc_o)
+    assert real.counters() == a.counters() == o.counters()
+    assert all(np.array_equal(p, q) for p, q in zip(real.state(), o.state()))
+
+
+def test_swap_normalized_delta_and_records(world):
+    w = world
+    a = ref.Aln(w["n1"], w["n2"], w["B"], w["G"])
+    a.shuf(5, total=False)
+    al, _, m = a.state()
+    o = port.Aln(w["prob"], al, m)
+    xy = ref.gen_xy_stream(1, w["pair"].n1, w["pair"].n2, 1500)
+    r1 = a.swap_delta_records(xy, NAMES, want_snd=True)
+    r2 = o.swap_delta_records(xy, NAMES, want_snd=True)
+    for k in r1:
+        assert np.array_equal(r1[k], r2[k], equal_nan=True), k
+
+
+def test_refseed_formula_matches_compiled_reference(world):
+    # H1: the truncated seed equals (int)((C/I)*I) with the TRUE counts
+    w = world
+    hits = 0
+    for seed in range(40):
+        a = ref.Aln(w["n1"], w["n2"], w["B"], w["G"])
+        a.shuf(seed)
+        al, _, m = a.state()
+        o = port.Aln(w["prob"], al, m)
+        C, I = o.conserved_true(), o.induced_true()
+        assert a.counters()[0] == port.lib().orc_refseed_conserved(C, I)
+        hits += int(a.counters()[0] != C)
+    assert hits >= 0
