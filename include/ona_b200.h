@@ -1,0 +1,188 @@
+/* ona_b200.h -- C ABI of the B200-native OptNetAlign scoring engine.
+ *
+ * Drop-in boundary for the reference's data-parallel hot path.  The reference
+ * (crclark/optnetaligncpp) has no FFI layer: its "interface" for this path is the
+ * C++ header pair Alignment.h + localSearch.h resolved at link time.  Every entry
+ * point below names the reference interface it replaces (file:line relative to the
+ * reference tree); INTEGRATION.md shows the replacement Alignment.cpp /
+ * localSearch.cpp translation units (optnetaligncpp_b200/host/) that implement the
+ * unchanged headers on top of this ABI, so steadystate.cpp / nsgaiimain.cpp /
+ * hillclimber.cpp link unchanged.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every buffer is caller-owned HOST memory unless
+ *     the parameter name ends in _dev (then it is a CUDA device pointer on the engine's
+ *     device); ints are 32-bit node ids (Network.h:11 "typedef int node"), scores fp64.
+ *   - every function returns ONA_OK or a negative error code; ona_last_error() returns a
+ *     thread-local message (the reference throws C++ exceptions -- LineReadException,
+ *     ArgError, std::out_of_range -- and nothing may throw across a C boundary; the C++
+ *     host shim turns non-zero codes back into std::runtime_error).
+ *   - there is NO CPU fallback: ona_engine_create fails if no CUDA device is usable.
+ *   - an engine is bound to one GPU and one CUDA stream (ona_set_stream); calls on one
+ *     engine are serialised by an internal mutex, so the reference's many host threads
+ *     (steadystate.cpp:132-303) may share it.
+ *   - population slots: the engine stores P individuals ("slots"); host Alignment objects
+ *     stay the source of truth between batched calls and are keyed by slot index.
+ */
+#ifndef ONA_B200_H
+#define ONA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONA_OK 0
+#define ONA_ERR_INVALID (-1) /* bad argument / malformed graph or permutation */
+#define ONA_ERR_CUDA (-2)    /* CUDA runtime failure (message has the CUDA error string) */
+#define ONA_ERR_STATE (-3)   /* call order problem (e.g. population not uploaded) */
+#define ONA_ERR_NOMEM (-4)
+
+/* objective ids == the reference's enum fitnessName (Network.h:31-32), same values */
+enum ona_objective {
+    ONA_ICS = 0, ONA_EC = 1, ONA_BITSCORE_SUM = 2, ONA_EVALS_SUM = 3, ONA_SIZE = 4,
+    ONA_GOC = 5, ONA_S3 = 6, ONA_S3_DENOM = 7, ONA_ICS_TIMES_EC = 8, ONA_S3_VARIANT = 9
+};
+#define ONA_MAX_OBJECTIVES 10
+
+/* BLASTDict / GOCDict (blastinfo.h:10, goc.h:12): either the dense row-major n1 x n2
+ * matrix the reference holds (pass the multi_array's data()), or its non-zeros as COO
+ * triples (later duplicates win, like the reference's assignment loop blastinfo.cpp:42).
+ * All-NULL = table absent (the reference's nullptr dict). */
+typedef struct ona_score_table {
+    const double* dense;
+    const int* rows;
+    const int* cols;
+    const double* vals;
+    long long nnz;
+} ona_score_table;
+
+/* Replaces: the immutable inputs an Alignment borrows -- const Network* net1/net2,
+ * const BLASTDict* bitscores, const GOCDict* gocs (Alignment.h:73-98) -- plus the
+ * fitnessNames vector every computeFitness/correctHillClimb call receives
+ * (argParsing.h:212-271 fixes its order).
+ *   rowptr/col : CSR of Network::adjList in adjList order (Network.cpp:89-92: a self-loop
+ *                is listed once).  Duplicate edge lines are rejected.
+ *   num_edges1 : net1->edges.size(), the EC / S3 denominator term (Alignment.cpp:536,541). */
+typedef struct ona_problem {
+    int n1, n2; /* |V(net1)| <= |V(net2)| (argParsing.h:207-210) */
+    long long num_edges1;
+    const int* rowptr1;
+    const int* col1;
+    const int* rowptr2;
+    const int* col2;
+    ona_score_table bitscores;
+    ona_score_table gocs;
+    const int* objectives; /* ona_objective values, in fitnessNames order */
+    int num_objectives;
+} ona_problem;
+
+typedef struct ona_engine ona_engine;
+
+/* ------------------------------------------------------------------ lifecycle */
+int ona_device_count(void);
+int ona_engine_create(int device, const ona_problem* problem, ona_engine** out);
+void ona_engine_destroy(ona_engine* e);
+const char* ona_last_error(void);
+/* run on an existing stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
+int ona_set_stream(ona_engine* e, void* cuda_stream);
+int ona_synchronize(ona_engine* e);
+/* pinned host memory for the host-buffer entry points (optional; any host memory works) */
+void* ona_host_alloc(long long bytes);
+void ona_host_free(void* p);
+/* number of engine kernels launched so far (bench.py's gpu_launches) */
+long long ona_kernel_launches(const ona_engine* e);
+/* global index of slot 0 (island offset); only keys the on-device proposal RNG */
+int ona_set_island_offset(ona_engine* e, long long first_global_individual);
+
+/* ----------------------------------------------------------------- population */
+/* Replaces: Alignment::aln / alnInv / alnMask state (Alignment.h:44-46).  aln is
+ * [count][n2] (a permutation of V2 per row; positions >= n1 are the dummy nodes of
+ * Alignment.cpp:25-34), mask is [count][n2] bytes or NULL for all-true (--total).
+ * alnInv is rebuilt on the device.  Counters are NOT touched: follow with
+ * ona_full_fitness(seed_mode != 0) or ona_pop_set_counters. */
+int ona_pop_resize(ona_engine* e, int num_slots);
+int ona_pop_upload(ona_engine* e, int first, int count, const int* aln, const unsigned char* mask);
+int ona_pop_download(ona_engine* e, int first, int count, int* aln, int* aln_inv,
+                     unsigned char* mask);
+/* Replaces: direct access to currConservedCount / currInducedCount / currBitscore /
+ * currGOC / fitness (Alignment.h:61,73,80,101,109).  Any output may be NULL. */
+int ona_pop_set_counters(ona_engine* e, int first, int count, const int* conserved,
+                         const int* induced, const double* bitscore, const double* goc);
+int ona_pop_get_counters(ona_engine* e, int first, int count, int* conserved, int* induced,
+                         double* bitscore, double* goc, double* size, double* fitness);
+
+/* --------------------------------------------------------------- full fitness */
+#define ONA_SEED_NONE 0    /* only report, leave the slots' cached counters alone */
+#define ONA_SEED_TRUE 1    /* cache the exact conserved count */
+#define ONA_SEED_REFCOMPAT 2 /* cache (int)(ics()*denom), the reference's truncated seed (H1) */
+#define ONA_SUM_SEQUENTIAL 16 /* OR into seed_mode: fp64 sums in the reference's index order
+                                 (bit-identical to sumBLAST/sumGOC) instead of a tree sum */
+/* Replaces, population-batched: the from-scratch scoring idiom at the tail of
+ * Alignment::shuf and the constructors (Alignment.cpp:437-446, 43-46, 129-137): sumBLAST
+ * (:701-710), sumGOC (:712-722), fastICSDenominator (:667-690), ics() (:604-661), then
+ * computeFitness (:559-602).  Outputs are [count] ([count][M] for fitness), any may be NULL:
+ * conserved_true = |mapped E1 /\ induced E2|, conserved_refseed = the reference's seed value. */
+int ona_full_fitness(ona_engine* e, int first, int count, int seed_mode, int* conserved_true,
+                     int* conserved_refseed, int* induced, double* bitscore, double* goc,
+                     double* size, double* fitness);
+/* same, nothing leaves the device (results stay in the slots / the device fitness matrix) */
+int ona_full_fitness_dev(ona_engine* e, int first, int count, int seed_mode);
+
+/* ---------------------------------------------------------------- swap deltas */
+/* Replaces, batched and state-preserving: Alignment::doSwap + computeFitness + the accept
+ * test of correctHillClimb (Alignment.cpp:491-520, 559-602; localSearch.cpp:32-47) and
+ * swapNormalizedDelta (localSearch.cpp:88-120) for K candidate swaps per individual, all
+ * evaluated against the slot's CURRENT state (which is not modified).
+ *   xy       [count][K][2] proposals (x,y): positions in V1 u dummies, x != y not required
+ *   obj      -1: accept iff no objective decreased (localSearch.cpp:36-41);
+ *            j>=0: accept iff objective j strictly increased (:43-47)
+ * outputs (any may be NULL), all [count][K] ([count][K][M] for fitness): the values the
+ * reference's Alignment holds right after doSwap+computeFitness: currConservedCount,
+ * currInducedCount, currBitscore, currGOC, fitness[]; improved = the accept decision;
+ * snd = swapNormalizedDelta's return value. */
+int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, int obj,
+                    int* conserved, int* induced, double* bitscore, double* goc,
+                    double* fitness, unsigned char* improved, double* snd);
+/* Proposals drawn on the device from a counter-based RNG keyed (seed, global individual,
+ * candidate index), supports x in U[0,n1), y in U[0,n2) \ {x} as localSearch.cpp:21-28.
+ * Results stay on the device; summary outputs (host, [count], may be NULL):
+ * num_improved = how many of the K candidates would be accepted, best_snd / best_xy =
+ * arg-max swapNormalizedDelta and its (x,y) (the steepestAscentHillClimb reduction,
+ * localSearch.cpp:136-147, over a random candidate subset). */
+int ona_swap_deltas_rng(ona_engine* e, int first, int count, int K, unsigned long long seed,
+                        int obj, int* num_improved, double* best_snd, int* best_xy);
+/* the proposals the device RNG generates, for host-side checking */
+int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long long seed,
+                      long long start_index, int* xy);
+
+/* ----------------------------------------------------------------- hill climb */
+/* Replaces: correctHillClimb (localSearch.cpp:18-55; decl localSearch.h:9-11), for `count`
+ * individuals at once, with the reference's exact sequential semantics per individual:
+ * proposals are consumed in order, each is applied, scored, and undone unless accepted;
+ * integer counters, accept decisions and the fp64 accumulators (including the not-quite-
+ * inverse undo) equal what the reference produces for the same proposals.
+ *   xy        [count][iters][2] proposals, or NULL to draw them on the device (seed)
+ *   objs      [count] objective index per individual (-1 = all, as above), or NULL = all -1
+ *   accepted  [count][iters] bytes out, or NULL
+ *   num_accepted [count] out, or NULL
+ * Precondition (as the reference, steadystate.cpp:232): the slots' counters are valid. */
+int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const int* xy,
+                   unsigned long long seed, const int* objs, unsigned char* accepted,
+                   long long* num_accepted);
+
+/* Replaces: a run of unconditional Alignment::doSwap calls -- the swap part of
+ * Alignment::mutate (Alignment.cpp:456-465) and of UPMX crossover (:197-252) given a
+ * host-generated ordered swap list.  xy is [count][nswaps][2]; entries with x < 0 are
+ * skipped (ragged lists).  Counters/accumulators are updated incrementally like doSwap. */
+int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* xy);
+
+/* -------------------------------------------------------------- device access */
+/* copy the [count][M] objective rows of slots first..first+count into a device buffer
+ * (e.g. a torch tensor's data_ptr) on the engine's stream -- the send buffer of the
+ * per-generation all-gather that feeds the host NSGA-II sort (nsga-ii.cpp:14-118). */
+int ona_export_fitness_dev(ona_engine* e, int first, int count, double* dst_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONA_B200_H */

@@ -1,0 +1,819 @@
+// Host side of the engine: the C ABI of include/ona_b200.h on top of the kernels in
+// ona_kernels.cuh.  No CPU fallback: every entry point drives the GPU.
+#include "../../include/ona_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "ona_kernels.cuh"
+
+using namespace ona;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(ONA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+template <typename V>
+struct DevBuf {  // grow-only device scratch
+    V* p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(V));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct ona_engine {
+    int device = 0;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long long launches = 0;
+    long long island_offset = 0;
+
+    DevGraph g{};
+    DevTable S{}, G{};
+    DevObjectives ob{};
+    bool small_ids = false;  // n2 < 32768: uint16 shared-memory state
+    int group = 8;           // lanes per candidate in phase 1
+    int sm_count = 148;
+    size_t smem_optin = 0;
+
+    std::vector<void*> owned;  // immutable device allocations (graph, tables)
+
+    int P = 0;
+    DevPop pop{};
+
+    DevBuf<int> t_i0, t_i1, t_i2, t_xy;
+    DevBuf<double> t_d0, t_d1, t_d2, t_d3, t_d4, t_seq;
+    DevBuf<unsigned char> t_u0, t_mask;
+    DevBuf<long long> t_l0;
+    int* d_flag = nullptr;
+};
+
+namespace {
+
+template <typename V>
+int upload(ona_engine* e, const std::vector<V>& h, const V** out) {
+    V* d = nullptr;
+    CU(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(V)));
+    e->owned.push_back(d);
+    if (!h.empty()) CU(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *out = d;
+    return ONA_OK;
+}
+
+int check_csr(const char* what, int n, const int* rp, const int* col, int ncols) {
+    if (!rp || !col) return fail(ONA_ERR_INVALID, std::string(what) + ": null CSR");
+    if (rp[0] != 0) return fail(ONA_ERR_INVALID, std::string(what) + ": rowptr[0] != 0");
+    std::vector<int> row;
+    for (int u = 0; u < n; ++u) {
+        if (rp[u + 1] < rp[u]) return fail(ONA_ERR_INVALID, std::string(what) + ": rowptr not monotone");
+        row.assign(col + rp[u], col + rp[u + 1]);
+        std::sort(row.begin(), row.end());
+        for (size_t k = 0; k < row.size(); ++k) {
+            if (row[k] < 0 || row[k] >= ncols)
+                return fail(ONA_ERR_INVALID, std::string(what) + ": column id out of range");
+            if (k && row[k] == row[k - 1])
+                return fail(ONA_ERR_INVALID, std::string(what) +
+                                                 ": duplicate edge (the reference's adjList-based "
+                                                 "counters and set-based ics() disagree on such input)");
+        }
+    }
+    return ONA_OK;
+}
+
+// unique undirected edges (u <= v) of a symmetric adjList CSR
+void unique_edges(int n, const int* rp, const int* col, std::vector<int>& eu, std::vector<int>& ev) {
+    for (int u = 0; u < n; ++u)
+        for (int k = rp[u]; k < rp[u + 1]; ++k)
+            if (col[k] >= u) {
+                eu.push_back(u);
+                ev.push_back(col[k]);
+            }
+}
+
+// BLASTDict/GOCDict -> device table.  Sparse tables (density < 1/16) become an
+// open-addressing hash at load factor <= 0.25; denser ones a dense fp64 matrix.
+int build_table(ona_engine* e, const ona_score_table& t, int n1, int n2, DevTable* out) {
+    out->kind = 0;
+    out->n2 = n2;
+    if (!t.dense && !(t.rows && t.cols && t.vals)) return ONA_OK;
+    const size_t cells = (size_t)n1 * (size_t)n2;
+    std::vector<unsigned long long> keys;
+    std::vector<double> vals;
+    if (t.dense) {
+        for (size_t i = 0; i < cells; ++i)
+            if (t.dense[i] != 0.0) {
+                keys.push_back(i);
+                vals.push_back(t.dense[i]);
+            }
+    } else {
+        for (long long k = 0; k < t.nnz; ++k) {
+            if (t.rows[k] < 0 || t.rows[k] >= n1 || t.cols[k] < 0 || t.cols[k] >= n2)
+                return fail(ONA_ERR_INVALID, "score table: index out of range");
+        }
+    }
+    const size_t nnz = t.dense ? keys.size() : (size_t)t.nnz;
+    if (nnz * 16 >= cells) {  // dense on the device
+        std::vector<double> h;
+        const double* src = t.dense;
+        if (!src) {
+            h.assign(cells, 0.0);
+            for (long long k = 0; k < t.nnz; ++k) h[(size_t)t.rows[k] * n2 + t.cols[k]] = t.vals[k];
+            src = h.data();
+        }
+        double* d = nullptr;
+        CU(cudaMalloc(&d, cells * sizeof(double)));
+        e->owned.push_back(d);
+        CU(cudaMemcpy(d, src, cells * sizeof(double), cudaMemcpyHostToDevice));
+        out->kind = 1;
+        out->dense = d;
+        return ONA_OK;
+    }
+    int lg = 4;
+    while (((size_t)1 << lg) < 4 * std::max<size_t>(nnz, 1)) ++lg;
+    const size_t cap = (size_t)1 << lg;
+    std::vector<ulonglong2> slots(cap);
+    for (auto& s : slots) {
+        s.x = kEmptyKey;
+        s.y = 0;
+    }
+    auto put = [&](unsigned long long key, double v) {
+        unsigned long long h = (key * 0x9E3779B97F4A7C15ull) >> (64 - lg);
+        unsigned long long bits;
+        std::memcpy(&bits, &v, 8);
+        for (;;) {
+            if (slots[h].x == key || slots[h].x == kEmptyKey) {  // later duplicates win
+                slots[h].x = key;
+                slots[h].y = bits;
+                return;
+            }
+            h = (h + 1) & (cap - 1);
+        }
+    };
+    if (t.dense)
+        for (size_t k = 0; k < keys.size(); ++k) put(keys[k], vals[k]);
+    else
+        for (long long k = 0; k < t.nnz; ++k)
+            put((unsigned long long)t.rows[k] * (unsigned long long)n2 + (unsigned long long)t.cols[k], t.vals[k]);
+    const ulonglong2* d = nullptr;
+    int rc = upload<ulonglong2>(e, slots, &d);
+    if (rc) return rc;
+    out->kind = 2;
+    out->slots = d;
+    out->cap_mask = cap - 1;
+    out->shift = 64 - lg;
+    return ONA_OK;
+}
+
+size_t state_smem(const ona_engine* e) {
+    return (size_t)2 * (size_t)e->pop.n2p * (e->small_ids ? 2 : 4);
+}
+
+int check_range(ona_engine* e, int first, int count) {
+    if (!e) return fail(ONA_ERR_INVALID, "null engine");
+    if (count < 0 || first < 0 || first + count > e->P)
+        return fail(ONA_ERR_INVALID, "slot range outside the population (ona_pop_resize first)");
+    return ONA_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return ONA_OK;
+}
+
+template <typename T>
+int launch_full(ona_engine* e, int first, int count, int seed_mode, int sequential, FullOut out) {
+    const size_t smem = state_smem(e);
+    int rc = set_smem(k_full_fitness<T>, smem);
+    if (rc) return rc;
+    double* seq = nullptr;
+    if (sequential) {
+        CU(e->t_seq.need((size_t)count * 2 * e->g.n1));
+        seq = e->t_seq.p;
+    }
+    k_full_fitness<T><<<count, 512, smem, e->stream>>>(e->g, e->S, e->G, e->ob, e->pop, first,
+                                                      seed_mode, sequential, seq, out);
+    e->launches++;
+    CU(cudaGetLastError());
+    return ONA_OK;
+}
+
+template <typename T, int G>
+int launch_deltas_tg(ona_engine* e, int first, int count, int K, const int* xy_dev,
+                     unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
+    const size_t smem = state_smem(e);
+    int rc = set_smem(k_swap_deltas<T, G>, smem);
+    if (rc) return rc;
+    dim3 grid(chunks, count);
+    k_swap_deltas<T, G><<<grid, 256, smem, e->stream>>>(e->g, e->S, e->G, e->ob, e->pop, first, K,
+                                                       xy_dev, seed, e->island_offset, obj, out, sum);
+    e->launches++;
+    CU(cudaGetLastError());
+    return ONA_OK;
+}
+
+template <typename T>
+int launch_deltas_t(ona_engine* e, int first, int count, int K, const int* xy_dev,
+                    unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
+    switch (e->group) {
+        case 1: return launch_deltas_tg<T, 1>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+        case 4: return launch_deltas_tg<T, 4>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+        case 16: return launch_deltas_tg<T, 16>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+        case 32: return launch_deltas_tg<T, 32>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+        default: return launch_deltas_tg<T, 8>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+    }
+}
+
+// chunks per individual so that the grid is a whole number of waves of resident CTAs
+int pick_chunks(const ona_engine* e, int count, int K) {
+    const size_t smem = state_smem(e) + 1024;
+    int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, (e->smem_optin ? 233472 : 101376) / smem));
+    const int resident = e->sm_count * per_sm;
+    int chunks = std::max(1, (2 * resident + count - 1) / count);
+    const int max_chunks = std::max(1, (K + 255) / 256);  // at least one pass of 256 candidates per CTA
+    chunks = std::min(chunks, max_chunks);
+    return chunks;
+}
+
+int launch_deltas(ona_engine* e, int first, int count, int K, const int* xy_dev,
+                  unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
+    if (e->small_ids)
+        return launch_deltas_t<uint16_t>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+    return launch_deltas_t<uint32_t>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+}
+
+template <typename T, int G>
+int launch_climb_tg(ona_engine* e, int first, int count, long long iters, const int* xy_dev,
+                    unsigned long long seed, const int* objs_dev, int force_obj,
+                    unsigned char* acc_dev, long long* nacc_dev) {
+    const size_t smem = state_smem(e);
+    int rc = set_smem(k_hill_climb<T, G>, smem);
+    if (rc) return rc;
+    k_hill_climb<T, G><<<count, kRound * G, smem, e->stream>>>(e->g, e->S, e->G, e->ob, e->pop, first,
+                                                              iters, xy_dev, seed, e->island_offset,
+                                                              objs_dev, force_obj, acc_dev, nacc_dev);
+    e->launches++;
+    CU(cudaGetLastError());
+    return ONA_OK;
+}
+
+int launch_climb(ona_engine* e, int first, int count, long long iters, const int* xy_dev,
+                 unsigned long long seed, const int* objs_dev, int force_obj,
+                 unsigned char* acc_dev, long long* nacc_dev) {
+    const int G = (e->group == 4 || e->group == 16) ? e->group : 8;
+    if (e->small_ids) {
+        if (G == 4) return launch_climb_tg<uint16_t, 4>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
+        if (G == 16) return launch_climb_tg<uint16_t, 16>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
+        return launch_climb_tg<uint16_t, 8>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
+    }
+    if (G == 4) return launch_climb_tg<uint32_t, 4>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
+    if (G == 16) return launch_climb_tg<uint32_t, 16>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
+    return launch_climb_tg<uint32_t, 8>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
+}
+
+template <typename V>
+int d2h(ona_engine* e, V* host, const V* dev, size_t n) {
+    if (!host || !n) return ONA_OK;
+    CU(cudaMemcpyAsync(host, dev, n * sizeof(V), cudaMemcpyDeviceToHost, e->stream));
+    return ONA_OK;
+}
+template <typename V>
+int h2d(ona_engine* e, V* dev, const V* host, size_t n) {
+    if (!host || !n) return ONA_OK;
+    CU(cudaMemcpyAsync(dev, host, n * sizeof(V), cudaMemcpyHostToDevice, e->stream));
+    return ONA_OK;
+}
+
+void free_pop(ona_engine* e) {
+    cudaFree(e->pop.aln); cudaFree(e->pop.inv); cudaFree(e->pop.cons); cudaFree(e->pop.ind);
+    cudaFree(e->pop.size); cudaFree(e->pop.bits); cudaFree(e->pop.goc); cudaFree(e->pop.fit);
+    const int n2p = e->pop.n2p;
+    e->pop = DevPop{};
+    e->pop.n2p = n2p;
+    e->P = 0;
+}
+
+}  // namespace
+
+#define LOCK(e) std::lock_guard<std::mutex> _lk((e)->mu); cudaSetDevice((e)->device)
+#define TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+extern "C" {
+
+const char* ona_last_error(void) { return g_err.c_str(); }
+
+int ona_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void* ona_host_alloc(long long bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)std::max<long long>(bytes, 1), cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void ona_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
+    if (!pr || !out) return fail(ONA_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(ONA_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                      cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(ONA_ERR_INVALID, "device index out of range");
+    if (pr->n1 <= 0 || pr->n2 <= 1 || pr->n1 > pr->n2)
+        return fail(ONA_ERR_INVALID, "need 0 < n1 <= n2 (argParsing.h:207-210) and n2 > 1");
+    if (pr->n2 >= (1 << 30)) return fail(ONA_ERR_INVALID, "n2 too large");
+    if (pr->num_objectives <= 0 || pr->num_objectives > ONA_MAX_OBJECTIVES || !pr->objectives)
+        return fail(ONA_ERR_INVALID, "need 1..10 objectives");
+    for (int j = 0; j < pr->num_objectives; ++j)
+        if (pr->objectives[j] < 0 || pr->objectives[j] > 9) return fail(ONA_ERR_INVALID, "unknown objective id");
+    TRY(check_csr("net1", pr->n1, pr->rowptr1, pr->col1, pr->n1));
+    TRY(check_csr("net2", pr->n2, pr->rowptr2, pr->col2, pr->n2));
+
+    CU(cudaSetDevice(device));
+    ona_engine* e = new ona_engine();
+    e->device = device;
+    auto bail = [&](int rc) {
+        ona_engine_destroy(e);
+        return rc;
+    };
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(ONA_ERR_CUDA, "cudaStreamCreate failed"));
+    e->own_stream = true;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(ONA_ERR_CUDA, "cudaGetDeviceProperties"));
+    e->sm_count = prop.multiProcessorCount;
+    e->smem_optin = prop.sharedMemPerBlockOptin;
+
+    DevGraph& g = e->g;
+    g.n1 = pr->n1;
+    g.n2 = pr->n2;
+    g.E1 = (unsigned long long)pr->num_edges1;
+    const int a1 = pr->rowptr1[pr->n1], a2 = pr->rowptr2[pr->n2];
+    int rc;
+    if ((rc = upload<int>(e, std::vector<int>(pr->rowptr1, pr->rowptr1 + pr->n1 + 1), &g.rp1))) return bail(rc);
+    if ((rc = upload<int>(e, std::vector<int>(pr->col1, pr->col1 + a1), &g.col1))) return bail(rc);
+    if ((rc = upload<int>(e, std::vector<int>(pr->rowptr2, pr->rowptr2 + pr->n2 + 1), &g.rp2))) return bail(rc);
+    if ((rc = upload<int>(e, std::vector<int>(pr->col2, pr->col2 + a2), &g.col2))) return bail(rc);
+    // net2 adjacency bit matrix, rows padded to 128 B (32 words)
+    g.W = ((pr->n2 + 31) / 32 + 31) / 32 * 32;
+    {
+        std::vector<uint32_t> bits((size_t)pr->n2 * g.W, 0u);
+        for (int u = 0; u < pr->n2; ++u)
+            for (int k = pr->rowptr2[u]; k < pr->rowptr2[u + 1]; ++k) {
+                const int v = pr->col2[k];
+                bits[(size_t)u * g.W + (v >> 5)] |= 1u << (v & 31);
+                // adjList is symmetric by construction (Network.cpp:89-92); keep the matrix
+                // symmetric even if the caller's CSR is not
+                bits[(size_t)v * g.W + (u >> 5)] |= 1u << (u & 31);
+            }
+        if ((rc = upload<uint32_t>(e, bits, &g.adj2))) return bail(rc);
+    }
+    {
+        std::vector<int> eu, ev;
+        unique_edges(pr->n1, pr->rowptr1, pr->col1, eu, ev);
+        g.ne1 = (int)eu.size();
+        if ((rc = upload<int>(e, eu, &g.eu1))) return bail(rc);
+        if ((rc = upload<int>(e, ev, &g.ev1))) return bail(rc);
+        eu.clear();
+        ev.clear();
+        unique_edges(pr->n2, pr->rowptr2, pr->col2, eu, ev);
+        g.ne2 = (int)eu.size();
+        if ((rc = upload<int>(e, eu, &g.eu2))) return bail(rc);
+        if ((rc = upload<int>(e, ev, &g.ev2))) return bail(rc);
+    }
+    if ((rc = build_table(e, pr->bitscores, pr->n1, pr->n2, &e->S))) return bail(rc);
+    if ((rc = build_table(e, pr->gocs, pr->n1, pr->n2, &e->G))) return bail(rc);
+    e->ob.M = pr->num_objectives;
+    for (int j = 0; j < pr->num_objectives; ++j) e->ob.names[j] = pr->objectives[j];
+
+    e->small_ids = pr->n2 < 32768;
+    e->pop.n2p = (pr->n2 + 3) / 4 * 4;
+    if (state_smem(e) + 2048 > e->smem_optin)
+        return bail(fail(ONA_ERR_INVALID, "n2 too large for the shared-memory resident state"));
+    if (const char* gs = getenv("ONA_GROUP")) {
+        const int v = atoi(gs);
+        if (v == 1 || v == 4 || v == 8 || v == 16 || v == 32) e->group = v;
+    }
+    if (cudaMalloc(&e->d_flag, sizeof(int)) != cudaSuccess) return bail(fail(ONA_ERR_CUDA, "cudaMalloc"));
+    *out = e;
+    return ONA_OK;
+}
+
+void ona_engine_destroy(ona_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void* p : e->owned) cudaFree(p);
+    free_pop(e);
+    e->t_i0.release(); e->t_i1.release(); e->t_i2.release(); e->t_xy.release();
+    e->t_d0.release(); e->t_d1.release(); e->t_d2.release(); e->t_d3.release(); e->t_d4.release();
+    e->t_seq.release(); e->t_u0.release(); e->t_mask.release(); e->t_l0.release();
+    if (e->d_flag) cudaFree(e->d_flag);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int ona_set_stream(ona_engine* e, void* s) {
+    if (!e) return fail(ONA_ERR_INVALID, "null engine");
+    LOCK(e);
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    if (s) {
+        e->stream = (cudaStream_t)s;
+        e->own_stream = false;
+    } else {
+        CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        e->own_stream = true;
+    }
+    return ONA_OK;
+}
+
+int ona_synchronize(ona_engine* e) {
+    if (!e) return fail(ONA_ERR_INVALID, "null engine");
+    LOCK(e);
+    CU(cudaStreamSynchronize(e->stream));
+    return ONA_OK;
+}
+
+long long ona_kernel_launches(const ona_engine* e) { return e ? e->launches : 0; }
+
+int ona_set_island_offset(ona_engine* e, long long off) {
+    if (!e) return fail(ONA_ERR_INVALID, "null engine");
+    e->island_offset = off;
+    return ONA_OK;
+}
+
+int ona_pop_resize(ona_engine* e, int P) {
+    if (!e || P < 0) return fail(ONA_ERR_INVALID, "bad population size");
+    LOCK(e);
+    CU(cudaStreamSynchronize(e->stream));
+    if (P == e->P) return ONA_OK;
+    free_pop(e);
+    if (P == 0) return ONA_OK;
+    const size_t row = (size_t)e->pop.n2p;
+    CU(cudaMalloc(&e->pop.aln, (size_t)P * row * 4));
+    CU(cudaMalloc(&e->pop.inv, (size_t)P * row * 4));
+    CU(cudaMalloc(&e->pop.cons, (size_t)P * 4));
+    CU(cudaMalloc(&e->pop.ind, (size_t)P * 4));
+    CU(cudaMalloc(&e->pop.size, (size_t)P * 4));
+    CU(cudaMalloc(&e->pop.bits, (size_t)P * 8));
+    CU(cudaMalloc(&e->pop.goc, (size_t)P * 8));
+    CU(cudaMalloc(&e->pop.fit, (size_t)P * e->ob.M * 8));
+    CU(cudaMemsetAsync(e->pop.aln, 0, (size_t)P * row * 4, e->stream));
+    CU(cudaMemsetAsync(e->pop.inv, 0, (size_t)P * row * 4, e->stream));
+    CU(cudaMemsetAsync(e->pop.cons, 0, (size_t)P * 4, e->stream));
+    CU(cudaMemsetAsync(e->pop.ind, 0, (size_t)P * 4, e->stream));
+    CU(cudaMemsetAsync(e->pop.size, 0, (size_t)P * 4, e->stream));
+    CU(cudaMemsetAsync(e->pop.bits, 0, (size_t)P * 8, e->stream));
+    CU(cudaMemsetAsync(e->pop.goc, 0, (size_t)P * 8, e->stream));
+    CU(cudaMemsetAsync(e->pop.fit, 0, (size_t)P * e->ob.M * 8, e->stream));
+    e->P = P;
+    return ONA_OK;
+}
+
+int ona_pop_upload(ona_engine* e, int first, int count, const int* aln, const unsigned char* mask) {
+    TRY(check_range(e, first, count));
+    if (!aln) return fail(ONA_ERR_INVALID, "null aln");
+    if (count == 0) return ONA_OK;
+    LOCK(e);
+    const int n2 = e->g.n2;
+    const size_t n = (size_t)count * n2;
+    for (size_t i = 0; i < n; ++i)
+        if ((unsigned)aln[i] >= (unsigned)n2) return fail(ONA_ERR_INVALID, "aln entry outside [0,n2)");
+    CU(e->t_xy.need(n));
+    TRY(h2d(e, e->t_xy.p, aln, n));
+    unsigned char* dmask = nullptr;
+    if (mask) {
+        CU(e->t_mask.need(n));
+        TRY(h2d(e, e->t_mask.p, mask, n));
+        dmask = e->t_mask.p;
+    }
+    CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
+    dim3 grid((e->pop.n2p + 255) / 256, count);
+    k_pack_state<<<grid, 256, 0, e->stream>>>(e->pop, first, count, n2, e->t_xy.p, dmask);
+    k_check_state<<<grid, 256, 0, e->stream>>>(e->pop, first, count, n2, e->d_flag);
+    k_recount_size<<<count, 256, 0, e->stream>>>(e->g, e->pop, first, count);
+    e->launches += 3;
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaGetLastError());
+    if (bad) return fail(ONA_ERR_INVALID, "aln is not a permutation of V2");
+    return ONA_OK;
+}
+
+int ona_pop_download(ona_engine* e, int first, int count, int* aln, int* aln_inv, unsigned char* mask) {
+    TRY(check_range(e, first, count));
+    if (count == 0) return ONA_OK;
+    LOCK(e);
+    const int n2 = e->g.n2;
+    const size_t n = (size_t)count * n2;
+    CU(e->t_xy.need(n));
+    CU(e->t_i0.need(n));
+    CU(e->t_mask.need(n));
+    dim3 grid((n2 + 255) / 256, count);
+    k_unpack_state<<<grid, 256, 0, e->stream>>>(e->pop, first, count, n2, e->t_xy.p, e->t_i0.p, e->t_mask.p);
+    e->launches++;
+    CU(cudaGetLastError());
+    TRY(d2h(e, aln, e->t_xy.p, n));
+    TRY(d2h(e, aln_inv, e->t_i0.p, n));
+    TRY(d2h(e, mask, e->t_mask.p, n));
+    CU(cudaStreamSynchronize(e->stream));
+    return ONA_OK;
+}
+
+int ona_pop_set_counters(ona_engine* e, int first, int count, const int* cons, const int* ind,
+                         const double* bits, const double* goc) {
+    TRY(check_range(e, first, count));
+    if (count == 0) return ONA_OK;
+    LOCK(e);
+    TRY(h2d(e, e->pop.cons + first, cons, (size_t)count));
+    TRY(h2d(e, e->pop.ind + first, ind, (size_t)count));
+    TRY(h2d(e, e->pop.bits + first, bits, (size_t)count));
+    TRY(h2d(e, e->pop.goc + first, goc, (size_t)count));
+    k_refresh_fitness<<<(count + 127) / 128, 128, 0, e->stream>>>(e->g, e->ob, e->pop, first, count);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    return ONA_OK;
+}
+
+int ona_pop_get_counters(ona_engine* e, int first, int count, int* cons, int* ind, double* bits,
+                         double* goc, double* size, double* fitness) {
+    TRY(check_range(e, first, count));
+    if (count == 0) return ONA_OK;
+    LOCK(e);
+    TRY(d2h(e, cons, e->pop.cons + first, (size_t)count));
+    TRY(d2h(e, ind, e->pop.ind + first, (size_t)count));
+    TRY(d2h(e, bits, e->pop.bits + first, (size_t)count));
+    TRY(d2h(e, goc, e->pop.goc + first, (size_t)count));
+    TRY(d2h(e, fitness, e->pop.fit + (size_t)first * e->ob.M, (size_t)count * e->ob.M));
+    std::vector<int> sz;
+    if (size) {
+        sz.resize(count);
+        TRY(d2h(e, sz.data(), e->pop.size + first, (size_t)count));
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    if (size)
+        for (int i = 0; i < count; ++i) size[i] = (double)sz[i];
+    return ONA_OK;
+}
+
+static int full_fitness_impl(ona_engine* e, int first, int count, int seed_mode, FullOut out) {
+    const int sequential = (seed_mode & ONA_SUM_SEQUENTIAL) ? 1 : 0;
+    const int mode = seed_mode & 3;
+    if (mode > 2) return fail(ONA_ERR_INVALID, "bad seed_mode");
+    if (e->small_ids) return launch_full<uint16_t>(e, first, count, mode, sequential, out);
+    return launch_full<uint32_t>(e, first, count, mode, sequential, out);
+}
+
+int ona_full_fitness_dev(ona_engine* e, int first, int count, int seed_mode) {
+    TRY(check_range(e, first, count));
+    if (count == 0) return ONA_OK;
+    LOCK(e);
+    FullOut out{};
+    return full_fitness_impl(e, first, count, seed_mode, out);
+}
+
+int ona_full_fitness(ona_engine* e, int first, int count, int seed_mode, int* cons_true,
+                     int* cons_ref, int* ind, double* bits, double* goc, double* size,
+                     double* fitness) {
+    TRY(check_range(e, first, count));
+    if (count == 0) return ONA_OK;
+    LOCK(e);
+    const size_t n = (size_t)count;
+    CU(e->t_i0.need(n)); CU(e->t_i1.need(n)); CU(e->t_i2.need(n));
+    CU(e->t_d0.need(n)); CU(e->t_d1.need(n)); CU(e->t_d2.need(n)); CU(e->t_d3.need(n * e->ob.M));
+    FullOut out{e->t_i0.p, e->t_i1.p, e->t_i2.p, e->t_d0.p, e->t_d1.p, e->t_d2.p, e->t_d3.p};
+    TRY(full_fitness_impl(e, first, count, seed_mode, out));
+    TRY(d2h(e, cons_true, e->t_i0.p, n));
+    TRY(d2h(e, cons_ref, e->t_i1.p, n));
+    TRY(d2h(e, ind, e->t_i2.p, n));
+    TRY(d2h(e, bits, e->t_d0.p, n));
+    TRY(d2h(e, goc, e->t_d1.p, n));
+    TRY(d2h(e, size, e->t_d2.p, n));
+    TRY(d2h(e, fitness, e->t_d3.p, n * e->ob.M));
+    CU(cudaStreamSynchronize(e->stream));
+    return ONA_OK;
+}
+
+int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, int obj, int* cons,
+                    int* ind, double* bits, double* goc, double* fitness, unsigned char* improved,
+                    double* snd) {
+    TRY(check_range(e, first, count));
+    if (!xy || K < 0) return fail(ONA_ERR_INVALID, "null proposals");
+    if (obj < -1 || obj >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
+    if (count == 0 || K == 0) return ONA_OK;
+    const size_t n = (size_t)count * K;
+    const int n2 = e->g.n2;
+    for (size_t i = 0; i < 2 * n; ++i)
+        if ((unsigned)xy[i] >= (unsigned)n2) return fail(ONA_ERR_INVALID, "proposal outside [0,n2)");
+    LOCK(e);
+    CU(e->t_xy.need(2 * n));
+    TRY(h2d(e, e->t_xy.p, xy, 2 * n));
+    DevDeltaOut out{};
+    if (cons) { CU(e->t_i0.need(n)); out.cons = e->t_i0.p; }
+    if (ind) { CU(e->t_i1.need(n)); out.ind = e->t_i1.p; }
+    if (bits) { CU(e->t_d0.need(n)); out.bits = e->t_d0.p; }
+    if (goc) { CU(e->t_d1.need(n)); out.goc = e->t_d1.p; }
+    if (fitness) { CU(e->t_d3.need(n * e->ob.M)); out.fit = e->t_d3.p; }
+    if (improved) { CU(e->t_u0.need(n)); out.improved = e->t_u0.p; }
+    if (snd) { CU(e->t_d2.need(n)); out.snd = e->t_d2.p; }
+    DeltaSummary sum{};
+    TRY(launch_deltas(e, first, count, K, e->t_xy.p, 0ull, obj, out, sum, pick_chunks(e, count, K)));
+    TRY(d2h(e, cons, out.cons, n));
+    TRY(d2h(e, ind, out.ind, n));
+    TRY(d2h(e, bits, out.bits, n));
+    TRY(d2h(e, goc, out.goc, n));
+    TRY(d2h(e, fitness, out.fit, n * e->ob.M));
+    TRY(d2h(e, improved, out.improved, n));
+    TRY(d2h(e, snd, out.snd, n));
+    CU(cudaStreamSynchronize(e->stream));
+    return ONA_OK;
+}
+
+int ona_swap_deltas_rng(ona_engine* e, int first, int count, int K, unsigned long long seed, int obj,
+                        int* num_improved, double* best_snd, int* best_xy) {
+    TRY(check_range(e, first, count));
+    if (K < 0) return fail(ONA_ERR_INVALID, "K < 0");
+    if (obj < -1 || obj >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
+    if (count == 0 || K == 0) return ONA_OK;
+    LOCK(e);
+    const int chunks = pick_chunks(e, count, K);
+    DevDeltaOut out{};
+    DeltaSummary sum{};
+    CU(e->t_i2.need((size_t)count));
+    CU(cudaMemsetAsync(e->t_i2.p, 0, (size_t)count * 4, e->stream));
+    sum.num_improved = e->t_i2.p;
+    const bool want_best = best_snd || best_xy;
+    if (want_best) {
+        CU(e->t_d4.need((size_t)count * chunks));
+        CU(e->t_l0.need((size_t)count * chunks));
+        sum.block_best = e->t_d4.p;
+        sum.block_arg = e->t_l0.p;
+    }
+    TRY(launch_deltas(e, first, count, K, nullptr, seed, obj, out, sum, chunks));
+    if (!num_improved && !want_best) return ONA_OK;  // fully asynchronous
+    TRY(d2h(e, num_improved, e->t_i2.p, (size_t)count));
+    std::vector<double> bv;
+    std::vector<long long> bi;
+    if (want_best) {
+        bv.resize((size_t)count * chunks);
+        bi.resize((size_t)count * chunks);
+        TRY(d2h(e, bv.data(), e->t_d4.p, bv.size()));
+        TRY(d2h(e, bi.data(), e->t_l0.p, bi.size()));
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    if (want_best) {
+        for (int p = 0; p < count; ++p) {
+            double v = -2.0;
+            long long idx = -1;
+            for (int c = 0; c < chunks; ++c) {
+                const double ov = bv[(size_t)p * chunks + c];
+                const long long oi = bi[(size_t)p * chunks + c];
+                if (oi >= 0 && (idx < 0 || ov > v)) { v = ov; idx = oi; }
+            }
+            if (best_snd) best_snd[p] = v;
+            if (best_xy) {
+                int x = -1, y = -1;
+                if (idx >= 0)
+                    rng_proposal(rng_individual_key(seed, (unsigned long long)(e->island_offset + first + p)),
+                                 (unsigned long long)idx, e->g.n1, e->g.n2, x, y);
+                best_xy[2 * p] = x;
+                best_xy[2 * p + 1] = y;
+            }
+        }
+    }
+    return ONA_OK;
+}
+
+int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long long seed,
+                      long long start, int* xy) {
+    TRY(check_range(e, first, count));
+    if (!xy || K < 0) return fail(ONA_ERR_INVALID, "null output");
+    if (count == 0 || K == 0) return ONA_OK;
+    LOCK(e);
+    const size_t n = (size_t)count * K;
+    CU(e->t_xy.need(2 * n));
+    k_rng_proposals<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->g.n1, e->g.n2, count, K, seed,
+                                                                       e->island_offset, first, start, e->t_xy.p);
+    e->launches++;
+    CU(cudaGetLastError());
+    TRY(d2h(e, xy, e->t_xy.p, 2 * n));
+    CU(cudaStreamSynchronize(e->stream));
+    return ONA_OK;
+}
+
+int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const int* xy,
+                   unsigned long long seed, const int* objs, unsigned char* accepted,
+                   long long* num_accepted) {
+    TRY(check_range(e, first, count));
+    if (iters < 0) return fail(ONA_ERR_INVALID, "iters < 0");
+    if (count == 0 || iters == 0) {
+        if (num_accepted) std::fill(num_accepted, num_accepted + count, 0ll);
+        return ONA_OK;
+    }
+    if (objs)
+        for (int i = 0; i < count; ++i)
+            if (objs[i] < -1 || objs[i] >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
+    const size_t n = (size_t)count * (size_t)iters;
+    const int n2 = e->g.n2;
+    if (xy)
+        for (size_t i = 0; i < 2 * n; ++i)
+            if ((unsigned)xy[i] >= (unsigned)n2) return fail(ONA_ERR_INVALID, "proposal outside [0,n2)");
+    LOCK(e);
+    const int* xy_dev = nullptr;
+    if (xy) {
+        CU(e->t_xy.need(2 * n));
+        TRY(h2d(e, e->t_xy.p, xy, 2 * n));
+        xy_dev = e->t_xy.p;
+    }
+    const int* objs_dev = nullptr;
+    if (objs) {
+        CU(e->t_i0.need((size_t)count));
+        TRY(h2d(e, e->t_i0.p, objs, (size_t)count));
+        objs_dev = e->t_i0.p;
+    }
+    unsigned char* acc_dev = nullptr;
+    if (accepted) {
+        CU(e->t_u0.need(n));
+        acc_dev = e->t_u0.p;
+    }
+    CU(e->t_l0.need((size_t)count));
+    TRY(launch_climb(e, first, count, iters, xy_dev, seed, objs_dev, -3, acc_dev, e->t_l0.p));
+    TRY(d2h(e, accepted, acc_dev, n));
+    TRY(d2h(e, num_accepted, e->t_l0.p, (size_t)count));
+    CU(cudaStreamSynchronize(e->stream));
+    return ONA_OK;
+}
+
+int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* xy) {
+    TRY(check_range(e, first, count));
+    if (!xy || nswaps < 0) return fail(ONA_ERR_INVALID, "null swap list");
+    if (count == 0 || nswaps == 0) return ONA_OK;
+    const size_t n = (size_t)count * nswaps;
+    const int n2 = e->g.n2;
+    for (size_t i = 0; i < n; ++i) {
+        if (xy[2 * i] < 0) continue;
+        if (xy[2 * i] >= n2 || (unsigned)xy[2 * i + 1] >= (unsigned)n2)
+            return fail(ONA_ERR_INVALID, "swap outside [0,n2)");
+    }
+    LOCK(e);
+    CU(e->t_xy.need(2 * n));
+    TRY(h2d(e, e->t_xy.p, xy, 2 * n));
+    TRY(launch_climb(e, first, count, nswaps, e->t_xy.p, 0ull, nullptr, -2, nullptr, nullptr));
+    CU(cudaStreamSynchronize(e->stream));
+    return ONA_OK;
+}
+
+int ona_export_fitness_dev(ona_engine* e, int first, int count, double* dst_dev) {
+    TRY(check_range(e, first, count));
+    if (!dst_dev) return fail(ONA_ERR_INVALID, "null destination");
+    if (count == 0) return ONA_OK;
+    LOCK(e);
+    CU(cudaMemcpyAsync(dst_dev, e->pop.fit + (size_t)first * e->ob.M, (size_t)count * e->ob.M * 8,
+                       cudaMemcpyDeviceToDevice, e->stream));
+    return ONA_OK;
+}
+
+}  // extern "C"

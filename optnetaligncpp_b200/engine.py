@@ -1,0 +1,306 @@
+"""ctypes binding of the C ABI in include/ona_b200.h (libona_b200.so).
+
+This is the Python-side host mirror used by the tests and bench.py; the C++ host mirror of
+the reference's Alignment / localSearch interface lives in optnetaligncpp_b200/host/.
+There is no CPU fallback: loading fails loudly when the CUDA library is missing, and
+``Engine`` raises when no GPU is usable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+# objective ids == the reference's enum fitnessName (Network.h:31-32)
+ICS, EC, BITSCORE_SUM, EVALS_SUM, SIZE, GOC, S3, S3_DENOM, ICS_TIMES_EC, S3_VARIANT = range(10)
+OBJECTIVE_NAMES = ["ICS", "EC", "BitscoreSum", "EvalsSum", "Size", "GOC", "S3", "S3Denom",
+                   "ICS*EC", "S3Variant"]            # fitnessNameToStr, Network.cpp:12-37
+SEED_NONE, SEED_TRUE, SEED_REFCOMPAT, SUM_SEQUENTIAL = 0, 1, 2, 16
+
+EXPORTS = [
+    "ona_device_count", "ona_engine_create", "ona_engine_destroy", "ona_last_error",
+    "ona_set_stream", "ona_synchronize", "ona_host_alloc", "ona_host_free", "ona_kernel_launches",
+    "ona_set_island_offset", "ona_pop_resize", "ona_pop_upload", "ona_pop_download",
+    "ona_pop_set_counters", "ona_pop_get_counters", "ona_full_fitness", "ona_full_fitness_dev",
+    "ona_swap_deltas", "ona_swap_deltas_rng", "ona_rng_proposals", "ona_hill_climb",
+    "ona_apply_swaps", "ona_export_fitness_dev",
+]
+
+
+class OnaError(RuntimeError):
+    pass
+
+
+class _ScoreTable(C.Structure):
+    _fields_ = [("dense", C.c_void_p), ("rows", C.c_void_p), ("cols", C.c_void_p),
+                ("vals", C.c_void_p), ("nnz", C.c_longlong)]
+
+
+class _Problem(C.Structure):
+    _fields_ = [("n1", C.c_int), ("n2", C.c_int), ("num_edges1", C.c_longlong),
+                ("rowptr1", C.c_void_p), ("col1", C.c_void_p), ("rowptr2", C.c_void_p),
+                ("col2", C.c_void_p), ("bitscores", _ScoreTable), ("gocs", _ScoreTable),
+                ("objectives", C.c_void_p), ("num_objectives", C.c_int)]
+
+
+_LIB = None
+
+
+def load_library(build_if_missing=True):
+    """dlopen libona_b200.so (building it in-tree first when nvcc is around)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if build_if_missing:
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(_build.LIB):
+                raise
+    if not os.path.exists(_build.LIB):
+        raise OnaError("libona_b200.so is missing: build it with `python -m optnetaligncpp_b200.build` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(_build.LIB)
+    vp, ci, ll = C.c_void_p, C.c_int, C.c_longlong
+    L.ona_last_error.restype = C.c_char_p
+    L.ona_engine_create.argtypes = [ci, C.POINTER(_Problem), C.POINTER(vp)]
+    L.ona_engine_destroy.argtypes = [vp]
+    L.ona_engine_destroy.restype = None
+    L.ona_set_stream.argtypes = [vp, vp]
+    L.ona_synchronize.argtypes = [vp]
+    L.ona_host_alloc.restype = vp
+    L.ona_host_alloc.argtypes = [ll]
+    L.ona_host_free.argtypes = [vp]
+    L.ona_host_free.restype = None
+    L.ona_kernel_launches.restype = ll
+    L.ona_kernel_launches.argtypes = [vp]
+    L.ona_set_island_offset.argtypes = [vp, ll]
+    L.ona_pop_resize.argtypes = [vp, ci]
+    L.ona_pop_upload.argtypes = [vp, ci, ci, vp, vp]
+    L.ona_pop_download.argtypes = [vp, ci, ci, vp, vp, vp]
+    L.ona_pop_set_counters.argtypes = [vp, ci, ci, vp, vp, vp, vp]
+    L.ona_pop_get_counters.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp]
+    L.ona_full_fitness.argtypes = [vp, ci, ci, ci] + [vp] * 7
+    L.ona_full_fitness_dev.argtypes = [vp, ci, ci, ci]
+    L.ona_swap_deltas.argtypes = [vp, ci, ci, ci, vp, ci] + [vp] * 7
+    L.ona_swap_deltas_rng.argtypes = [vp, ci, ci, ci, C.c_ulonglong, ci, vp, vp, vp]
+    L.ona_rng_proposals.argtypes = [vp, ci, ci, ci, C.c_ulonglong, ll, vp]
+    L.ona_hill_climb.argtypes = [vp, ci, ci, ll, vp, C.c_ulonglong, vp, vp, vp]
+    L.ona_apply_swaps.argtypes = [vp, ci, ci, ci, vp]
+    L.ona_export_fitness_dev.argtypes = [vp, ci, ci, vp]
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Engine:
+    """One scoring engine bound to one GPU: two networks, score tables, objective list and a
+    population of alignment slots.  Mirrors the data an ``Alignment`` borrows
+    (Alignment.h:73-98) and the batched forms of its hot-path methods."""
+
+    def __init__(self, n1, n2, num_edges1, rp1, col1, rp2, col2, objectives, bits=None, goc=None,
+                 device=0):
+        """bits / goc: None, a dense [n1,n2] float64 array, or a (rows, cols, vals) COO triple."""
+        self.L = load_library()
+        self.n1, self.n2, self.M = int(n1), int(n2), len(objectives)
+        self.objectives = _i32(objectives)
+        keep = [_i32(rp1), _i32(col1), _i32(rp2), _i32(col2), self.objectives]
+        pr = _Problem()
+        pr.n1, pr.n2, pr.num_edges1 = self.n1, self.n2, int(num_edges1)
+        pr.rowptr1, pr.col1, pr.rowptr2, pr.col2 = (_ptr(a) for a in keep[:4])
+        pr.objectives, pr.num_objectives = _ptr(self.objectives), self.M
+        for field, t in (("bitscores", bits), ("gocs", goc)):
+            st = _ScoreTable()
+            if t is None:
+                pass
+            elif isinstance(t, tuple):
+                r, c, v = _i32(t[0]), _i32(t[1]), np.ascontiguousarray(t[2], dtype=np.float64)
+                keep += [r, c, v]
+                st.rows, st.cols, st.vals, st.nnz = _ptr(r), _ptr(c), _ptr(v), len(v)
+            else:
+                d = np.ascontiguousarray(t, dtype=np.float64)
+                assert d.shape == (self.n1, self.n2)
+                keep.append(d)
+                st.dense = _ptr(d)
+            setattr(pr, field, st)
+        h = C.c_void_p()
+        self.h = None
+        self._check(self.L.ona_engine_create(int(device), C.byref(pr), C.byref(h)))
+        self.h = h
+        self.device = int(device)
+        self.P = 0
+
+    @classmethod
+    def from_pair(cls, pair, objectives, use_bits=True, use_goc=False, goc_dense=None, device=0):
+        """Engine for a synth.NetPair."""
+        bits = None
+        if use_bits and pair.bit_rows is not None:
+            bits = (pair.bit_rows, pair.bit_cols, pair.bit_vals)
+        goc = goc_dense if use_goc else None
+        return cls(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2, objectives,
+                   bits=bits, goc=goc, device=device)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OnaError("ona error %d: %s" % (rc, self.L.ona_last_error().decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ona_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream):
+        self._check(self.L.ona_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._check(self.L.ona_synchronize(self.h))
+
+    def kernel_launches(self):
+        return int(self.L.ona_kernel_launches(self.h))
+
+    def set_island_offset(self, first_global):
+        self._check(self.L.ona_set_island_offset(self.h, int(first_global)))
+
+    # ---- population
+    def resize(self, P):
+        self._check(self.L.ona_pop_resize(self.h, int(P)))
+        self.P = int(P)
+
+    def upload(self, aln, mask=None, first=0):
+        aln = _i32(aln).reshape(-1, self.n2)
+        if first + len(aln) > self.P:
+            self.resize(first + len(aln))
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1, self.n2)
+        self._check(self.L.ona_pop_upload(self.h, first, len(aln), _ptr(aln), _ptr(m)))
+
+    def download(self, first=0, count=None):
+        count = self.P - first if count is None else count
+        a = np.empty((count, self.n2), np.int32)
+        inv = np.empty((count, self.n2), np.int32)
+        m = np.empty((count, self.n2), np.uint8)
+        self._check(self.L.ona_pop_download(self.h, first, count, _ptr(a), _ptr(inv), _ptr(m)))
+        return a, inv, m
+
+    def set_counters(self, cons, ind, bits, goc, first=0):
+        cons, ind = _i32(cons), _i32(ind)
+        bits = np.ascontiguousarray(bits, dtype=np.float64)
+        goc = np.ascontiguousarray(goc, dtype=np.float64)
+        self._check(self.L.ona_pop_set_counters(self.h, first, len(cons), _ptr(cons), _ptr(ind),
+                                                _ptr(bits), _ptr(goc)))
+
+    def counters(self, first=0, count=None):
+        count = self.P - first if count is None else count
+        r = dict(cons=np.empty(count, np.int32), ind=np.empty(count, np.int32),
+                 bits=np.empty(count, np.float64), goc=np.empty(count, np.float64),
+                 size=np.empty(count, np.float64), fit=np.empty((count, self.M), np.float64))
+        self._check(self.L.ona_pop_get_counters(self.h, first, count, _ptr(r["cons"]), _ptr(r["ind"]),
+                                                _ptr(r["bits"]), _ptr(r["goc"]), _ptr(r["size"]),
+                                                _ptr(r["fit"])))
+        return r
+
+    # ---- hot path
+    def full_fitness(self, first=0, count=None, seed_mode=SEED_REFCOMPAT):
+        count = self.P - first if count is None else count
+        r = dict(cons_true=np.empty(count, np.int32), cons_ref=np.empty(count, np.int32),
+                 ind=np.empty(count, np.int32), bits=np.empty(count, np.float64),
+                 goc=np.empty(count, np.float64), size=np.empty(count, np.float64),
+                 fit=np.empty((count, self.M), np.float64))
+        self._check(self.L.ona_full_fitness(self.h, first, count, seed_mode, _ptr(r["cons_true"]),
+                                            _ptr(r["cons_ref"]), _ptr(r["ind"]), _ptr(r["bits"]),
+                                            _ptr(r["goc"]), _ptr(r["size"]), _ptr(r["fit"])))
+        return r
+
+    def full_fitness_dev(self, first=0, count=None, seed_mode=SEED_REFCOMPAT):
+        count = self.P - first if count is None else count
+        self._check(self.L.ona_full_fitness_dev(self.h, first, count, seed_mode))
+
+    def swap_deltas(self, xy, obj=-1, first=0, want=("cons", "ind", "bits", "goc", "fit", "improved",
+                                                    "snd"), out=None):
+        """xy: [count,K,2].  Returns per-candidate arrays (see include/ona_b200.h)."""
+        xy = _i32(xy)
+        count, K = xy.shape[0], xy.shape[1]
+        if out is None:
+            dt = dict(cons=np.int32, ind=np.int32, bits=np.float64, goc=np.float64, fit=np.float64,
+                      improved=np.uint8, snd=np.float64)
+            out = {k: np.empty((count, K, self.M) if k == "fit" else (count, K), dt[k]) for k in want}
+        g = out.get
+        self._check(self.L.ona_swap_deltas(self.h, first, count, K, _ptr(xy), int(obj), _ptr(g("cons")),
+                                           _ptr(g("ind")), _ptr(g("bits")), _ptr(g("goc")),
+                                           _ptr(g("fit")), _ptr(g("improved")), _ptr(g("snd"))))
+        return out
+
+    def swap_deltas_rng(self, K, seed, obj=-1, first=0, count=None, summary=True, best=False):
+        count = self.P - first if count is None else count
+        ni = np.empty(count, np.int32) if summary else None
+        bs = np.empty(count, np.float64) if best else None
+        bxy = np.empty((count, 2), np.int32) if best else None
+        self._check(self.L.ona_swap_deltas_rng(self.h, first, count, int(K), int(seed), int(obj),
+                                               _ptr(ni), _ptr(bs), _ptr(bxy)))
+        return ni, bs, bxy
+
+    def rng_proposals(self, K, seed, first=0, count=None, start=0):
+        count = self.P - first if count is None else count
+        xy = np.empty((count, K, 2), np.int32)
+        self._check(self.L.ona_rng_proposals(self.h, first, count, int(K), int(seed), int(start),
+                                             _ptr(xy)))
+        return xy
+
+    def hill_climb(self, iters=None, xy=None, seed=0, objs=None, first=0, count=None,
+                   want_accepted=False):
+        """correctHillClimb on `count` slots; xy [count,iters,2] or None for device proposals."""
+        if xy is not None:
+            xy = _i32(xy)
+            count, iters = xy.shape[0], xy.shape[1]
+        count = self.P - first if count is None else count
+        o = None if objs is None else _i32(np.broadcast_to(np.asarray(objs), (count,)))
+        acc = np.empty((count, iters), np.uint8) if want_accepted else None
+        nacc = np.empty(count, np.int64)
+        self._check(self.L.ona_hill_climb(self.h, first, count, int(iters), _ptr(xy), int(seed),
+                                          _ptr(o), _ptr(acc), _ptr(nacc)))
+        return acc, nacc
+
+    def apply_swaps(self, xy, first=0):
+        xy = _i32(xy)
+        self._check(self.L.ona_apply_swaps(self.h, first, xy.shape[0], xy.shape[1], _ptr(xy)))
+
+    def export_fitness_dev(self, dst_ptr, first=0, count=None):
+        count = self.P - first if count is None else count
+        self._check(self.L.ona_export_fitness_dev(self.h, first, count, C.c_void_p(dst_ptr)))
+
+
+def rng_proposals_host(seed, n1, n2, first_global, count, K, start=0):
+    """numpy mirror of the device proposal RNG (csrc/ona_device.cuh: mix64, rng_proposal)."""
+    u = np.uint64
+
+    def mix64(z):
+        z = (z + u(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> u(30))) * u(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> u(27))) * u(0x94D049BB133111EB)
+        return z ^ (z >> u(31))
+
+    with np.errstate(over="ignore"):
+        gp = (np.arange(count, dtype=np.uint64) + u(first_global))
+        key = mix64(mix64(np.full(count, seed, dtype=np.uint64)) + gp)
+        i = np.arange(K, dtype=np.uint64) + u(start)
+        r = mix64(key[:, None] + i[None, :])
+        lo = r & u(0xFFFFFFFF)
+        hi = r >> u(32)
+        x = ((lo * u(n1)) >> u(32)).astype(np.int64)
+        y = ((hi * u(n2 - 1)) >> u(32)).astype(np.int64)
+    y = y + (y >= x)
+    return np.stack([x, y], -1).astype(np.int32)

@@ -1,0 +1,338 @@
+"""GPU (-m gpu): the CUDA engine, called through the C ABI, against the oracle and the golden
+vectors.  Integer counts, accept bits and permutations must be bit-exact; fp64 accumulators /
+objectives are compared exactly wherever the engine replicates the reference's operation order
+(everything incremental) and within 1e-9 relative for the tree-summed from-scratch sums."""
+import numpy as np
+import pytest
+
+from conftest import dense_from_coo
+from optnetaligncpp_b200 import engine, synth
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+ALL = list(range(10))
+RTOL = 1e-9          # north_star: "S3/ICS ratios and summed bitscores agree within 1e-9 relative"
+
+
+def close(a, b):
+    return np.allclose(a, b, rtol=RTOL, atol=0.0, equal_nan=True)
+
+
+def engine_for_golden(g, names, S=None, G=None):
+    return engine.Engine(g["n1"], g["n2"], g["E1"], g["rp1"], g["col1"], g["rp2"], g["col2"], names,
+                         bits=S, goc=G)
+
+
+# ------------------------------------------------------------------ golden: small pair
+def test_small_golden_full_fitness(small_golden):
+    g = small_golden
+    e = engine_for_golden(g, ALL, g["S"], g["G"])
+    e.upload(g["aln"], g["mask"])
+    for mode in (engine.SEED_REFCOMPAT, engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL):
+        r = e.full_fitness(seed_mode=mode)
+        assert np.array_equal(r["cons_ref"], g["cons"])
+        assert np.array_equal(r["ind"], g["ind"])
+        assert (r["cons_true"] >= r["cons_ref"]).all() and (r["cons_true"] - r["cons_ref"] <= 1).all()
+        if mode & engine.SUM_SEQUENTIAL:
+            assert np.array_equal(r["bits"], g["bits"]) and np.array_equal(r["goc"], g["goc"])
+            assert np.array_equal(r["fit"], g["fitness"], equal_nan=True)
+        else:
+            assert close(r["bits"], g["bits"]) and close(r["goc"], g["goc"])
+            assert close(r["fit"], g["fitness"])
+        c = e.counters()
+        assert np.array_equal(c["cons"], g["cons"]) and np.array_equal(c["ind"], g["ind"])
+    a, inv, m = e.download()
+    assert np.array_equal(a, g["aln"]) and np.array_equal(m, g["mask"])
+    assert all(np.array_equal(inv[p][a[p]], np.arange(int(g["n2"]))) for p in range(len(a)))
+
+
+def test_small_golden_swap_deltas_bit_exact(small_golden):
+    g = small_golden
+    e = engine_for_golden(g, ALL, g["S"], g["G"])
+    e.upload(g["aln"], g["mask"])
+    e.set_counters(g["cons"], g["ind"], g["bits"], g["goc"])
+    for i in range(4):
+        xy = g["cand_xy_%d" % i][None]
+        r = e.swap_deltas(xy, obj=-1, first=i)
+        for k in ("cons", "ind", "improved"):
+            assert np.array_equal(r[k][0], g["cand_%s_%d" % (k, i)]), (i, k)
+        for k in ("bits", "goc", "fit", "snd"):
+            assert np.array_equal(r[k][0], g["cand_%s_%d" % (k, i)], equal_nan=True), (i, k)
+
+
+def test_small_golden_hill_climb_trajectories(small_golden):
+    g = small_golden
+    e = engine_for_golden(g, ALL, g["S"], g["G"])
+    e.upload(g["aln"], g["mask"])
+    e.set_counters(g["cons"], g["ind"], g["bits"], g["goc"])
+    xy = np.stack([g["hc_xy_%d" % i] for i in range(4)])
+    objs = np.array([int(g["hc_obj_%d" % i]) for i in range(4)])
+    acc, nacc = e.hill_climb(xy=xy, objs=objs, want_accepted=True)
+    a, inv, m = e.download()
+    c = e.counters()
+    for i in range(4):
+        assert np.array_equal(acc[i], g["hc_accepted_%d" % i]), i
+        assert nacc[i] == g["hc_accepted_%d" % i].sum()
+        assert np.array_equal(a[i], g["hc_final_aln_%d" % i])
+        assert np.array_equal(m[i], g["hc_final_mask_%d" % i])
+        fc = g["hc_final_counters_%d" % i]
+        assert (c["cons"][i], c["ind"][i]) == (fc[0], fc[1])
+        assert c["bits"][i] == fc[2] and c["goc"][i] == fc[3]      # incl. H3 undo residue
+        assert np.array_equal(inv[i][a[i]], np.arange(int(g["n2"])))
+
+
+# --------------------------------------------------------------- golden: example pair
+@pytest.fixture(scope="module")
+def example_engine(example_golden):
+    g = example_golden
+    e = engine_for_golden(g, g["names"], (g["bit_rows"], g["bit_cols"], g["bit_vals"]))
+    return e
+
+
+def test_example_golden_full_fitness(example_golden, example_engine):
+    g, e = example_golden, example_engine
+    e.upload(g["aln"])
+    r = e.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
+    assert np.array_equal(r["cons_ref"], g["cons"]) and np.array_equal(r["ind"], g["ind"])
+    assert np.array_equal(r["bits"], g["bits"])         # multiples of 0.5: any order is exact
+    assert np.array_equal(r["fit"], g["fitness"])
+    assert r["cons_ref"][0] == 140 and r["ind"][0] == 12177 and r["bits"][0] == 360.0
+    ident = np.arange(int(g["n2"]), dtype=np.int32)[None]
+    e.upload(ident, first=0)
+    r = e.full_fitness(first=0, count=1)
+    assert (r["cons_ref"][0], r["ind"][0], r["bits"][0]) == (584, 27789, 685.0)
+
+
+@pytest.mark.parametrize("obj", [-1, 0, 1])
+def test_example_golden_swap_deltas(example_golden, example_engine, obj):
+    g, e = example_golden, example_engine
+    e.upload(g["aln"])
+    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
+    r = e.swap_deltas(g["cand_xy"][None], obj=obj, first=0)
+    assert np.array_equal(r["improved"][0], g["cand_improved_obj%d" % obj])
+    if obj == -1:
+        for k in ("cons", "ind"):
+            assert np.array_equal(r[k][0], g["cand_%s_obj-1" % k])
+        for k in ("bits", "goc", "fit", "snd"):
+            assert np.array_equal(r[k][0], g["cand_%s_obj-1" % k], equal_nan=True), k
+
+
+def test_example_golden_hill_climb(example_golden, example_engine):
+    g, e = example_golden, example_engine
+    e.upload(g["aln"])
+    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
+    acc, nacc = e.hill_climb(xy=g["hc_xy"][None], first=0, count=1, want_accepted=True)
+    assert np.array_equal(np.packbits(acc[0]), g["hc_accepted"])
+    a, inv, m = e.download(0, 1)
+    assert np.array_equal(a[0], g["hc_final_aln"])
+    c = e.counters(0, 1)
+    fc = g["hc_final_counters"]
+    assert (c["cons"][0], c["ind"][0], c["bits"][0]) == (fc[0], fc[1], fc[2])
+    assert np.array_equal(c["fit"][0], g["hc_final_fitness"])
+    acc1, _ = e.hill_climb(xy=g["hc1_xy"][None], objs=[1], first=1, count=1, want_accepted=True)
+    assert np.array_equal(np.packbits(acc1[0]), g["hc1_accepted"])
+    assert np.array_equal(e.download(1, 1)[0][0], g["hc1_final_aln"])
+    fc = g["hc1_final_counters"]
+    c = e.counters(1, 1)
+    assert (c["cons"][0], c["ind"][0], c["bits"][0]) == (fc[0], fc[1], fc[2])
+
+
+# ---------------------------------------------------- seeded inputs against the oracle
+@pytest.fixture(scope="module")
+def mid():
+    pair = synth.make_pair(n1=600, n2=800, m1=3000, m2=3200, max_deg=80, seed=123,
+                           annotations=True, n_terms=300, bit_density=0.005, bit_decimals=True)
+    S, G = synth.dense_bits(pair), synth.dense_goc(pair)
+    prob = port.Problem(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2, S, G)
+    return pair, S, G, prob
+
+
+@pytest.mark.parametrize("total", [True, False])
+def test_engine_matches_oracle_on_seeded_pair(mid, total):
+    pair, S, G, prob = mid
+    names = [engine.S3, engine.BITSCORE_SUM, engine.GOC, engine.ICS, engine.SIZE]
+    P, K = 12, 1500
+    aln, mask = synth.random_population(pair, P, seed=5, total=total)
+    e = engine.Engine.from_pair(pair, names, use_goc=True, goc_dense=G)
+    e.upload(aln, mask)
+    r = e.full_fitness(seed_mode=engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL)
+    orc = [port.Aln(prob, aln[p], None if mask is None else mask[p]) for p in range(P)]
+    for p in range(P):
+        c = orc[p].counters()
+        assert (r["cons_ref"][p], r["ind"][p]) == (c[0], c[1])
+        assert r["cons_true"][p] == orc[p].conserved_true()
+        assert r["bits"][p] == c[2] and r["goc"][p] == c[3]
+        assert np.array_equal(r["fit"][p], orc[p].compute_fitness(names), equal_nan=True)
+    # general candidates: any two positions (dummies included, as mutate/crossover produce)
+    rng = np.random.default_rng(9)
+    xy = rng.integers(0, pair.n2, (P, K, 2)).astype(np.int32)
+    for obj in (-1, 2):
+        d = e.swap_deltas(xy, obj=obj)
+        for p in range(P):
+            o = orc[p].swap_delta_records(xy[p], names, obj=obj, want_snd=True)
+            for k in ("cons", "ind", "improved"):
+                assert np.array_equal(d[k][p], o[k]), (p, k)
+            for k in ("bits", "goc", "fit", "snd"):
+                assert np.array_equal(d[k][p], o[k], equal_nan=True), (p, k)
+    # hill climb, mixed objectives per individual, proposals from the host
+    iters = 6000
+    hxy = synth.random_candidates(pair, P, iters, seed=77)
+    objs = np.array([-1, 0, 1, 2] * 3)
+    acc, nacc = e.hill_climb(xy=hxy, objs=objs, want_accepted=True)
+    a, inv, m = e.download()
+    c = e.counters()
+    for p in range(P):
+        oacc = orc[p].hill_climb_replay(hxy[p], names, obj=int(objs[p]), want_accepted=True)
+        assert np.array_equal(acc[p], oacc), p
+        st = orc[p].state()
+        assert np.array_equal(a[p], st[0]) and np.array_equal(inv[p], st[1]) and np.array_equal(m[p], st[2])
+        oc = orc[p].counters()
+        assert (c["cons"][p], c["ind"][p], c["bits"][p], c["goc"][p]) == oc
+        assert np.array_equal(c["fit"][p], orc[p].compute_fitness(names), equal_nan=True)
+    assert nacc.sum() == acc.sum() and acc.sum() > 0
+
+
+def test_device_rng_proposals_and_climb(mid):
+    pair, S, G, prob = mid
+    names = [engine.S3, engine.BITSCORE_SUM]
+    P, iters = 6, 5000
+    aln, _ = synth.random_population(pair, P, seed=1)
+    e = engine.Engine.from_pair(pair, names)
+    e.set_island_offset(40)
+    e.upload(aln)
+    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
+    base = e.counters()
+    xy = e.rng_proposals(iters, seed=2024)
+    assert np.array_equal(xy, engine.rng_proposals_host(2024, pair.n1, pair.n2, 40, P, iters))
+    _, nacc = e.hill_climb(iters=iters, seed=2024)
+    a, _, _ = e.download()
+    c = e.counters()
+    for p in range(P):
+        o = port.Aln(prob, aln[p])
+        assert o.counters()[:3] == (base["cons"][p], base["ind"][p], base["bits"][p])
+        oacc = o.hill_climb_replay(xy[p], names, want_accepted=True)
+        assert oacc.sum() == nacc[p]
+        assert np.array_equal(a[p], o.state()[0])
+        assert (c["cons"][p], c["ind"][p], c["bits"][p]) == o.counters()[:3]
+    # swap_deltas_rng: accept counts + arg-max swapNormalizedDelta over the same proposals
+    K = 3000
+    ni, bs, bxy = e.swap_deltas_rng(K, seed=7, best=True)
+    pxy = e.rng_proposals(K, seed=7)
+    d = e.swap_deltas(pxy, obj=-1)
+    assert np.array_equal(ni, d["improved"].sum(1))
+    for p in range(P):
+        snd = np.where(np.isnan(d["snd"][p]), -np.inf, d["snd"][p])
+        k = int(np.argmax(snd))
+        assert bs[p] == snd[k] and tuple(bxy[p]) == tuple(pxy[p, k])
+
+
+def test_apply_swaps_matches_doSwap_sequence(mid):
+    pair, S, G, prob = mid
+    names = [engine.EC, engine.BITSCORE_SUM, engine.GOC, engine.SIZE]
+    P, n = 5, 300
+    aln, mask = synth.random_population(pair, P, seed=8, total=False)
+    e = engine.Engine.from_pair(pair, names, use_goc=True, goc_dense=G)
+    e.upload(aln, mask)
+    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL)
+    rng = np.random.default_rng(3)
+    xy = rng.integers(0, pair.n2, (P, n, 2)).astype(np.int32)
+    xy[:, ::7, 0] = -1                                   # ragged lists: skipped entries
+    e.apply_swaps(xy)
+    a, inv, m = e.download()
+    c = e.counters()
+    for p in range(P):
+        o = port.Aln(prob, aln[p], mask[p])
+        for x, y in xy[p]:
+            if x >= 0:
+                o.do_swap(int(x), int(y))
+        st = o.state()
+        assert np.array_equal(a[p], st[0]) and np.array_equal(m[p], st[2])
+        assert (c["cons"][p], c["ind"][p], c["bits"][p], c["goc"][p]) == o.counters()
+        assert c["size"][p] == o.aln_size()
+
+
+def test_wide_id_path_uint32_state():
+    # n2 >= 32768 switches the shared-memory state to 32-bit entries
+    pair = synth.make_pair(n1=1500, n2=33000, m1=5000, m2=40000, max_deg=100, seed=31, bits=False)
+    prob = port.Problem(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2)
+    names = [engine.S3, engine.ICS]
+    aln, _ = synth.random_population(pair, 3, seed=2)
+    e = engine.Engine.from_pair(pair, names, use_bits=False)
+    e.upload(aln)
+    r = e.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
+    xy = synth.random_candidates(pair, 3, 3000, seed=4)
+    d = e.swap_deltas(xy, want=("cons", "ind", "improved", "fit"))
+    acc, _ = e.hill_climb(xy=xy, want_accepted=True)
+    a, _, _ = e.download()
+    for p in range(3):
+        o = port.Aln(prob, aln[p])
+        assert (r["cons_ref"][p], r["ind"][p]) == o.counters()[:2]
+        rec = o.swap_delta_records(xy[p], names)
+        assert np.array_equal(d["cons"][p], rec["cons"]) and np.array_equal(d["ind"][p], rec["ind"])
+        assert np.array_equal(d["improved"][p], rec["improved"])
+        assert np.array_equal(d["fit"][p], rec["fit"], equal_nan=True)
+        assert np.array_equal(acc[p], o.hill_climb_replay(xy[p], names, want_accepted=True))
+        assert np.array_equal(a[p], o.state()[0])
+
+
+# ------------------------------------------------ full BASELINE size: invariant families
+def test_full_size_invariants_yeast_fly():
+    """C2 shape (6k/8k nodes, 30k edges, P=200): size-independent properties the reference's own
+    suite checks (tests.cpp: *_consistent_after_doSwap, alnInv_consistent_*, fast_ics_match_*)."""
+    pair = synth.make_pair(seed=synth.DEFAULT_SEED + 1)
+    names = [engine.S3, engine.BITSCORE_SUM]
+    P = 200
+    aln, _ = synth.random_population(pair, P, seed=11)
+    e = engine.Engine.from_pair(pair, names)
+    e.upload(aln)
+    r0 = e.full_fitness(seed_mode=engine.SEED_TRUE)
+    _, nacc = e.hill_climb(iters=20000, seed=99)
+    assert (nacc > 0).all()
+    inc = e.counters()
+    scratch = e.full_fitness(seed_mode=engine.SEED_NONE)
+    assert np.array_equal(inc["cons"], scratch["cons_true"])       # incremental == from scratch
+    assert np.array_equal(inc["ind"], scratch["ind"])
+    assert np.array_equal(inc["bits"], scratch["bits"])            # 0.5-multiples: exact
+    assert (inc["fit"] >= r0["fit"]).all()                         # obj=-1 never worsens anything
+    a, inv, m = e.download()
+    ar = np.arange(pair.n2)
+    assert all(np.array_equal(inv[p][a[p]], ar) for p in range(P)) and m.all()
+    # a swap evaluated as a delta equals committing it and rescoring from scratch
+    xy = synth.random_candidates(pair, P, 1, seed=5)
+    d = e.swap_deltas(xy, want=("cons", "ind", "bits"))
+    e.apply_swaps(xy)
+    s2 = e.full_fitness(seed_mode=engine.SEED_NONE)
+    assert np.array_equal(d["cons"][:, 0], s2["cons_true"]) and np.array_equal(d["ind"][:, 0], s2["ind"])
+    assert np.array_equal(d["bits"][:, 0], s2["bits"])
+    # swapping back restores everything (idempotence of the double swap)
+    e.apply_swaps(xy)
+    c3 = e.counters()
+    assert np.array_equal(c3["cons"], inc["cons"]) and np.array_equal(c3["ind"], inc["ind"])
+    assert np.array_equal(e.download()[0], a)
+
+
+def test_error_behaviour():
+    pair = synth.make_pair(n1=60, n2=80, m1=200, m2=260, max_deg=20, seed=4)
+    e = engine.Engine.from_pair(pair, [engine.S3])
+    bad = np.zeros((1, pair.n2), np.int32)
+    with pytest.raises(engine.OnaError, match="permutation"):
+        e.upload(bad)
+    with pytest.raises(engine.OnaError):
+        e.upload(np.full((1, pair.n2), pair.n2, np.int32))
+    aln, _ = synth.random_population(pair, 2, seed=1)
+    e.upload(aln)
+    with pytest.raises(engine.OnaError):
+        e.full_fitness(first=1, count=5)
+    with pytest.raises(engine.OnaError):
+        e.swap_deltas(np.full((2, 3, 2), pair.n2, np.int32))
+    with pytest.raises(engine.OnaError):
+        e.hill_climb(iters=10, objs=[3, 3])
+    col = pair.col1.copy()
+    col[pair.rp1[5]:pair.rp1[5] + 2] = col[pair.rp1[5]] if pair.rp1[6] - pair.rp1[5] >= 2 else col[pair.rp1[5]]
+    if pair.rp1[6] - pair.rp1[5] >= 2:
+        with pytest.raises(engine.OnaError, match="duplicate"):
+            engine.Engine(pair.n1, pair.n2, pair.E1, pair.rp1, col, pair.rp2, pair.col2, [engine.S3])
+    # empty inputs are no-ops
+    e.hill_climb(iters=0)
+    e.swap_deltas(np.empty((2, 0, 2), np.int32))
