@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Headline benchmark: swap-deltas/s (and full-fitness evals/s) of the OptNetAlign hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+Workload (BASELINE.json configs[1]): synthetic yeast-fly-sized PPI pair (6000 / 8000 nodes,
+~30k edges each, power-law), `--total --s3 --bitscores --blastsum`, popsize 200 per GPU.
+One step = one pass of the hot path over one batch: K_c candidate swaps per individual scored
+against the population's current state (swap-delta kernel), then one from-scratch
+full-fitness evaluation of every individual, then (N > 1) the all-gather of the objective
+vectors that feeds the host NSGA-II sort.  Islands: each rank owns P individuals, graph and
+score tables are replicated, there is no data-path collective (weak scaling).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from optnetaligncpp_b200 import synth  # noqa: E402
+
+METRIC = "swap_deltas_per_sec"
+UNIT = "swap-deltas/s"
+POP_PER_GPU = 200
+CAND_PER_IND = 16384
+OBJECTIVES = [6, 2]                     # S3, BitscoreSum  (--s3 --blastsum)
+WORKLOAD = ("synthetic yeast-fly pair n1=6000 n2=8000 ~30k edges each, --total --s3 --bitscores "
+            "--blastsum, popsize %d per GPU, %d candidate swaps per individual per step"
+            % (POP_PER_GPU, CAND_PER_IND))
+PAIR_SEED = synth.DEFAULT_SEED + 1
+FALLBACK_HBM_GBS = 6650.0               # B200_PROFILING.md fallback
+
+
+def make_workload():
+    return synth.make_pair(n1=6000, n2=8000, m1=30000, m2=30000, seed=PAIR_SEED)
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+def algorithmic_bytes(pair, aln, xy, ntables):
+    """SURVEY 8d B_min summed exactly over candidates xy [P,K,2] against aln [P,n2]:
+    8 [aln[x],aln[y]] + sum_{u in {x,y}, u<n1} (8 + d1(u)*(4+4+2/8))
+      + [y>=n1] sum_{a in {aln[x],aln[y]}} (8 + d2(a)*(4+4)) + (16 + 16[y<n1])*tables + 24."""
+    d1 = np.diff(pair.rp1).astype(np.float64)
+    d2 = np.diff(pair.rp2).astype(np.float64)
+    d1 = np.concatenate([d1, np.zeros(pair.n2 - pair.n1)])
+    x, y = xy[..., 0], xy[..., 1]
+    yreal = y < pair.n1
+    b = 8.0 + (8.0 + d1[x] * 8.25) + np.where(yreal, 8.0 + d1[y] * 8.25, 0.0)
+    ax = np.take_along_axis(aln, x, 1)
+    ay = np.take_along_axis(aln, y, 1)
+    b += np.where(~yreal, 16.0 + (d2[ax] + d2[ay]) * 8.0, 0.0)
+    b += (16.0 + 16.0 * yreal) * ntables + 24.0
+    return float(b.mean())
+
+
+def full_fitness_bytes(pair, ntables, M):
+    """E1*(8+8+1/8) + E2*(8+8) + n1*(4 + 8*tables) + 8*M per evaluation."""
+    return pair.E1 * 16.125 + pair.E2 * 16.0 + pair.n1 * (4.0 + 8.0 * ntables) + 8.0 * M
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, smax, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = max(smax, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference CPU arm
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class CpuArm:
+    """The reference's own CPU implementation of the path: threaded swapNormalizedDelta on
+    private Alignment copies (worker pattern of localSearch.cpp:130-147) through the compiled
+    reference (oracle/_ref) when it travelled, else the C port of it (oracle/ona_oracle.c)."""
+
+    def __init__(self, pair, nalns=8, seed=7):
+        from oracle import port, ref
+        self.pair = pair
+        self.threads = cpu_threads()
+        nalns = min(nalns, max(1, self.threads))
+        aln, _ = synth.random_population(pair, nalns, seed=seed)
+        if ref.available():
+            self.kind = "reference"
+            d = tempfile.mkdtemp(prefix="ona_bench_")
+            paths = synth.write_text(pair, os.path.join(d, "w"))
+            self.n1, self.n2 = ref.Net(paths["net1"]), ref.Net(paths["net2"])
+            self.B = ref.Dict.load_blast(self.n1, self.n2, paths["sim"])
+            self.alns = []
+            for p in range(nalns):
+                a = ref.Aln(self.n1, self.n2, self.B, None)
+                a.set_state(aln[p])
+                self.alns.append(a)
+            self.mod = ref
+        else:
+            self.kind = "port"
+            self.S = synth.dense_bits(pair)
+            self.prob = port.Problem(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2,
+                                     pair.col2, self.S, None)
+            self.alns = [port.Aln(self.prob, aln[p]) for p in range(nalns)]
+            self.mod = port
+
+    def swap_deltas(self, n, seed):
+        xy = synth.random_candidates(self.pair, 1, n, seed=seed)[0]
+        t, _ = self.mod.time_swap_deltas(self.alns, OBJECTIVES, xy, self.threads)
+        return t
+
+    def full_fitness(self, reps):
+        if self.kind == "reference":
+            t_ics, _ = self.mod.time_full_fitness(self.alns, OBJECTIVES, reps, self.threads, True)
+            t_adj, _ = self.mod.time_full_fitness(self.alns, OBJECTIVES, reps * 20, self.threads, False)
+            return reps / t_ics, reps * 20 / t_adj
+        t, _ = self.mod.time_full_fitness(self.alns, OBJECTIVES, reps * 20, self.threads)
+        return None, reps * 20 / t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pair = make_workload()
+    arm = CpuArm(pair)
+    per_step = 60000 * arm.threads            # ~0.15-0.3 s of all-core work per step
+    for w in range(args.warmup):
+        arm.swap_deltas(per_step, seed=100 + w)
+    total = 0.0
+    for s in range(args.steps):
+        total += arm.swap_deltas(per_step, seed=1000 + s)
+    value = per_step * args.steps / total
+    sample = "%d candidates per step (%d threads x 60000) on %d private individuals" % (
+        per_step, arm.threads, len(arm.alns))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "pair_seed": PAIR_SEED},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.threads, "kind": arm.kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------- our CUDA arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from optnetaligncpp_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    pair = make_workload()
+    P, K, M = POP_PER_GPU, CAND_PER_IND, len(OBJECTIVES)
+    e = engine.Engine.from_pair(pair, OBJECTIVES, device=local)
+    stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream shared with torch
+    torch.cuda.set_stream(stream)
+    e.set_stream(stream.cuda_stream)
+    e.set_island_offset(rank * P)
+    aln, _ = synth.random_population(pair, P, seed=1000 + rank)
+    e.upload(aln)
+    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
+
+    # device-resident outputs of the swap-delta kernel
+    o_cons = torch.empty((P, K), dtype=torch.int32, device=dev)
+    o_ind = torch.empty((P, K), dtype=torch.int32, device=dev)
+    o_fit = torch.empty((P, K, M), dtype=torch.float64, device=dev)
+    o_imp = torch.empty((P, K), dtype=torch.uint8, device=dev)
+    o_nimp = torch.zeros((P,), dtype=torch.int32, device=dev)
+    fit_local = torch.empty((P, M), dtype=torch.float64, device=dev)
+    fit_all = torch.empty((world * P, M), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(seed, ev=None):
+        flush.zero_()                                  # L2 flush between timed iterations
+        if ev:
+            ev[0].record(stream)
+        e.swap_deltas_dev(K, seed=seed, obj=-1, cons=o_cons.data_ptr(), ind=o_ind.data_ptr(),
+                          fit=o_fit.data_ptr(), improved=o_imp.data_ptr(),
+                          num_improved=o_nimp.data_ptr())
+        if ev:
+            ev[1].record(stream)
+        e.full_fitness_dev(seed_mode=engine.SEED_REFCOMPAT)
+        if ev:
+            ev[2].record(stream)
+        e.export_fitness_dev(fit_local.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(fit_all, fit_local)
+        if ev:
+            ev[3].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(max(args.warmup, 0)):
+        step(seed=10_000 + w)
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    launches0 = e.kernel_launches()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        step(seed=s, ev=evs[s])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = e.kernel_launches() - launches0
+    step_ms = [ev[0].elapsed_time(ev[3]) for ev in evs]
+    delta_ms = [ev[0].elapsed_time(ev[1]) for ev in evs]
+    full_ms = [ev[1].elapsed_time(ev[2]) for ev in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * P * K * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the C ABI with HOST buffers (pinned): H2D proposals, D2H results
+    e2e_steps = max(3, min(args.steps, 10))
+    xy_host = [torch.from_numpy(synth.random_candidates(pair, P, K, seed=50 + i)).pin_memory()
+               for i in range(2)]
+    h_out = dict(cons=torch.empty((P, K), dtype=torch.int32).pin_memory().numpy(),
+                 ind=torch.empty((P, K), dtype=torch.int32).pin_memory().numpy(),
+                 fit=torch.empty((P, K, M), dtype=torch.float64).pin_memory().numpy(),
+                 improved=torch.empty((P, K), dtype=torch.uint8).pin_memory().numpy())
+    for i in range(2):
+        e.swap_deltas(xy_host[i % 2].numpy(), obj=-1, out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e.swap_deltas(xy_host[i % 2].numpy(), obj=-1, out=h_out)
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * K * e2e_steps / float(e2e_t.item())
+    h2d = P * K * 2 * 4
+    d2h = sum(v.nbytes for v in h_out.values())
+
+    if rank == 0:
+        peak, peak_kind = hbm_peak()
+        xy0 = engine.rng_proposals_host(0, pair.n1, pair.n2, 0, P, K)
+        bytes_per_delta = algorithmic_bytes(pair, aln, xy0.astype(np.int64), ntables=1)
+        k_ms = float(np.mean(delta_ms))
+        achieved = bytes_per_delta * P * K / (k_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = tj.get("k_swap_deltas", {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        ff_ms = float(np.mean(full_ms))
+        ff_bytes = full_fitness_bytes(pair, 1, M)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pair_seed": PAIR_SEED, "popsize_per_gpu": P,
+                       "candidates_per_individual": K, "objectives": ["S3", "BitscoreSum"],
+                       "proposals": "device counter-based RNG", "l2": "flushed between timed steps "
+                       "(256 MiB memset)", "parallelism": "islands x%d, no data-path collective" % world},
+            "roofline": {"kernel": "k_swap_deltas", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "peak_kind": "of " + peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "algorithmic_bytes_per_swap_delta": bytes_per_delta,
+                         "units_per_launch": P * K, "kernel_ms": k_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "call": "ona_swap_deltas (host proposals -> conserved, induced, objectives, accept bit)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "full_fitness": {"value": world * P / (ff_ms * 1e-3), "unit": "full-fitness evals/s",
+                             "kernel_ms": ff_ms, "algorithmic_bytes_per_eval": ff_bytes,
+                             "achieved_gbs": ff_bytes * P / (ff_ms * 1e-3) / 1e9,
+                             "frac": ff_bytes * P / (ff_ms * 1e-3) / 1e9 / peak},
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            arm = CpuArm(pair)
+            n = 150000 * arm.threads
+            arm.swap_deltas(20000 * arm.threads, seed=1)
+            ts = [arm.swap_deltas(n, seed=2 + i) for i in range(3)]
+            ff_ics, ff_adj = arm.full_fitness(reps=max(arm.threads, 8))
+            line["cpu_baseline"] = {
+                "value": n / float(np.median(ts)), "unit": UNIT, "cores": arm.threads, "kind": arm.kind,
+                "sample": "%d candidates (%d threads x 150000) on %d private individuals, median of 3; "
+                          "swapNormalizedDelta worker pattern (localSearch.cpp:130-147)" % (
+                              n, arm.threads, len(arm.alns)),
+                "full_fitness_evals_per_sec_with_ics": ff_ics,
+                "full_fitness_evals_per_sec_adjacency_recount": ff_adj}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -151,6 +151,14 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
  * localSearch.cpp:136-147, over a random candidate subset). */
 int ona_swap_deltas_rng(ona_engine* e, int first, int count, int K, unsigned long long seed,
                         int obj, int* num_improved, double* best_snd, int* best_xy);
+/* Device-resident form: proposals from xy_dev ([count][K][2] on the device) or, when xy_dev
+ * is NULL, from the device RNG; every output pointer is a DEVICE buffer (or NULL) laid out as
+ * in ona_swap_deltas; num_improved_dev is [count] and is accumulated into (zero it first).
+ * Asynchronous on the engine's stream; nothing is copied or synchronised. */
+int ona_swap_deltas_dev(ona_engine* e, int first, int count, int K, const int* xy_dev,
+                        unsigned long long seed, int obj, int* conserved_dev, int* induced_dev,
+                        double* bitscore_dev, double* goc_dev, double* fitness_dev,
+                        unsigned char* improved_dev, double* snd_dev, int* num_improved_dev);
 /* the proposals the device RNG generates, for host-side checking */
 int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long long seed,
                       long long start_index, int* xy);

@@ -239,7 +239,7 @@ int launch_deltas_tg(ona_engine* e, int first, int count, int K, const int* xy_d
     if (rc) return rc;
     dim3 grid(chunks, count);
     k_swap_deltas<T, G><<<grid, 256, smem, e->stream>>>(e->g, e->S, e->G, e->ob, e->pop, first, K,
-                                                       xy_dev, seed, e->island_offset, obj, out, sum);
+                                                       xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag);
     e->launches++;
     CU(cudaGetLastError());
     return ONA_OK;
@@ -284,7 +284,7 @@ int launch_climb_tg(ona_engine* e, int first, int count, long long iters, const 
     if (rc) return rc;
     k_hill_climb<T, G><<<count, kRound * G, smem, e->stream>>>(e->g, e->S, e->G, e->ob, e->pop, first,
                                                               iters, xy_dev, seed, e->island_offset,
-                                                              objs_dev, force_obj, acc_dev, nacc_dev);
+                                                              objs_dev, force_obj, acc_dev, nacc_dev, e->d_flag);
     e->launches++;
     CU(cudaGetLastError());
     return ONA_OK;
@@ -314,6 +314,15 @@ template <typename V>
 int h2d(ona_engine* e, V* dev, const V* host, size_t n) {
     if (!host || !n) return ONA_OK;
     CU(cudaMemcpyAsync(dev, host, n * sizeof(V), cudaMemcpyHostToDevice, e->stream));
+    return ONA_OK;
+}
+
+// drain the stream and turn the device-side validation flag into an error code
+int finish_checked(ona_engine* e, const char* what) {
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (bad) return fail(ONA_ERR_INVALID, what);
     return ONA_OK;
 }
 
@@ -645,11 +654,9 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
     if (obj < -1 || obj >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
     if (count == 0 || K == 0) return ONA_OK;
     const size_t n = (size_t)count * K;
-    const int n2 = e->g.n2;
-    for (size_t i = 0; i < 2 * n; ++i)
-        if ((unsigned)xy[i] >= (unsigned)n2) return fail(ONA_ERR_INVALID, "proposal outside [0,n2)");
     LOCK(e);
     CU(e->t_xy.need(2 * n));
+    CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
     TRY(h2d(e, e->t_xy.p, xy, 2 * n));
     DevDeltaOut out{};
     if (cons) { CU(e->t_i0.need(n)); out.cons = e->t_i0.p; }
@@ -668,8 +675,7 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
     TRY(d2h(e, fitness, out.fit, n * e->ob.M));
     TRY(d2h(e, improved, out.improved, n));
     TRY(d2h(e, snd, out.snd, n));
-    CU(cudaStreamSynchronize(e->stream));
-    return ONA_OK;
+    return finish_checked(e, "proposal outside [0,n2)");
 }
 
 int ona_swap_deltas_rng(ona_engine* e, int first, int count, int K, unsigned long long seed, int obj,
@@ -727,6 +733,21 @@ int ona_swap_deltas_rng(ona_engine* e, int first, int count, int K, unsigned lon
     return ONA_OK;
 }
 
+int ona_swap_deltas_dev(ona_engine* e, int first, int count, int K, const int* xy_dev,
+                        unsigned long long seed, int obj, int* cons_dev, int* ind_dev,
+                        double* bits_dev, double* goc_dev, double* fit_dev,
+                        unsigned char* improved_dev, double* snd_dev, int* num_improved_dev) {
+    TRY(check_range(e, first, count));
+    if (K < 0) return fail(ONA_ERR_INVALID, "K < 0");
+    if (obj < -1 || obj >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
+    if (count == 0 || K == 0) return ONA_OK;
+    LOCK(e);
+    DevDeltaOut out{cons_dev, ind_dev, bits_dev, goc_dev, fit_dev, improved_dev, snd_dev};
+    DeltaSummary sum{};
+    sum.num_improved = num_improved_dev;
+    return launch_deltas(e, first, count, K, xy_dev, seed, obj, out, sum, pick_chunks(e, count, K));
+}
+
 int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long long seed,
                       long long start, int* xy) {
     TRY(check_range(e, first, count));
@@ -757,11 +778,8 @@ int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const i
         for (int i = 0; i < count; ++i)
             if (objs[i] < -1 || objs[i] >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
     const size_t n = (size_t)count * (size_t)iters;
-    const int n2 = e->g.n2;
-    if (xy)
-        for (size_t i = 0; i < 2 * n; ++i)
-            if ((unsigned)xy[i] >= (unsigned)n2) return fail(ONA_ERR_INVALID, "proposal outside [0,n2)");
     LOCK(e);
+    CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
     const int* xy_dev = nullptr;
     if (xy) {
         CU(e->t_xy.need(2 * n));
@@ -783,8 +801,7 @@ int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const i
     TRY(launch_climb(e, first, count, iters, xy_dev, seed, objs_dev, -3, acc_dev, e->t_l0.p));
     TRY(d2h(e, accepted, acc_dev, n));
     TRY(d2h(e, num_accepted, e->t_l0.p, (size_t)count));
-    CU(cudaStreamSynchronize(e->stream));
-    return ONA_OK;
+    return finish_checked(e, "proposal outside [0,n2)");
 }
 
 int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* xy) {
@@ -792,18 +809,12 @@ int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* 
     if (!xy || nswaps < 0) return fail(ONA_ERR_INVALID, "null swap list");
     if (count == 0 || nswaps == 0) return ONA_OK;
     const size_t n = (size_t)count * nswaps;
-    const int n2 = e->g.n2;
-    for (size_t i = 0; i < n; ++i) {
-        if (xy[2 * i] < 0) continue;
-        if (xy[2 * i] >= n2 || (unsigned)xy[2 * i + 1] >= (unsigned)n2)
-            return fail(ONA_ERR_INVALID, "swap outside [0,n2)");
-    }
     LOCK(e);
+    CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
     CU(e->t_xy.need(2 * n));
     TRY(h2d(e, e->t_xy.p, xy, 2 * n));
     TRY(launch_climb(e, first, count, nswaps, e->t_xy.p, 0ull, nullptr, -2, nullptr, nullptr));
-    CU(cudaStreamSynchronize(e->stream));
-    return ONA_OK;
+    return finish_checked(e, "swap outside [0,n2)");
 }
 
 int ona_export_fitness_dev(ona_engine* e, int first, int count, double* dst_dev) {

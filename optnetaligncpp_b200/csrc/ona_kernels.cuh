@@ -233,7 +233,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(256)
 k_swap_deltas(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first, int K,
               const int* __restrict__ xy, unsigned long long seed, long long island_offset,
-              int obj, DevDeltaOut out, DeltaSummary sum) {
+              int obj, DevDeltaOut out, DeltaSummary sum, int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_aln = reinterpret_cast<T*>(smem_raw);
     T* s_inv = s_aln + pop.n2p;
@@ -270,6 +270,10 @@ k_swap_deltas(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop,
             if (xy) {
                 const int2 v = __ldg(reinterpret_cast<const int2*>(xy) + (size_t)pl * K + c);
                 x = v.x; y = v.y;
+                if ((unsigned)x >= (unsigned)g.n2 || (unsigned)y >= (unsigned)g.n2) {
+                    atomicOr(err_flag, 1);  // reported by the host entry point as ONA_ERR_INVALID
+                    x = 0; y = 0;
+                }
             } else {
                 rng_proposal(ikey, (unsigned long long)c, g.n1, g.n2, x, y);
             }
@@ -363,7 +367,8 @@ __global__ void __launch_bounds__(kRound * G)
 k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first,
              long long iters, const int* __restrict__ xy, unsigned long long seed,
              long long island_offset, const int* __restrict__ objs, int force_obj,
-             unsigned char* __restrict__ accepted, long long* __restrict__ num_accepted) {
+             unsigned char* __restrict__ accepted, long long* __restrict__ num_accepted,
+             int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_aln = reinterpret_cast<T*>(smem_raw);
     T* s_inv = s_aln + pop.n2p;
@@ -398,7 +403,11 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                 if (xy) {
                     const int2 v = __ldg(reinterpret_cast<const int2*>(xy) + (size_t)pl * iters + pos + grp);
                     x = v.x; y = v.y;
-                    if (x < 0) { x = 0; y = 0; }  // ragged swap lists (ona_apply_swaps)
+                    if (x < 0 && force_obj == -2) { x = 0; y = 0; }  // ragged swap lists (ona_apply_swaps)
+                    if ((unsigned)x >= (unsigned)g.n2 || (unsigned)y >= (unsigned)g.n2) {
+                        atomicOr(err_flag, 1);
+                        x = 0; y = 0;
+                    }
                 } else {
                     rng_proposal(ikey, (unsigned long long)(pos + grp), g.n1, g.n2, x, y);
                 }

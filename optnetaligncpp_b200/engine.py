@@ -23,7 +23,7 @@ EXPORTS = [
     "ona_set_stream", "ona_synchronize", "ona_host_alloc", "ona_host_free", "ona_kernel_launches",
     "ona_set_island_offset", "ona_pop_resize", "ona_pop_upload", "ona_pop_download",
     "ona_pop_set_counters", "ona_pop_get_counters", "ona_full_fitness", "ona_full_fitness_dev",
-    "ona_swap_deltas", "ona_swap_deltas_rng", "ona_rng_proposals", "ona_hill_climb",
+    "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_rng_proposals", "ona_hill_climb",
     "ona_apply_swaps", "ona_export_fitness_dev",
 ]
 
@@ -85,6 +85,7 @@ def load_library(build_if_missing=True):
     L.ona_full_fitness_dev.argtypes = [vp, ci, ci, ci]
     L.ona_swap_deltas.argtypes = [vp, ci, ci, ci, vp, ci] + [vp] * 7
     L.ona_swap_deltas_rng.argtypes = [vp, ci, ci, ci, C.c_ulonglong, ci, vp, vp, vp]
+    L.ona_swap_deltas_dev.argtypes = [vp, ci, ci, ci, vp, C.c_ulonglong, ci] + [vp] * 8
     L.ona_rng_proposals.argtypes = [vp, ci, ci, ci, C.c_ulonglong, ll, vp]
     L.ona_hill_climb.argtypes = [vp, ci, ci, ll, vp, C.c_ulonglong, vp, vp, vp]
     L.ona_apply_swaps.argtypes = [vp, ci, ci, ci, vp]
@@ -252,6 +253,17 @@ class Engine:
         self._check(self.L.ona_swap_deltas_rng(self.h, first, count, int(K), int(seed), int(obj),
                                                _ptr(ni), _ptr(bs), _ptr(bxy)))
         return ni, bs, bxy
+
+    def swap_deltas_dev(self, K, seed=0, obj=-1, first=0, count=None, xy_dev=None, cons=None,
+                        ind=None, bits=None, goc=None, fit=None, improved=None, snd=None,
+                        num_improved=None):
+        """device-resident, asynchronous; every array argument is a raw device pointer (int)."""
+        count = self.P - first if count is None else count
+        vp = C.c_void_p
+        self._check(self.L.ona_swap_deltas_dev(self.h, first, count, int(K), vp(xy_dev or 0), int(seed),
+                                               int(obj), vp(cons or 0), vp(ind or 0), vp(bits or 0),
+                                               vp(goc or 0), vp(fit or 0), vp(improved or 0),
+                                               vp(snd or 0), vp(num_improved or 0)))
 
     def rng_proposals(self, K, seed, first=0, count=None, start=0):
         count = self.P - first if count is None else count

@@ -201,7 +201,7 @@ def test_device_rng_proposals_and_climb(mid):
     e = engine.Engine.from_pair(pair, names)
     e.set_island_offset(40)
     e.upload(aln)
-    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
+    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL)
     base = e.counters()
     xy = e.rng_proposals(iters, seed=2024)
     assert np.array_equal(xy, engine.rng_proposals_host(2024, pair.n1, pair.n2, 40, P, iters))
