@@ -38,6 +38,7 @@ def build(force=False, verbose=False):
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
            "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-ccbin", host_compiler(),
            "-o", LIB] + SOURCES
+    cmd += os.environ.get("ONA_NVCC_FLAGS", "").split()     # tuning experiments only
     if verbose:
         cmd += ["-Xptxas", "-v"]
     out = subprocess.run(cmd, capture_output=True, text=True)

@@ -56,6 +56,17 @@ struct DevGraph {
     const int* ev2;
     int ne1, ne2;
     unsigned long long E1;  // net1->edges.size()
+    // quad-padded CSR: every row padded with -1 to a multiple of 4 columns so that one 128-bit
+    // load fetches four neighbours; rq[u]..rq[u+1] index int4 quads
+    const int* rq1;
+    const int4* cq1;
+    const int* rq2;
+    const int4* cq2;
+    // neighbourhood signature of every net2 node: three 32-bit Bloom words -- for every
+    // neighbour j bit (j & 31) of .x, bit ((j >> 5) & 31) of .y and bit ((j >> 10) & 31) of .z
+    // are set.  A clear bit proves "not adjacent" without touching the bit matrix, and one
+    // 16-byte signature serves all the tests against that row.
+    const uint4* sig2;
 };
 
 // BLASTDict / GOCDict on the device: dense fp64 matrix, or an open-addressing hash of the
@@ -186,8 +197,8 @@ __device__ __forceinline__ double objective(int name, const Scalars& s, unsigned
 //   dind  = (ic'(a_x,-1) + ic'(a_y,a_x)) - (ic(a_x,-1) + ic(a_y,a_x))   :494-495,509-510,518
 // with primes = after exchanging the images AND mask bits of x and y (:496-504).
 template <typename T, int G>
-__device__ __forceinline__ void topo_delta(const DevGraph& g, const T* __restrict__ s_aln,
-                                           const T* __restrict__ s_inv, int x, int y, int gl,
+__device__ __forceinline__ void topo_delta(const DevGraph& g, const T* s_aln, const T* s_inv,
+                                           int x, int y, int gl,
                                            int& dc, int& di) {
     constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
     dc = 0;
@@ -251,6 +262,165 @@ __device__ __forceinline__ void topo_delta(const DevGraph& g, const T* __restric
                 di += (Ly_new & an) - (Ly_old & ao);
             }
         }
+    }
+}
+
+// ---- quad-CSR walkers (the sorted swap-delta kernel) -------------------------------------
+// Per-candidate context: images, masks and "alive" flags before/after the exchange.
+struct SwapCtx {
+    int x, y, ax, ay;
+    int mx, my;                          // alnMask[x], alnMask[y] before the exchange
+    int Lx_old, Lx_new, Ly_old, Ly_new;  // is a_x / a_y the image of a real, unmasked node
+    bool xr, yr;
+};
+template <typename T>
+__device__ __forceinline__ SwapCtx make_ctx(const DevGraph& g, const T* s_aln, int x, int y) {
+    constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
+    SwapCtx c;
+    const uint32_t rx = s_aln[x], ry = s_aln[y];
+    c.x = x; c.y = y;
+    c.ax = (int)(rx & MASK); c.ay = (int)(ry & MASK);
+    c.mx = (rx & FLAG) ? 0 : 1; c.my = (ry & FLAG) ? 0 : 1;
+    c.xr = x < g.n1; c.yr = y < g.n1;
+    c.Lx_old = (c.xr ? 1 : 0) & c.mx; c.Lx_new = (c.yr ? 1 : 0) & c.mx;
+    c.Ly_old = (c.yr ? 1 : 0) & c.my; c.Ly_new = (c.xr ? 1 : 0) & c.my;
+    return c;
+}
+__device__ __forceinline__ bool induced_changes(const SwapCtx& c) {
+    return c.Lx_old != c.Lx_new || c.Ly_old != c.Ly_new;
+}
+
+// Scoring the four neighbours of one quad, whichever list it is from.
+//
+// Conserved lists (N1(x), N1(y)), Alignment.cpp:799-803 before and after the exchange: for a
+// neighbour t with image it = aln[t] (and mask bit mt) the x-list term is
+//     mt * ( my*A2[a_y][it] - mx*A2[a_x][it] )  =:  mt * D(it)
+// and the y-list term is exactly -mt * D(it) (old and new rows trade places), so one item
+// routine serves both lists and only a per-quad sign differs.  A2[row][it] is answered by the
+// row's neighbourhood signature first (three 32-bit Bloom words; signature AND mask are folded
+// into sgx/sgy once per candidate): only when all three bits are set is the exact word of
+// the L2-resident bit matrix probed, with a predicated load -- the common "not an edge" case
+// costs no memory traffic and no branch.
+// Induced lists (N2(a_x), N2(a_y)), Alignment.cpp:818-822: a neighbour contributes
+// coef = L_new - L_old of the list's owner when its pre-image is alive (inv[v] < n1).
+// Neighbours that are themselves exchanged (x or y; a_x or a_y) are skipped here and only
+// recorded; their closed-form terms are added once per candidate (special_terms).
+struct QuadCtx {
+    const void* table;   // s_aln (conserved lists) or s_inv (induced lists)
+    bool cons;
+    int sp0, sp1;        // the two exchanged ids of this list's id space
+};
+struct RowSig {
+    uint4 sx, sy;        // masked signatures of rows a_x, a_y
+    unsigned rax, ray;   // word offsets of the two bit-matrix rows
+};
+
+template <typename T>
+__device__ __forceinline__ void quad_item(const DevGraph& g, const QuadCtx& qc, const RowSig& rs, int t,
+                                          int& cv, int& iv, bool& is0, bool& is1) {
+    constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
+    const bool valid = t >= 0;  // t < 0: row padding
+    const uint32_t r = static_cast<const T*>(qc.table)[valid ? t : 0];
+    is0 |= t == qc.sp0;
+    is1 |= t == qc.sp1;
+    const bool plain = valid & (t != qc.sp0) & (t != qc.sp1);
+    const unsigned it = r & MASK, h1 = it >> 5, h2 = it >> 10;  // shifts use the low 5 bits
+    const bool live = plain & qc.cons & !(r & FLAG);
+    const bool pX = live & ((((rs.sx.x >> (it & 31u)) & (rs.sx.y >> (h1 & 31u)) & (rs.sx.z >> (h2 & 31u))) & 1u) != 0u);
+    const bool pY = live & ((((rs.sy.x >> (it & 31u)) & (rs.sy.y >> (h1 & 31u)) & (rs.sy.z >> (h2 & 31u))) & 1u) != 0u);
+    unsigned wX = 0u, wY = 0u;
+    if (pX) wX = __ldg(g.adj2 + (unsigned)(rs.rax + h1));
+    if (pY) wY = __ldg(g.adj2 + (unsigned)(rs.ray + h1));
+    cv += (int)((wY >> (it & 31u)) & 1u) - (int)((wX >> (it & 31u)) & 1u);
+    iv += (plain & !qc.cons & (r < (uint32_t)g.n1)) ? 1 : 0;
+}
+
+// `seen` bits
+constexpr int kSeenXinX = 1, kSeenYinY = 2, kSeenAXinAX = 4, kSeenAYinAX = 8, kSeenAYinAY = 16;
+
+// Closed-form terms of the exchanged nodes themselves (rare: self-loops and the a_x - a_y edge):
+//   self-loop at x:   new my*A2[ay][ay] - old mx*A2[ax][ax]      (x in N1(x), Alignment.cpp:801)
+//   self-loop at y:   new mx*A2[ax][ax] - old my*A2[ay][ay]
+//   edge x-y:         cancels (the image pair is only mirrored); y's copy is the `ignore` (:493)
+//   self-loop at a_x: Lx_new - Lx_old;  self-loop at a_y: Ly_new - Ly_old        (:820)
+//   edge a_x-a_y:     (Lx_new & Ly_new) - (Lx_old & Ly_old); a_y's copy is the `ignore` (:495)
+__device__ __forceinline__ void special_terms(const DevGraph& g, const SwapCtx& c, int seen, int& dc,
+                                              int& di) {
+    if (seen & (kSeenXinX | kSeenYinY)) {
+        const int sx = probe(g, c.ax, c.ax), sy = probe(g, c.ay, c.ay);
+        if (seen & kSeenXinX) dc += (c.my & sy) - (c.mx & sx);
+        if (seen & kSeenYinY) dc += (c.mx & sx) - (c.my & sy);
+    }
+    if (seen & kSeenAXinAX) di += c.Lx_new - c.Lx_old;
+    if (seen & kSeenAYinAY) di += c.Ly_new - c.Ly_old;
+    if (seen & kSeenAYinAX) di += (c.Lx_new & c.Ly_new) - (c.Lx_old & c.Ly_old);
+}
+
+// The (up to) four quad lists of one candidate as one index space [0, e3):
+// [0,e0) N1(x)  [e0,e1) N1(y)  [e1,e2) N2(a_x)  [e2,e3) N2(a_y); quad q of list l is b[l] + q.
+struct QuadPlan {
+    int e0, e1, e2, e3;
+    int b0, b1, b2, b3;
+};
+__device__ __forceinline__ QuadPlan make_plan(const DevGraph& g, const SwapCtx& c) {
+    QuadPlan p;
+    p.e0 = p.e1 = p.e2 = p.e3 = 0;
+    p.b0 = p.b1 = p.b2 = p.b3 = 0;
+    if (c.x == c.y) return p;  // doSwap(x,x): every term cancels
+    int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    if (c.xr) { p.b0 = __ldg(g.rq1 + c.x); q0 = __ldg(g.rq1 + c.x + 1) - p.b0; }
+    if (c.yr) { p.b1 = __ldg(g.rq1 + c.y); q1 = __ldg(g.rq1 + c.y + 1) - p.b1; }
+    if (induced_changes(c)) {  // otherwise the induced subgraph is unchanged
+        p.b2 = __ldg(g.rq2 + c.ax); q2 = __ldg(g.rq2 + c.ax + 1) - p.b2;
+        p.b3 = __ldg(g.rq2 + c.ay); q3 = __ldg(g.rq2 + c.ay + 1) - p.b3;
+    }
+    p.e0 = q0; p.e1 = q0 + q1; p.e2 = p.e1 + q2; p.e3 = p.e2 + q3;
+    p.b1 -= p.e0; p.b2 -= p.e1; p.b3 -= p.e2;
+    return p;
+}
+
+// (dcons, dind) of one candidate: quads [first, first+stride, ...) of its plan.  One loop and
+// one branch-free item routine for all four lists, so that the lanes of a warp (each on its
+// own candidate, or all on one hub) stay converged whatever the individual list lengths are.
+// `seen` must be OR-reduced over the lanes that share a candidate before special_terms.
+template <typename T>
+__device__ __forceinline__ void walk_plan(const DevGraph& g, const T* s_aln, const T* s_inv,
+                                          const SwapCtx& c, const QuadPlan& p, int first, int stride,
+                                          int& dc, int& di, int& seen) {
+    dc = 0;
+    di = 0;
+    seen = 0;
+    RowSig rs;
+    rs.rax = (unsigned)c.ax * (unsigned)g.W;
+    rs.ray = (unsigned)c.ay * (unsigned)g.W;
+    rs.sx = make_uint4(0u, 0u, 0u, 0u);
+    rs.sy = rs.sx;
+    if (p.e1 > 0) {  // some conserved list will be walked; a masked-off row never matches
+        if (c.mx) rs.sx = __ldg(g.sig2 + c.ax);
+        if (c.my) rs.sy = __ldg(g.sig2 + c.ay);
+    }
+    const int coefx = c.Lx_new - c.Lx_old, coefy = c.Ly_new - c.Ly_old;
+    for (int q = first; q < p.e3; q += stride) {
+        const int l = (q >= p.e0 ? 1 : 0) + (q >= p.e1 ? 1 : 0) + (q >= p.e2 ? 1 : 0);
+        const int idx = (l == 0 ? p.b0 : l == 1 ? p.b1 : l == 2 ? p.b2 : p.b3) + q;
+        const int4 t = __ldg((l < 2 ? g.cq1 : g.cq2) + idx);
+        QuadCtx qc;
+        qc.cons = l < 2;
+        qc.table = qc.cons ? static_cast<const void*>(s_aln) : static_cast<const void*>(s_inv);
+        qc.sp0 = qc.cons ? c.x : c.ax;
+        qc.sp1 = qc.cons ? c.y : c.ay;
+        int cv = 0, iv = 0;
+        bool is0 = false, is1 = false;
+        quad_item<T>(g, qc, rs, t.x, cv, iv, is0, is1);
+        quad_item<T>(g, qc, rs, t.y, cv, iv, is0, is1);
+        quad_item<T>(g, qc, rs, t.z, cv, iv, is0, is1);
+        quad_item<T>(g, qc, rs, t.w, cv, iv, is0, is1);
+        const bool odd = (l & 1) != 0;  // lists owned by y / a_y
+        dc += odd ? -cv : cv;
+        di += iv * (odd ? coefy : coefx);
+        // what meeting sp0 / sp1 in this list means (0 = contributes nothing)
+        if (is0) seen |= l == 0 ? kSeenXinX : l == 2 ? kSeenAXinAX : 0;
+        if (is1) seen |= l == 1 ? kSeenYinY : l == 2 ? kSeenAYinAX : l == 3 ? kSeenAYinAY : 0;
     }
 }
 
@@ -331,31 +501,35 @@ __device__ __forceinline__ void undo_accumulators(const Scalars& after, const Sc
     goc = (after.goc + (-d.dgx)) + (-d.dgy);
 }
 
-// accept test, localSearch.cpp:35-47.  obj == -2: unconditional (ona_apply_swaps)
-__device__ __forceinline__ bool accept_move(const DevObjectives& ob, int obj, const double* cur,
-                                            const double* nw) {
-    if (obj == -2) return true;
-    bool improved = true;
-    if (obj == -1) {
-        for (int j = 0; j < ob.M; ++j)
-            if (nw[j] < cur[j]) improved = false;
-    } else {
-        if (nw[obj] <= cur[obj]) improved = false;
-    }
-    return improved;
-}
-
-// swapNormalizedDelta's return value, localSearch.cpp:98-119
-__device__ __forceinline__ double normalized_delta(const DevObjectives& ob, const double* cur,
-                                                   const double* nw) {
-    bool oneNeg = false;
+// computeFitness on the swapped state + the accept test of correctHillClimb
+// (localSearch.cpp:35-47) + swapNormalizedDelta's return value (:98-119), one objective at a
+// time so that no objective vector has to live in registers or local memory.
+//   obj == -1: accept iff no objective decreased; obj = j: iff objective j strictly increased;
+//   obj == -2: unconditional (ona_apply_swaps).
+//   curfit: the current state's objectives (any address space), or nullptr to derive them
+//           from `cur`;  fit_out (nullable): receives the new objectives.
+__device__ __forceinline__ bool judge_move(const DevObjectives& ob, int obj, const Scalars& cur,
+                                           const double* curfit, const Scalars& nw,
+                                           unsigned long long E1, double* fit_out, bool want_snd,
+                                           double& snd) {
+    bool any_lt = false, obj_le = false, oneNeg = false;
     double sumSq = 0.0;
     for (int j = 0; j < ob.M; ++j) {
-        double pct = (nw[j] - cur[j]) / cur[j];
-        if (pct < 0) oneNeg = true;
-        sumSq += pct * pct;
+        const int name = ob.names[j];
+        const double fn = objective(name, nw, E1);
+        const double fc = curfit ? curfit[j] : objective(name, cur, E1);
+        if (fit_out) fit_out[j] = fn;
+        if (fn < fc) any_lt = true;
+        if (j == obj && fn <= fc) obj_le = true;
+        if (want_snd) {
+            const double pct = (fn - fc) / fc;
+            if (pct < 0) oneNeg = true;
+            sumSq += pct * pct;
+        }
     }
-    return oneNeg ? -1.0 : sqrt(sumSq);
+    snd = want_snd ? (oneNeg ? -1.0 : sqrt(sumSq)) : 0.0;
+    if (obj == -2) return true;
+    return obj == -1 ? !any_lt : !obj_le;
 }
 
 // ------------------------------------------------------------- smem staging
@@ -391,5 +565,30 @@ __device__ __forceinline__ void unstage_state(const DevPop& pop, int p, const T*
         gi[i] = (b & MASK) | ((b & FLAG) ? kGFlag : 0u);
     }
 }
+
+// Where one individual's packed state lives while a CTA works on it:
+//   uint16_t : staged into shared memory (n2 < 32768; 4*n2 bytes), written back on release
+//   uint32_t : used in place in HBM/L2 (any n2); same flag layout as the global arrays
+template <typename T> struct State;
+template <> struct State<uint16_t> {
+    __device__ static __forceinline__ void acquire(const DevPop& pop, int p, int n2,
+                                                   unsigned char* smem, uint16_t*& a, uint16_t*& i) {
+        a = reinterpret_cast<uint16_t*>(smem);
+        i = a + pop.n2p;
+        stage_state<uint16_t>(pop, p, n2, a, i);
+    }
+    __device__ static __forceinline__ void release(const DevPop& pop, int p, const uint16_t* a,
+                                                   const uint16_t* i) {
+        unstage_state<uint16_t>(pop, p, a, i);
+    }
+};
+template <> struct State<uint32_t> {
+    __device__ static __forceinline__ void acquire(const DevPop& pop, int p, int, unsigned char*,
+                                                   uint32_t*& a, uint32_t*& i) {
+        a = pop.aln + (size_t)p * pop.n2p;
+        i = pop.inv + (size_t)p * pop.n2p;
+    }
+    __device__ static __forceinline__ void release(const DevPop&, int, const uint32_t*, const uint32_t*) {}
+};
 
 }  // namespace ona

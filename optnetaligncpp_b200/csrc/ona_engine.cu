@@ -64,7 +64,8 @@ struct ona_engine {
     DevTable S{}, G{};
     DevObjectives ob{};
     bool small_ids = false;  // n2 < 32768: uint16 shared-memory state
-    int group = 8;           // lanes per candidate in phase 1
+    int group = 8;           // lanes per candidate in the hill-climb kernel's phase 1
+    int delta_group = -1;    // swap-delta kernel: -1 = degree-sorted (default), 0 = flat walk, else lanes per candidate
     int sm_count = 148;
     size_t smem_optin = 0;
 
@@ -198,7 +199,8 @@ int build_table(ona_engine* e, const ona_score_table& t, int n1, int n2, DevTabl
 }
 
 size_t state_smem(const ona_engine* e) {
-    return (size_t)2 * (size_t)e->pop.n2p * (e->small_ids ? 2 : 4);
+    // uint16 state is staged in shared memory; wider ids are used in place in HBM/L2
+    return e->small_ids ? (size_t)2 * (size_t)e->pop.n2p * 2 : 0;
 }
 
 int check_range(ona_engine* e, int first, int count) {
@@ -246,9 +248,41 @@ int launch_deltas_tg(ona_engine* e, int first, int count, int K, const int* xy_d
 }
 
 template <typename T>
+int launch_deltas_flat(ona_engine* e, int first, int count, int K, const int* xy_dev,
+                       unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
+    const size_t smem = state_smem(e);
+    int rc = set_smem(k_swap_deltas_flat<T>, smem);
+    if (rc) return rc;
+    dim3 grid(chunks, count);
+    k_swap_deltas_flat<T><<<grid, kFlatWarps * 32, smem, e->stream>>>(
+        e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag);
+    e->launches++;
+    CU(cudaGetLastError());
+    return ONA_OK;
+}
+
+template <typename T>
+int launch_deltas_sorted(ona_engine* e, int first, int count, int K, const int* xy_dev,
+                         unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
+    const size_t smem = state_smem(e);
+    int rc = set_smem(k_swap_deltas_sorted<T>, smem);
+    if (rc) return rc;
+    dim3 grid(chunks, count);
+    k_swap_deltas_sorted<T><<<grid, kSortThreads, smem, e->stream>>>(
+        e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag);
+    e->launches++;
+    CU(cudaGetLastError());
+    return ONA_OK;
+}
+
+template <typename T>
 int launch_deltas_t(ona_engine* e, int first, int count, int K, const int* xy_dev,
                     unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
-    switch (e->group) {
+    if (e->delta_group == -1)
+        return launch_deltas_sorted<T>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+    if (e->delta_group == 0)
+        return launch_deltas_flat<T>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+    switch (e->delta_group) {
         case 1: return launch_deltas_tg<T, 1>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
         case 4: return launch_deltas_tg<T, 4>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
         case 16: return launch_deltas_tg<T, 16>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
@@ -257,11 +291,17 @@ int launch_deltas_t(ona_engine* e, int first, int count, int K, const int* xy_de
     }
 }
 
-// chunks per individual so that the grid is a whole number of waves of resident CTAs
+// chunks per individual (grid.x).  The sorted kernel works in passes of kSortCap candidates,
+// so a chunk is a whole number of passes unless that would leave SMs idle.
 int pick_chunks(const ona_engine* e, int count, int K) {
     const size_t smem = state_smem(e) + 1024;
     int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, (e->smem_optin ? 233472 : 101376) / smem));
     const int resident = e->sm_count * per_sm;
+    if (e->delta_group == -1) {
+        int chunks = std::max(1, (K + kSortCap - 1) / kSortCap);
+        while ((long long)chunks * count < 2LL * e->sm_count && K / (chunks * 2) >= 64) chunks *= 2;
+        return chunks;
+    }
     int chunks = std::max(1, (2 * resident + count - 1) / count);
     const int max_chunks = std::max(1, (K + 255) / 256);  // at least one pass of 256 candidates per CTA
     chunks = std::min(chunks, max_chunks);
@@ -430,6 +470,44 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
         if ((rc = upload<int>(e, eu, &g.eu2))) return bail(rc);
         if ((rc = upload<int>(e, ev, &g.ev2))) return bail(rc);
     }
+    for (int net = 0; net < 2; ++net) {  // quad-padded CSR (rows padded with -1 to multiples of 4)
+        const int n = net ? pr->n2 : pr->n1;
+        const int* rp = net ? pr->rowptr2 : pr->rowptr1;
+        const int* col = net ? pr->col2 : pr->col1;
+        std::vector<int> rq(n + 1, 0);
+        std::vector<int4> cq;
+        for (int u = 0; u < n; ++u) {
+            rq[u] = (int)cq.size();
+            for (int k = rp[u]; k < rp[u + 1]; k += 4) {
+                int4 q = make_int4(-1, -1, -1, -1);
+                q.x = col[k];
+                if (k + 1 < rp[u + 1]) q.y = col[k + 1];
+                if (k + 2 < rp[u + 1]) q.z = col[k + 2];
+                if (k + 3 < rp[u + 1]) q.w = col[k + 3];
+                cq.push_back(q);
+            }
+        }
+        rq[n] = (int)cq.size();
+        if ((rc = upload<int>(e, rq, net ? &g.rq2 : &g.rq1))) return bail(rc);
+        if ((rc = upload<int4>(e, cq, net ? &g.cq2 : &g.cq1))) return bail(rc);
+    }
+    {  // neighbourhood signatures of net2
+        std::vector<uint4> sig(pr->n2, make_uint4(0, 0, 0, 0));
+        for (int u = 0; u < pr->n2; ++u)
+            for (int k = pr->rowptr2[u]; k < pr->rowptr2[u + 1]; ++k) {
+                const int v = pr->col2[k];
+                auto set = [&](int a, int b) {
+                    sig[a].x |= 1u << (b & 31);
+                    sig[a].y |= 1u << ((b >> 5) & 31);
+                    sig[a].z |= 1u << ((b >> 10) & 31);
+                };
+                set(u, v);
+                set(v, u);
+            }
+        if ((rc = upload<uint4>(e, sig, &g.sig2))) return bail(rc);
+    }
+    if ((size_t)pr->n2 * (size_t)g.W >= ((size_t)1 << 32))
+        return bail(fail(ONA_ERR_INVALID, "net2 bit matrix exceeds 2^32 words"));
     if ((rc = build_table(e, pr->bitscores, pr->n1, pr->n2, &e->S))) return bail(rc);
     if ((rc = build_table(e, pr->gocs, pr->n1, pr->n2, &e->G))) return bail(rc);
     e->ob.M = pr->num_objectives;
@@ -437,11 +515,10 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
 
     e->small_ids = pr->n2 < 32768;
     e->pop.n2p = (pr->n2 + 3) / 4 * 4;
-    if (state_smem(e) + 2048 > e->smem_optin)
-        return bail(fail(ONA_ERR_INVALID, "n2 too large for the shared-memory resident state"));
     if (const char* gs = getenv("ONA_GROUP")) {
         const int v = atoi(gs);
-        if (v == 1 || v == 4 || v == 8 || v == 16 || v == 32) e->group = v;
+        if (v == 4 || v == 8 || v == 16) e->group = v;
+        if (v == -1 || v == 0 || v == 1 || v == 4 || v == 8 || v == 16 || v == 32) e->delta_group = v;
     }
     if (cudaMalloc(&e->d_flag, sizeof(int)) != cudaSuccess) return bail(fail(ONA_ERR_CUDA, "cudaMalloc"));
     *out = e;

@@ -99,13 +99,12 @@ __global__ void __launch_bounds__(512)
 k_full_fitness(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first,
                int seed_mode, int sequential, double* __restrict__ seq_scratch, FullOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_aln = reinterpret_cast<T*>(smem_raw);
-    T* s_inv = s_aln + pop.n2p;
+    T *s_aln, *s_inv;
     __shared__ double red_d[32];
     __shared__ int red_i[32];
     constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
     const int pl = blockIdx.x, p = first + pl;
-    stage_state<T>(pop, p, g.n2, s_aln, s_inv);
+    State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
     __syncthreads();
 
     int c = 0, ind = 0, sz = 0;
@@ -235,19 +234,17 @@ k_swap_deltas(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop,
               const int* __restrict__ xy, unsigned long long seed, long long island_offset,
               int obj, DevDeltaOut out, DeltaSummary sum, int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_aln = reinterpret_cast<T*>(smem_raw);
-    T* s_inv = s_aln + pop.n2p;
+    T *s_aln, *s_inv;
     __shared__ double s_bestv[8];
     __shared__ long long s_besti[8];
     const int pl = blockIdx.y, p = first + pl;
-    stage_state<T>(pop, p, g.n2, s_aln, s_inv);
+    State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
 
     Scalars cur;
     cur.C = pop.cons[p]; cur.I = pop.ind[p]; cur.size = pop.size[p];
     cur.bits = pop.bits[p]; cur.goc = pop.goc[p];
-    double curfit[kMaxObj];
-#pragma unroll
-    for (int j = 0; j < kMaxObj; ++j) curfit[j] = j < ob.M ? objective(ob.names[j], cur, g.E1) : 0.0;
+    __shared__ double s_curfit[kMaxObj];
+    if (threadIdx.x < ob.M) s_curfit[threadIdx.x] = objective(ob.names[threadIdx.x], cur, g.E1);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -301,21 +298,18 @@ k_swap_deltas(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop,
         if (valid) {
             const ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, x, y);
             const Scalars nw = apply_delta(cur, my_dc, my_di, sd);
-            double nfit[kMaxObj];
-#pragma unroll
-            for (int j = 0; j < kMaxObj; ++j) nfit[j] = j < ob.M ? objective(ob.names[j], nw, g.E1) : 0.0;
-            const bool imp = accept_move(ob, obj, curfit, nfit);
             const size_t o = (size_t)pl * K + c;
+            const bool want_snd = out.snd || sum.block_best;
+            double v;
+            const bool imp = judge_move(ob, obj, cur, s_curfit, nw, g.E1,
+                                        out.fit ? out.fit + o * ob.M : nullptr, want_snd, v);
             if (out.cons) out.cons[o] = nw.C;
             if (out.ind) out.ind[o] = nw.I;
             if (out.bits) out.bits[o] = nw.bits;
             if (out.goc) out.goc[o] = nw.goc;
-            if (out.fit)
-                for (int j = 0; j < ob.M; ++j) out.fit[o * ob.M + j] = nfit[j];
             if (out.improved) out.improved[o] = imp ? 1 : 0;
             n_imp += imp ? 1 : 0;
-            if (out.snd || sum.block_best) {
-                const double v = normalized_delta(ob, curfit, nfit);
+            if (want_snd) {
                 if (out.snd) out.snd[o] = v;
                 if (v > bestv) { bestv = v; besti = c; }  // strict >, first wins (localSearch.cpp:141)
             }
@@ -336,6 +330,463 @@ k_swap_deltas(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop,
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int w = 1; w < nwarps; ++w) {
+                const double ov = s_bestv[w];
+                const long long oi = s_besti[w];
+                if (oi >= 0 && (besti < 0 || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
+            }
+            sum.block_best[(size_t)pl * gridDim.x + blockIdx.x] = bestv;
+            sum.block_arg[(size_t)pl * gridDim.x + blockIdx.x] = besti;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------
+// S1-S7, load-balanced form (the default): a warp takes 32 candidates at a time.
+//   A. one candidate per lane: images, masks and the <= 4 neighbour-list extents
+//      (N1(x), N1(y), and for real<->dummy swaps N2(a_x), N2(a_y));
+//   B. the 32 candidates' lists are concatenated into ONE flat item list that the warp
+//      walks 32 items per step -- consecutive lanes read consecutive CSR columns
+//      (coalesced), every lane is busy whatever the degree skew, and a hub costs the warp
+//      deg/32 steps instead of stalling one group for deg/G.  Per item: one CSR column
+//      load, one shared-memory gather of the packed state, two single-word probes of the
+//      L2-resident net2 bit matrix (or one alive test for the induced lists).  Item
+//      contributions are combined with a segmented warp scan and accumulated per candidate;
+//   C. one candidate per lane again: <= 8 score-table lookups, objectives in the
+//      reference's fp64 order, accept bit, coalesced stores.
+// --------------------------------------------------------------------------------
+struct __align__(16) CandRec {
+    int offs;            // first flat item of this candidate
+    int e0, e1, e2;      // list ends inside the candidate: [0,e0) N1(x) [e0,e1) N1(y) [e1,e2) N2(a_x) [e2,..) N2(a_y)
+    int b0, b1, b2, b3;  // CSR start of each list minus the list's first item index: k = b[l] + j
+    int x, y;
+    uint32_t ax, ay;     // images, bit 31 set = mask bit off
+};
+
+#ifndef ONA_FLAT_WARPS
+#define ONA_FLAT_WARPS 8
+#endif
+#ifndef ONA_FLAT_MINBLOCKS
+#define ONA_FLAT_MINBLOCKS 4
+#endif
+constexpr int kFlatWarps = ONA_FLAT_WARPS;
+
+template <typename T>
+__global__ void __launch_bounds__(kFlatWarps * 32, ONA_FLAT_MINBLOCKS)
+k_swap_deltas_flat(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first, int K,
+                   const int* __restrict__ xy, unsigned long long seed, long long island_offset,
+                   int obj, DevDeltaOut out, DeltaSummary sum, int* __restrict__ err_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ CandRec s_rec_all[kFlatWarps][32];
+    __shared__ int2 s_acc_all[kFlatWarps][32];
+    __shared__ unsigned char s_r2c_all[kFlatWarps][32];
+    __shared__ double s_bestv[kFlatWarps];
+    __shared__ long long s_besti[kFlatWarps];
+    constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
+    T *s_aln, *s_inv;
+    const int pl = blockIdx.y, p = first + pl;
+    State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
+
+    Scalars cur;
+    cur.C = pop.cons[p]; cur.I = pop.ind[p]; cur.size = pop.size[p];
+    cur.bits = pop.bits[p]; cur.goc = pop.goc[p];
+    __shared__ double s_curfit[kMaxObj];
+    if (threadIdx.x < ob.M) s_curfit[threadIdx.x] = objective(ob.names[threadIdx.x], cur, g.E1);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    CandRec* s_rec = s_rec_all[warp];
+    int2* s_acc = s_acc_all[warp];
+    unsigned char* s_r2c = s_r2c_all[warp];
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
+    const int per = (K + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(K, lo + per);
+    const unsigned long long ikey = rng_individual_key(seed, (unsigned long long)(island_offset + p));
+
+    int n_imp = 0;
+    double bestv = -2.0;
+    long long besti = -1;
+
+    for (int base = lo + warp * 32; base < hi; base += nwarps * 32) {
+        const int c = base + lane;
+        const bool valid = c < hi;
+        int x = 0, y = 0;
+        if (valid) {
+            if (xy) {
+                const int2 v = __ldg(reinterpret_cast<const int2*>(xy) + (size_t)pl * K + c);
+                x = v.x; y = v.y;
+                if ((unsigned)x >= (unsigned)g.n2 || (unsigned)y >= (unsigned)g.n2) {
+                    atomicOr(err_flag, 1);  // reported by the host entry point as ONA_ERR_INVALID
+                    x = 0; y = 0;
+                }
+            } else {
+                rng_proposal(ikey, (unsigned long long)c, g.n1, g.n2, x, y);
+            }
+        }
+        // ---- A: per-lane candidate record
+        const uint32_t rx = s_aln[x], ry = s_aln[y];
+        const int ax = (int)(rx & MASK), ay = (int)(ry & MASK);
+        const int mx = (rx & FLAG) ? 0 : 1, my = (ry & FLAG) ? 0 : 1;
+        const bool xr = x < g.n1, yr = y < g.n1;
+        const int Lx_old = (xr ? 1 : 0) & mx, Lx_new = (yr ? 1 : 0) & mx;
+        const int Ly_old = (yr ? 1 : 0) & my, Ly_new = (xr ? 1 : 0) & my;
+        int b0 = 0, b1 = 0, b2 = 0, b3 = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+        if (x != y) {  // doSwap(x,x): every term cancels
+            if (xr) { b0 = __ldg(g.rp1 + x); d0 = __ldg(g.rp1 + x + 1) - b0; }
+            if (yr) { b1 = __ldg(g.rp1 + y); d1 = __ldg(g.rp1 + y + 1) - b1; }
+            if (Lx_old != Lx_new || Ly_old != Ly_new) {  // else the induced subgraph is unchanged
+                b2 = __ldg(g.rp2 + ax); d2 = __ldg(g.rp2 + ax + 1) - b2;
+                b3 = __ldg(g.rp2 + ay); d3 = __ldg(g.rp2 + ay + 1) - b3;
+            }
+        }
+        const int tot = d0 + d1 + d2 + d3;
+        int incl = tot;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+        }
+        const int offs = incl - tot;
+        const int T_items = __shfl_sync(0xffffffffu, incl, 31);
+        const bool nonempty = tot > 0;
+        const unsigned nemask = __ballot_sync(0xffffffffu, nonempty);
+        if (nonempty) s_r2c[__popc(nemask & lt_mask)] = (unsigned char)lane;
+        {
+            CandRec r;
+            r.offs = offs; r.e0 = d0; r.e1 = d0 + d1; r.e2 = d0 + d1 + d2;
+            r.b0 = b0; r.b1 = b1 - r.e0; r.b2 = b2 - r.e1; r.b3 = b3 - r.e2;
+            r.x = x; r.y = y;
+            r.ax = (uint32_t)ax | (mx ? 0u : kGFlag);
+            r.ay = (uint32_t)ay | (my ? 0u : kGFlag);
+            int4* dst = reinterpret_cast<int4*>(&s_rec[lane]);
+            dst[0] = make_int4(r.offs, r.e0, r.e1, r.e2);
+            dst[1] = make_int4(r.b0, r.b1, r.b2, r.b3);
+            dst[2] = make_int4(r.x, r.y, (int)r.ax, (int)r.ay);
+        }
+        s_acc[lane] = make_int2(0, 0);
+        __syncwarp();
+
+        // ---- B: flat item walk, 32 items per step
+        int base_rank = 0;
+        for (int it0 = 0; it0 < T_items; it0 += 32) {
+            const int it = it0 + lane;
+            const unsigned sb = (nonempty && offs >= it0 && offs < it0 + 32) ? (1u << (offs - it0)) : 0u;
+            const unsigned wm = __reduce_or_sync(0xffffffffu, sb);  // candidates starting in this window
+            int contrib = 0, cand = 0;
+            if (it < T_items) {
+                cand = s_r2c[base_rank + __popc(wm & le_mask) - 1];
+                const int4* src = reinterpret_cast<const int4*>(&s_rec[cand]);
+                const int4 q0 = src[0], q1 = src[1], q2 = src[2];
+                const int j = it - q0.x;
+                const int l = (j >= q0.y ? 1 : 0) + (j >= q0.z ? 1 : 0) + (j >= q0.w ? 1 : 0);
+                const int k = (l == 0 ? q1.x : l == 1 ? q1.y : l == 2 ? q1.z : q1.w) + j;
+                const int v = __ldg((l < 2 ? g.col1 : g.col2) + k);
+                const int cx = q2.x, cy = q2.y;
+                const int cax = (int)((uint32_t)q2.z & kGMask), cay = (int)((uint32_t)q2.w & kGMask);
+                const int cmx = ((uint32_t)q2.z & kGFlag) ? 0 : 1, cmy = ((uint32_t)q2.w & kGFlag) ? 0 : 1;
+                if (l < 2) {
+                    // conservedCount terms, Alignment.cpp:799-803, before and after the exchange
+                    const uint32_t rt = s_aln[v];
+                    const int it_ = (int)(rt & MASK), mt = (rt & FLAG) ? 0 : 1;
+                    int it2 = it_, mt2 = mt;
+                    if (v == cx) { it2 = cay; mt2 = cmy; }
+                    else if (v == cy) { it2 = cax; mt2 = cmx; }
+                    const int rowO = l == 0 ? cax : cay, rowN = l == 0 ? cay : cax;
+                    const int mO = l == 0 ? cmx : cmy, mN = l == 0 ? cmy : cmx;
+                    const int o = mO & mt & probe(g, rowO, it_);
+                    const int n = mN & mt2 & probe(g, rowN, it2);
+                    contrib = (l == 1 && v == cx) ? 0 : (n - o);  // ignore = x (:493,:507)
+                } else {
+                    // inducedCount terms, Alignment.cpp:818-822
+                    const bool cxr = cx < g.n1, cyr = cy < g.n1;
+                    const int cLx_old = (cxr ? 1 : 0) & cmx, cLx_new = (cyr ? 1 : 0) & cmx;
+                    const int cLy_old = (cyr ? 1 : 0) & cmy, cLy_new = (cxr ? 1 : 0) & cmy;
+                    const int ao = ((uint32_t)s_inv[v] < (uint32_t)g.n1) ? 1 : 0;
+                    const int an = (v == cax) ? cLx_new : (v == cay) ? cLy_new : ao;
+                    int d;
+                    if (l == 2) d = (cLx_new & an) - (cLx_old & ao);
+                    else d = (v == cax) ? 0 : ((cLy_new & an) - (cLy_old & ao));  // ignore = a_x (:495,:510)
+                    contrib = d << 16;
+                }
+            }
+            base_rank += __popc(wm);
+            // segmented inclusive scan of the packed (dcons | dind << 16) contributions
+            const unsigned heads = wm | 1u;
+            const int seg_start = 31 - __clz((int)(heads & le_mask));
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, contrib, off);
+                if (lane - off >= seg_start) contrib += o;
+            }
+            const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u) || (it + 1 >= T_items);
+            if (it < T_items && tail) {
+                const int dc = (int)(short)(contrib & 0xffff);
+                const int di = (contrib - dc) >> 16;
+                int2 a = s_acc[cand];
+                a.x += dc; a.y += di;
+                s_acc[cand] = a;
+            }
+            __syncwarp();
+        }
+        const int2 accv = s_acc[lane];
+        const int my_dc = accv.x, my_di = accv.y;
+        __syncwarp();
+
+        // ---- C: one candidate per lane
+        if (valid) {
+            const ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, x, y);
+            const Scalars nw = apply_delta(cur, my_dc, my_di, sd);
+            const size_t o = (size_t)pl * K + c;
+            const bool want_snd = out.snd || sum.block_best;
+            double v;
+            const bool imp = judge_move(ob, obj, cur, s_curfit, nw, g.E1,
+                                        out.fit ? out.fit + o * ob.M : nullptr, want_snd, v);
+            if (out.cons) out.cons[o] = nw.C;
+            if (out.ind) out.ind[o] = nw.I;
+            if (out.bits) out.bits[o] = nw.bits;
+            if (out.goc) out.goc[o] = nw.goc;
+            if (out.improved) out.improved[o] = imp ? 1 : 0;
+            n_imp += imp ? 1 : 0;
+            if (want_snd) {
+                if (out.snd) out.snd[o] = v;
+                if (v > bestv) { bestv = v; besti = c; }  // strict >, first wins (localSearch.cpp:141)
+            }
+        }
+    }
+    if (sum.num_improved) {
+        n_imp = warp_sum<int>(n_imp);
+        if (lane == 0 && n_imp) atomicAdd(sum.num_improved + pl, n_imp);
+    }
+    if (sum.block_best) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bestv, off);
+            const long long oi = __shfl_xor_sync(0xffffffffu, besti, off);
+            if (oi >= 0 && (besti < 0 || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
+        }
+        if (lane == 0) { s_bestv[warp] = bestv; s_besti[warp] = besti; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < nwarps; ++w) {
+                const double ov = s_bestv[w];
+                const long long oi = s_besti[w];
+                if (oi >= 0 && (besti < 0 || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
+            }
+            sum.block_best[(size_t)pl * gridDim.x + blockIdx.x] = bestv;
+            sum.block_arg[(size_t)pl * gridDim.x + blockIdx.x] = besti;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------
+// S1-S7, degree-sorted form (the default).  PPI degree distributions are heavy-tailed
+// (median 6, max ~250 here), so candidates of one warp have wildly different amounts of
+// neighbour-list work.  Each CTA therefore takes a pass of kSortCap candidates of its
+// individual and
+//   A. (one candidate per thread, original order) draws/loads (x,y) and counts the candidate's
+//      work in quads of four neighbours (four rowptr pairs);
+//   B. counting-sorts the pass by that count, longest first (18 bins, warp-ballot ranks --
+//      no shared-memory atomics);
+//   C. walks the lists ONE CANDIDATE PER THREAD in sorted order, so that the 32 lanes of a
+//      warp run loops of (almost) equal length; the few hubs (> kHubQuads quads) are walked
+//      by whole warps instead.  Rows are quad-padded, so every neighbour fetch is one 128-bit
+//      load feeding four independent gather -> probe chains (memory-level parallelism
+//      without unrolling); gathers hit the shared-memory copy of the individual, adjacency
+//      tests are single-word probes of the L2-resident bit matrix;
+//   D. (one candidate per thread, original order again) <= 8 score-table lookups, objectives
+//      in the reference's fp64 order, accept bit, coalesced stores.
+// --------------------------------------------------------------------------------
+#ifndef ONA_SORT_THREADS
+#define ONA_SORT_THREADS 512
+#endif
+#ifndef ONA_SORT_PER_THREAD
+#define ONA_SORT_PER_THREAD 2
+#endif
+#ifndef ONA_SORT_MINBLOCKS
+#define ONA_SORT_MINBLOCKS 2
+#endif
+constexpr int kSortThreads = ONA_SORT_THREADS;
+constexpr int kSortPer = ONA_SORT_PER_THREAD;
+constexpr int kSortCap = kSortThreads * kSortPer;  // candidates per CTA pass
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kHubQuads = 16;                      // more quads than this: walked by a whole warp
+constexpr int kSortBins = kHubQuads + 2;           // 0..kHubQuads exact, last bin = hubs
+
+template <typename T>
+__global__ void __launch_bounds__(kSortThreads, ONA_SORT_MINBLOCKS)
+k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first, int K,
+                     const int* __restrict__ xy, unsigned long long seed, long long island_offset,
+                     int obj, DevDeltaOut out, DeltaSummary sum, int* __restrict__ err_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int2 s_xy[kSortCap];                 // proposals of this pass, original order
+    __shared__ int2 s_res[kSortCap];                // (dcons, dind), original order
+    __shared__ unsigned short s_order[kSortCap];    // sorted position -> candidate
+    __shared__ unsigned short s_cnt[kSortWarps * kSortPer][kSortBins];  // per (virtual) warp histogram
+    __shared__ int s_nhub, s_next;
+    __shared__ double s_curfit[kMaxObj];
+    __shared__ double s_bestv[kSortWarps];
+    __shared__ long long s_besti[kSortWarps];
+    T *s_aln, *s_inv;
+    const int pl = blockIdx.y, p = first + pl;
+    State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
+
+    Scalars cur;
+    cur.C = pop.cons[p]; cur.I = pop.ind[p]; cur.size = pop.size[p];
+    cur.bits = pop.bits[p]; cur.goc = pop.goc[p];
+    if (threadIdx.x < ob.M) s_curfit[threadIdx.x] = objective(ob.names[threadIdx.x], cur, g.E1);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int per = (K + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(K, lo + per);
+    const unsigned long long ikey = rng_individual_key(seed, (unsigned long long)(island_offset + p));
+
+    int n_imp = 0;
+    double bestv = -2.0;
+    long long besti = -1;
+
+    for (int pass = lo; pass < hi; pass += kSortCap) {
+        const int n = min(kSortCap, hi - pass);
+        // ---- A: proposals + work count; per-virtual-warp histogram by ballots
+        int key[kSortPer], rank[kSortPer];
+#pragma unroll
+        for (int j = 0; j < kSortPer; ++j) {
+            const int i = j * kSortThreads + threadIdx.x;  // index inside the pass
+            const int c = pass + i;
+            int x = 0, y = 0;
+            if (i < n) {
+                if (xy) {
+                    const int2 v = __ldg(reinterpret_cast<const int2*>(xy) + (size_t)pl * K + c);
+                    x = v.x; y = v.y;
+                    if ((unsigned)x >= (unsigned)g.n2 || (unsigned)y >= (unsigned)g.n2) {
+                        atomicOr(err_flag, 1);  // reported by the host entry point as ONA_ERR_INVALID
+                        x = 0; y = 0;
+                    }
+                } else {
+                    rng_proposal(ikey, (unsigned long long)c, g.n1, g.n2, x, y);
+                }
+                s_xy[i] = make_int2(x, y);
+            }
+            const SwapCtx cx = make_ctx<T>(g, s_aln, x, y);
+            const int k = i < n ? min(make_plan(g, cx).e3, kSortBins - 1) : -1;
+            key[j] = k;
+            int r = 0;
+#pragma unroll
+            for (int b = 0; b < kSortBins; ++b) {
+                const unsigned m = __ballot_sync(0xffffffffu, k == b);
+                if (k == b) r = __popc(m & lt_mask);
+                if (lane == 0) s_cnt[j * kSortWarps + warp][b] = (unsigned short)__popc(m);
+            }
+            rank[j] = r;
+        }
+        __syncthreads();
+        // ---- B: exclusive scan over (bin descending, virtual warp ascending) by warp 0
+        if (warp == 0) {
+            int running = 0;
+            constexpr int NV = kSortWarps * kSortPer;
+            for (int b = kSortBins - 1; b >= 0; --b) {
+                for (int v0 = 0; v0 < NV; v0 += 32) {
+                    const int v = v0 + lane;
+                    const int cnt = v < NV ? (int)s_cnt[v][b] : 0;
+                    int incl = cnt;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, incl, off);
+                        if (lane >= off) incl += o;
+                    }
+                    if (v < NV) s_cnt[v][b] = (unsigned short)(running + incl - cnt);
+                    running += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (b == kSortBins - 1 && lane == 0) { s_nhub = running; s_next = 0; }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kSortPer; ++j) {
+            const int i = j * kSortThreads + threadIdx.x;
+            if (key[j] >= 0) s_order[(int)s_cnt[j * kSortWarps + warp][key[j]] + rank[j]] = (unsigned short)i;
+        }
+        __syncthreads();
+        // ---- C: walk.  Warps pull work units, longest first: a hub (walked by the whole warp)
+        //      or 32 consecutive sorted candidates (one per lane, equal loop lengths)
+        const int nhub = s_nhub;
+        for (;;) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(&s_next, 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u < nhub) {
+                const int i = s_order[u];
+                const int2 q = s_xy[i];
+                const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
+                const QuadPlan pl4 = make_plan(g, cx);
+                int dc, di, seen;
+                walk_plan<T>(g, s_aln, s_inv, cx, pl4, lane, 32, dc, di, seen);
+                dc = warp_sum<int>(dc);
+                di = warp_sum<int>(di);
+                seen = __reduce_or_sync(0xffffffffu, (unsigned)seen);
+                if (lane == 0) {
+                    special_terms(g, cx, seen, dc, di);
+                    s_res[i] = make_int2(dc, di);
+                }
+                continue;
+            }
+            const int pos = nhub + (u - nhub) * 32 + lane;
+            if (pos - lane >= n) break;
+            if (pos < n) {
+                const int i = s_order[pos];
+                const int2 q = s_xy[i];
+                const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
+                const QuadPlan pl4 = make_plan(g, cx);
+                int dc, di, seen;
+                walk_plan<T>(g, s_aln, s_inv, cx, pl4, 0, 1, dc, di, seen);
+                if (seen) special_terms(g, cx, seen, dc, di);
+                s_res[i] = make_int2(dc, di);
+            }
+        }
+        __syncthreads();
+        // ---- D: scores, objectives, outputs -- original order, coalesced
+#pragma unroll
+        for (int j = 0; j < kSortPer; ++j) {
+            const int i = j * kSortThreads + threadIdx.x;
+            if (i >= n) continue;
+            const int c = pass + i;
+            const int2 q = s_xy[i];
+            const int2 r = s_res[i];
+            const ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, q.x, q.y);
+            const Scalars nw = apply_delta(cur, r.x, r.y, sd);
+            const size_t o = (size_t)pl * K + c;
+            const bool want_snd = out.snd || sum.block_best;
+            double v;
+            const bool imp = judge_move(ob, obj, cur, s_curfit, nw, g.E1,
+                                        out.fit ? out.fit + o * ob.M : nullptr, want_snd, v);
+            if (out.cons) out.cons[o] = nw.C;
+            if (out.ind) out.ind[o] = nw.I;
+            if (out.bits) out.bits[o] = nw.bits;
+            if (out.goc) out.goc[o] = nw.goc;
+            if (out.improved) out.improved[o] = imp ? 1 : 0;
+            n_imp += imp ? 1 : 0;
+            if (want_snd) {
+                if (out.snd) out.snd[o] = v;
+                if (v > bestv || (v == bestv && c < besti)) { bestv = v; besti = c; }  // first wins (localSearch.cpp:141)
+            }
+        }
+        __syncthreads();
+    }
+    if (sum.num_improved) {
+        n_imp = warp_sum<int>(n_imp);
+        if (lane == 0 && n_imp) atomicAdd(sum.num_improved + pl, n_imp);
+    }
+    if (sum.block_best) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bestv, off);
+            const long long oi = __shfl_xor_sync(0xffffffffu, besti, off);
+            if (oi >= 0 && (besti < 0 || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
+        }
+        if (lane == 0) { s_bestv[warp] = bestv; s_besti[warp] = besti; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < kSortWarps; ++w) {
                 const double ov = s_bestv[w];
                 const long long oi = s_besti[w];
                 if (oi >= 0 && (besti < 0 || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
@@ -370,14 +821,13 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
              unsigned char* __restrict__ accepted, long long* __restrict__ num_accepted,
              int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_aln = reinterpret_cast<T*>(smem_raw);
-    T* s_inv = s_aln + pop.n2p;
+    T *s_aln, *s_inv;
     __shared__ int s_x[kRound], s_y[kRound], s_dc[kRound], s_di[kRound];
     __shared__ long long s_pos;
     constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
 
     const int pl = blockIdx.x, p = first + pl;
-    stage_state<T>(pop, p, g.n2, s_aln, s_inv);
+    State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
     if (threadIdx.x == 0) s_pos = 0;
     const int obj = force_obj != -3 ? force_obj : (objs ? objs[pl] : -1);
     const unsigned long long ikey = rng_individual_key(seed, (unsigned long long)(island_offset + p));
@@ -429,14 +879,9 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
             ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, valid ? x : 0, valid ? y : 0);
             int start = 0, consumed = nvalid, acc_lane = -1;
             for (;;) {
-                double curfit[kMaxObj], nfit[kMaxObj];
                 const Scalars nw = apply_delta(cur, dc, di, sd);
-#pragma unroll
-                for (int j = 0; j < kMaxObj; ++j) {
-                    curfit[j] = j < ob.M ? objective(ob.names[j], cur, g.E1) : 0.0;
-                    nfit[j] = j < ob.M ? objective(ob.names[j], nw, g.E1) : 0.0;
-                }
-                const bool acc = accept_move(ob, obj, curfit, nfit);
+                double unused;
+                const bool acc = judge_move(ob, obj, cur, nullptr, nw, g.E1, nullptr, false, unused);
                 double ub, ug;
                 undo_accumulators(nw, sd, ub, ug);
                 const bool pert = !acc && (__double_as_longlong(ub) != __double_as_longlong(cur.bits) ||
@@ -475,7 +920,8 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
         __syncthreads();
     }
     // write the individual back
-    unstage_state<T>(pop, p, s_aln, s_inv);
+    __syncthreads();
+    State<T>::release(pop, p, s_aln, s_inv);
     if (threadIdx.x == 0) {
         pop.cons[p] = cur.C; pop.ind[p] = cur.I; pop.size[p] = cur.size;
         pop.bits[p] = cur.bits; pop.goc[p] = cur.goc;
