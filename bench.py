@@ -166,6 +166,18 @@ class CpuArm:
         t, _ = self.mod.time_swap_deltas(self.alns, OBJECTIVES, xy, self.threads)
         return t
 
+    def hill_climb(self, iters):
+        """correctHillClimb on independent individuals, one per thread at a time (worker pattern of
+        steadystate.cpp:132-253); the individuals are private copies."""
+        n = max(self.threads, len(self.alns))
+        copies = [self.alns[i % len(self.alns)].clone() for i in range(n)]
+        if self.kind == "reference":
+            t = self.mod.time_hill_climb(copies, OBJECTIVES, 11, iters, -1, self.threads)
+        else:
+            xy = synth.random_candidates(self.pair, n, iters, seed=11)
+            t = self.mod.time_hill_climb(copies, OBJECTIVES, xy, iters, -1, self.threads)
+        return n * iters / t
+
     def full_fitness(self, reps):
         if self.kind == "reference":
             t_ics, _ = self.mod.time_full_fitness(self.alns, OBJECTIVES, reps, self.threads, True)
@@ -293,10 +305,10 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 10))
     xy_host = [torch.from_numpy(synth.random_candidates(pair, P, K, seed=50 + i)).pin_memory()
                for i in range(2)]
-    h_out = dict(cons=torch.empty((P, K), dtype=torch.int32).pin_memory().numpy(),
-                 ind=torch.empty((P, K), dtype=torch.int32).pin_memory().numpy(),
-                 fit=torch.empty((P, K, M), dtype=torch.float64).pin_memory().numpy(),
-                 improved=torch.empty((P, K), dtype=torch.uint8).pin_memory().numpy())
+    # what the reference's own API returns per candidate: the accept decision of correctHillClimb
+    # (localSearch.cpp:35-47) and swapNormalizedDelta's double (:88-120)
+    h_out = dict(improved=torch.empty((P, K), dtype=torch.uint8).pin_memory().numpy(),
+                 snd=torch.empty((P, K), dtype=torch.float64).pin_memory().numpy())
     for i in range(2):
         e.swap_deltas(xy_host[i % 2].numpy(), obj=-1, out=h_out)
     barrier()
@@ -310,6 +322,22 @@ def run_ours(args):
     e2e_value = world * P * K * e2e_steps / float(e2e_t.item())
     h2d = P * K * 2 * 4
     d2h = sum(v.nbytes for v in h_out.values())
+
+    # ---- correctHillClimb (sequential-exact semantics), device proposals, on a scratch copy
+    hc_iters = 20000
+    e.upload(aln)
+    e.full_fitness_dev(seed_mode=engine.SEED_REFCOMPAT)
+    e.hill_climb(iters=2000, seed=1)                       # warm-up
+    hc_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    hc_ev[0].record(stream)
+    _, hc_nacc = e.hill_climb(iters=hc_iters, seed=2)
+    hc_ev[1].record(stream)
+    barrier()
+    hc_ms = torch.tensor([hc_ev[0].elapsed_time(hc_ev[1])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(hc_ms, op=dist.ReduceOp.MAX)
+    hc_ms = float(hc_ms.item())
 
     if rank == 0:
         peak, peak_kind = hbm_peak()
@@ -339,13 +367,17 @@ def run_ours(args):
                          "units_per_launch": P * K, "kernel_ms": k_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "call": "ona_swap_deltas (host proposals -> conserved, induced, objectives, accept bit)"},
+                    "call": "ona_swap_deltas: pinned host proposals [P,K,2] int32 -> accept bit (u8) + swapNormalizedDelta (f64) per candidate, pinned host"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "full_fitness": {"value": world * P / (ff_ms * 1e-3), "unit": "full-fitness evals/s",
                              "kernel_ms": ff_ms, "algorithmic_bytes_per_eval": ff_bytes,
                              "achieved_gbs": ff_bytes * P / (ff_ms * 1e-3) / 1e9,
                              "frac": ff_bytes * P / (ff_ms * 1e-3) / 1e9 / peak},
+            "hill_climb": {"value": world * P * hc_iters / (hc_ms * 1e-3), "unit": "correctHillClimb iterations/s",
+                           "iters_per_individual": hc_iters, "ms": hc_ms,
+                           "accept_rate": float(hc_nacc.sum()) / (P * hc_iters),
+                           "semantics": "sequential-exact (bit-identical trajectory to the reference)"},
             "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -360,7 +392,8 @@ def run_ours(args):
                           "swapNormalizedDelta worker pattern (localSearch.cpp:130-147)" % (
                               n, arm.threads, len(arm.alns)),
                 "full_fitness_evals_per_sec_with_ics": ff_ics,
-                "full_fitness_evals_per_sec_adjacency_recount": ff_adj}
+                "full_fitness_evals_per_sec_adjacency_recount": ff_adj,
+                "hill_climb_iters_per_sec": arm.hill_climb(20000)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -56,8 +56,8 @@ struct DevGraph {
     const int* ev2;
     int ne1, ne2;
     unsigned long long E1;  // net1->edges.size()
-    // quad-padded CSR: every row padded with -1 to a multiple of 4 columns so that one 128-bit
-    // load fetches four neighbours; rq[u]..rq[u+1] index int4 quads
+    // quad-padded CSR: every row padded with the dummy id n2 to a multiple of 4 columns so that
+    // one 128-bit load fetches four neighbours; rq[u]..rq[u+1] index int4 quads
     const int* rq1;
     const int4* cq1;
     const int* rq2;
@@ -67,6 +67,9 @@ struct DevGraph {
     // are set.  A clear bit proves "not adjacent" without touching the bit matrix, and one
     // 16-byte signature serves all the tests against that row.
     const uint4* sig2;
+    const uint4* sig1;  // same for net1 (hill-climb conflict tests)
+    const uint32_t* adj1;  // net1 adjacency bit matrix [n1][W1] (hill-climb conflict tests)
+    int W1;
 };
 
 // BLASTDict / GOCDict on the device: dense fp64 matrix, or an open-addressing hash of the
@@ -89,7 +92,8 @@ struct DevObjectives {
 struct DevPop {
     uint32_t* aln;  // [P][n2p] packed
     uint32_t* inv;  // [P][n2p] packed
-    int n2p;        // row stride (n2 rounded up to a multiple of 4)
+    int n2p;        // row stride: n2 + 1 (slot n2 = the "masked off" dummy that pads CSR quads)
+                    // rounded up to a multiple of 4
     int* cons;      // currConservedCount
     int* ind;       // currInducedCount
     int* size;      // alnSize() as an integer
@@ -319,11 +323,12 @@ template <typename T>
 __device__ __forceinline__ void quad_item(const DevGraph& g, const QuadCtx& qc, const RowSig& rs, int t,
                                           int& cv, int& iv, bool& is0, bool& is1) {
     constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
-    const bool valid = t >= 0;  // t < 0: row padding
-    const uint32_t r = static_cast<const T*>(qc.table)[valid ? t : 0];
+    // row padding is the dummy id n2, whose packed entries are "masked off" in both tables, so
+    // it needs no test here: it is never live and never alive
+    const uint32_t r = static_cast<const T*>(qc.table)[t];
     is0 |= t == qc.sp0;
     is1 |= t == qc.sp1;
-    const bool plain = valid & (t != qc.sp0) & (t != qc.sp1);
+    const bool plain = (t != qc.sp0) & (t != qc.sp1);
     const unsigned it = r & MASK, h1 = it >> 5, h2 = it >> 10;  // shifts use the low 5 bits
     const bool live = plain & qc.cons & !(r & FLAG);
     const bool pX = live & ((((rs.sx.x >> (it & 31u)) & (rs.sx.y >> (h1 & 31u)) & (rs.sx.z >> (h2 & 31u))) & 1u) != 0u);

@@ -52,6 +52,8 @@ struct DevBuf {  // grow-only device scratch
 
 }  // namespace
 
+constexpr int kPipeSlices = 8;
+
 struct ona_engine {
     int device = 0;
     std::mutex mu;
@@ -79,6 +81,9 @@ struct ona_engine {
     DevBuf<unsigned char> t_u0, t_mask;
     DevBuf<long long> t_l0;
     int* d_flag = nullptr;
+    // copy streams + events of the host-buffer pipeline (ona_swap_deltas)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[kPipeSlices] = {}, ev_k[kPipeSlices] = {}, ev_out = nullptr;
 };
 
 namespace {
@@ -479,7 +484,7 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
         for (int u = 0; u < n; ++u) {
             rq[u] = (int)cq.size();
             for (int k = rp[u]; k < rp[u + 1]; k += 4) {
-                int4 q = make_int4(-1, -1, -1, -1);
+                int4 q = make_int4(pr->n2, pr->n2, pr->n2, pr->n2);  // dummy id: contributes nothing
                 q.x = col[k];
                 if (k + 1 < rp[u + 1]) q.y = col[k + 1];
                 if (k + 2 < rp[u + 1]) q.z = col[k + 2];
@@ -491,20 +496,33 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
         if ((rc = upload<int>(e, rq, net ? &g.rq2 : &g.rq1))) return bail(rc);
         if ((rc = upload<int4>(e, cq, net ? &g.cq2 : &g.cq1))) return bail(rc);
     }
-    {  // neighbourhood signatures of net2
-        std::vector<uint4> sig(pr->n2, make_uint4(0, 0, 0, 0));
-        for (int u = 0; u < pr->n2; ++u)
-            for (int k = pr->rowptr2[u]; k < pr->rowptr2[u + 1]; ++k) {
-                const int v = pr->col2[k];
-                auto set = [&](int a, int b) {
-                    sig[a].x |= 1u << (b & 31);
-                    sig[a].y |= 1u << ((b >> 5) & 31);
-                    sig[a].z |= 1u << ((b >> 10) & 31);
-                };
-                set(u, v);
-                set(v, u);
+    g.W1 = (pr->n1 + 31) / 32;
+    {
+        std::vector<uint32_t> bits((size_t)pr->n1 * g.W1, 0u);
+        for (int u = 0; u < pr->n1; ++u)
+            for (int k = pr->rowptr1[u]; k < pr->rowptr1[u + 1]; ++k) {
+                const int v = pr->col1[k];
+                bits[(size_t)u * g.W1 + (v >> 5)] |= 1u << (v & 31);
+                bits[(size_t)v * g.W1 + (u >> 5)] |= 1u << (u & 31);
             }
-        if ((rc = upload<uint4>(e, sig, &g.sig2))) return bail(rc);
+        if ((rc = upload<uint32_t>(e, bits, &g.adj1))) return bail(rc);
+    }
+    for (int net = 0; net < 2; ++net) {  // Bloom neighbourhood signatures (3 x 32 bits per node)
+        const int n = net ? pr->n2 : pr->n1;
+        const int* rp = net ? pr->rowptr2 : pr->rowptr1;
+        const int* col = net ? pr->col2 : pr->col1;
+        std::vector<uint4> sig(n, make_uint4(0, 0, 0, 0));
+        auto set = [&](int a, int b) {
+            sig[a].x |= 1u << (b & 31);
+            sig[a].y |= 1u << ((b >> 5) & 31);
+            sig[a].z |= 1u << ((b >> 10) & 31);
+        };
+        for (int u = 0; u < n; ++u)
+            for (int k = rp[u]; k < rp[u + 1]; ++k) {
+                set(u, col[k]);
+                set(col[k], u);
+            }
+        if ((rc = upload<uint4>(e, sig, net ? &g.sig2 : &g.sig1))) return bail(rc);
     }
     if ((size_t)pr->n2 * (size_t)g.W >= ((size_t)1 << 32))
         return bail(fail(ONA_ERR_INVALID, "net2 bit matrix exceeds 2^32 words"));
@@ -513,14 +531,22 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
     e->ob.M = pr->num_objectives;
     for (int j = 0; j < pr->num_objectives; ++j) e->ob.names[j] = pr->objectives[j];
 
-    e->small_ids = pr->n2 < 32768;
-    e->pop.n2p = (pr->n2 + 3) / 4 * 4;
+    e->small_ids = pr->n2 < 32767;  // ids 0..n2 (with the dummy) must leave bit 15 for the flag
+    e->pop.n2p = (pr->n2 + 1 + 3) / 4 * 4;  // + the dummy slot n2
     if (const char* gs = getenv("ONA_GROUP")) {
         const int v = atoi(gs);
         if (v == 4 || v == 8 || v == 16) e->group = v;
         if (v == -1 || v == 0 || v == 1 || v == 4 || v == 8 || v == 16 || v == 32) e->delta_group = v;
     }
     if (cudaMalloc(&e->d_flag, sizeof(int)) != cudaSuccess) return bail(fail(ONA_ERR_CUDA, "cudaMalloc"));
+    if (cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(ONA_ERR_CUDA, "stream/event creation failed"));
+    for (int i = 0; i < kPipeSlices; ++i)
+        if (cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming) != cudaSuccess)
+            return bail(fail(ONA_ERR_CUDA, "event creation failed"));
     *out = e;
     return ONA_OK;
 }
@@ -535,6 +561,13 @@ void ona_engine_destroy(ona_engine* e) {
     e->t_d0.release(); e->t_d1.release(); e->t_d2.release(); e->t_d3.release(); e->t_d4.release();
     e->t_seq.release(); e->t_u0.release(); e->t_mask.release(); e->t_l0.release();
     if (e->d_flag) cudaFree(e->d_flag);
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
+    if (e->ev_out) cudaEventDestroy(e->ev_out);
+    for (int i = 0; i < kPipeSlices; ++i) {
+        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+        if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]);
+    }
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -731,27 +764,58 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
     if (obj < -1 || obj >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
     if (count == 0 || K == 0) return ONA_OK;
     const size_t n = (size_t)count * K;
+    const int M = e->ob.M;
     LOCK(e);
     CU(e->t_xy.need(2 * n));
     CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
-    TRY(h2d(e, e->t_xy.p, xy, 2 * n));
     DevDeltaOut out{};
     if (cons) { CU(e->t_i0.need(n)); out.cons = e->t_i0.p; }
     if (ind) { CU(e->t_i1.need(n)); out.ind = e->t_i1.p; }
     if (bits) { CU(e->t_d0.need(n)); out.bits = e->t_d0.p; }
     if (goc) { CU(e->t_d1.need(n)); out.goc = e->t_d1.p; }
-    if (fitness) { CU(e->t_d3.need(n * e->ob.M)); out.fit = e->t_d3.p; }
+    if (fitness) { CU(e->t_d3.need(n * M)); out.fit = e->t_d3.p; }
     if (improved) { CU(e->t_u0.need(n)); out.improved = e->t_u0.p; }
     if (snd) { CU(e->t_d2.need(n)); out.snd = e->t_d2.p; }
     DeltaSummary sum{};
-    TRY(launch_deltas(e, first, count, K, e->t_xy.p, 0ull, obj, out, sum, pick_chunks(e, count, K)));
-    TRY(d2h(e, cons, out.cons, n));
-    TRY(d2h(e, ind, out.ind, n));
-    TRY(d2h(e, bits, out.bits, n));
-    TRY(d2h(e, goc, out.goc, n));
-    TRY(d2h(e, fitness, out.fit, n * e->ob.M));
-    TRY(d2h(e, improved, out.improved, n));
-    TRY(d2h(e, snd, out.snd, n));
+    // Software pipeline over slices of the individuals: H2D of slice i+1 (copy-in stream) overlaps
+    // the kernel of slice i (engine stream) and the D2H of slice i-1 (copy-out stream); PCIe is
+    // full duplex, so with pinned host buffers the call costs about max(H2D, kernel, D2H).
+    const int slices = std::min(count, kPipeSlices);
+    CU(cudaEventRecord(e->ev_k[0], e->stream));           // copy-in must follow the flag reset / prior work
+    CU(cudaStreamWaitEvent(e->s_in, e->ev_k[0], 0));
+    for (int sidx = 0; sidx < slices; ++sidx) {
+        const int f = (int)((long long)count * sidx / slices), l = (int)((long long)count * (sidx + 1) / slices);
+        const int cnt = l - f;
+        if (cnt == 0) continue;
+        const size_t off = (size_t)f * K, m = (size_t)cnt * K;
+        CU(cudaMemcpyAsync(e->t_xy.p + 2 * off, xy + 2 * off, 2 * m * sizeof(int), cudaMemcpyHostToDevice, e->s_in));
+        CU(cudaEventRecord(e->ev_in[sidx], e->s_in));
+        CU(cudaStreamWaitEvent(e->stream, e->ev_in[sidx], 0));
+        DevDeltaOut o = out;
+        if (o.cons) o.cons += off;
+        if (o.ind) o.ind += off;
+        if (o.bits) o.bits += off;
+        if (o.goc) o.goc += off;
+        if (o.fit) o.fit += off * M;
+        if (o.improved) o.improved += off;
+        if (o.snd) o.snd += off;
+        TRY(launch_deltas(e, first + f, cnt, K, e->t_xy.p + 2 * off, 0ull, obj, o, sum, pick_chunks(e, cnt, K)));
+        CU(cudaEventRecord(e->ev_k[sidx], e->stream));
+        CU(cudaStreamWaitEvent(e->s_out, e->ev_k[sidx], 0));
+        auto back = [&](void* host, const void* dev, size_t bytes) -> cudaError_t {
+            if (!host) return cudaSuccess;
+            return cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, e->s_out);
+        };
+        CU(back(cons ? cons + off : nullptr, o.cons, m * 4));
+        CU(back(ind ? ind + off : nullptr, o.ind, m * 4));
+        CU(back(bits ? bits + off : nullptr, o.bits, m * 8));
+        CU(back(goc ? goc + off : nullptr, o.goc, m * 8));
+        CU(back(fitness ? fitness + off * M : nullptr, o.fit, m * M * 8));
+        CU(back(improved ? improved + off : nullptr, o.improved, m));
+        CU(back(snd ? snd + off : nullptr, o.snd, m * 8));
+    }
+    CU(cudaEventRecord(e->ev_out, e->s_out));
+    CU(cudaStreamWaitEvent(e->stream, e->ev_out, 0));
     return finish_checked(e, "proposal outside [0,n2)");
 }
 

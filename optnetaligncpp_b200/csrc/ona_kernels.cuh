@@ -21,9 +21,9 @@ __global__ void k_pack_state(DevPop pop, int first, int count, int n2, const int
             const uint32_t f = (mask && !mask[(size_t)p * n2 + i]) ? kGFlag : 0u;
             ga[i] = v | f;
             gi[v] = (uint32_t)i | f;
-        } else {
-            ga[i] = 0;
-            gi[i] = 0;
+        } else {  // slot n2 and the alignment padding: permanently "masked off"
+            ga[i] = kGFlag;
+            gi[i] = kGFlag;
         }
     }
 }
@@ -596,13 +596,13 @@ k_swap_deltas_flat(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop
 //      in the reference's fp64 order, accept bit, coalesced stores.
 // --------------------------------------------------------------------------------
 #ifndef ONA_SORT_THREADS
-#define ONA_SORT_THREADS 512
+#define ONA_SORT_THREADS 256
 #endif
 #ifndef ONA_SORT_PER_THREAD
-#define ONA_SORT_PER_THREAD 2
+#define ONA_SORT_PER_THREAD 4
 #endif
 #ifndef ONA_SORT_MINBLOCKS
-#define ONA_SORT_MINBLOCKS 2
+#define ONA_SORT_MINBLOCKS 3
 #endif
 constexpr int kSortThreads = ONA_SORT_THREADS;
 constexpr int kSortPer = ONA_SORT_PER_THREAD;
@@ -802,16 +802,45 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
 // individual, state resident in shared memory for the whole climb.
 //
 // Speculative rounds: the next R = 32 proposals are all scored against the current state in
-// parallel (32 groups of G lanes); warp 0 then resolves them IN ORDER.  Proposals are mostly
-// rejected (~95 %), and a rejected proposal leaves aln/alnInv untouched, so every score up to
-// and including the first accepted proposal is exactly what the sequential loop would have
-// computed.  The first accepted proposal is committed, later ones in the round are discarded
-// and re-proposed in the next round.  The fp64 accumulators after a rejected proposal are
-// (acc1 - dX) - dY, not acc0 (H3); whenever that differs from acc0 in any bit the round's
-// later decisions are re-taken with the perturbed accumulators, so accumulators and decisions
-// stay bit-identical to the reference.
+// parallel (32 groups of G lanes walking the quad lists); warp 0 then resolves them IN ORDER:
+//   * a rejected proposal leaves aln/alnInv untouched, so later scores stay valid;
+//   * an accepted proposal is committed (doSwap's state change) and every later proposal of
+//     the round is checked for a read-after-write conflict with it: its own positions, the
+//     net1 neighbourhoods of its positions (Bloom signatures, conservative) and the net2
+//     neighbourhoods of its images.  The round ends just before the first conflicting
+//     proposal, which is re-scored in the next round; non-conflicting scores stay exact;
+//   * decisions compare against the CURRENT objectives, so whenever a commit (or the fp64
+//     residue of a rejected proposal's undo, SURVEY H3: (acc1 - dX) - dY != acc0) changes a
+//     counter or accumulator bit, the remaining decisions of the round are re-taken.
+// Counters, accumulators, accept decisions and the final permutation are therefore
+// bit-identical to running the reference's loop on the same proposal stream.
 // --------------------------------------------------------------------------------
 constexpr int kRound = 32;
+
+__device__ __forceinline__ bool bloom_has(const uint4& sg, int id) {
+    const unsigned u = (unsigned)id;
+    return (((sg.x >> (u & 31u)) & (sg.y >> ((u >> 5) & 31u)) & (sg.z >> ((u >> 10) & 31u))) & 1u) != 0u;
+}
+
+// Does the score of proposal j = (xj,yj | images axj,ayj) read anything that committing
+// proposal i = (xi,yi | images axi,ayi) writes?  Its own positions, the net1 neighbourhoods of
+// its positions (aln[] gathers) and the net2 neighbourhoods of its images (alnInv[] gathers).
+// Bloom signatures first, the exact adjacency bit only on a hit.
+__device__ __forceinline__ bool commit_conflicts(const DevGraph& g, int xj, int yj, int axj, int ayj,
+                                                 const uint4& n1x, const uint4& n1y, const uint4& n2x,
+                                                 const uint4& n2y, int xi, int yi, int axi, int ayi) {
+    bool dirty = (xj == xi) | (xj == yi) | (yj == xi) | (yj == yi);
+    const bool xir = xi < g.n1, yir = yi < g.n1;
+    if (xir && bloom_has(n1x, xi)) dirty |= ((__ldg(g.adj1 + (size_t)xj * g.W1 + (xi >> 5)) >> (xi & 31)) & 1u) != 0u;
+    if (yir && bloom_has(n1x, yi)) dirty |= ((__ldg(g.adj1 + (size_t)xj * g.W1 + (yi >> 5)) >> (yi & 31)) & 1u) != 0u;
+    if (xir && bloom_has(n1y, xi)) dirty |= ((__ldg(g.adj1 + (size_t)yj * g.W1 + (xi >> 5)) >> (xi & 31)) & 1u) != 0u;
+    if (yir && bloom_has(n1y, yi)) dirty |= ((__ldg(g.adj1 + (size_t)yj * g.W1 + (yi >> 5)) >> (yi & 31)) & 1u) != 0u;
+    if (bloom_has(n2x, axi)) dirty |= probe(g, axj, axi) != 0;
+    if (bloom_has(n2x, ayi)) dirty |= probe(g, axj, ayi) != 0;
+    if (bloom_has(n2y, axi)) dirty |= probe(g, ayj, axi) != 0;
+    if (bloom_has(n2y, ayi)) dirty |= probe(g, ayj, ayi) != 0;
+    return dirty;
+}
 
 template <typename T, int G>
 __global__ void __launch_bounds__(kRound * G)
@@ -846,7 +875,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
         const long long pos = s_pos;
         if (pos >= iters) break;
         const int nvalid = (int)min((long long)kRound, iters - pos);
-        // ---- phase 1: group `grp` scores proposal pos+grp
+        // ---- phase 1: group `grp` scores proposal pos+grp against the current state
         {
             int x = 0, y = 0;
             if (grp < nvalid) {
@@ -862,33 +891,93 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     rng_proposal(ikey, (unsigned long long)(pos + grp), g.n1, g.n2, x, y);
                 }
             }
-            int dc, di;
-            topo_delta<T, G>(g, s_aln, s_inv, x, y, gl, dc, di);
-            if (G <= 32) {
-                dc = group_sum<(G <= 32 ? G : 32)>(dc, gmask);
-                di = group_sum<(G <= 32 ? G : 32)>(di, gmask);
+            const SwapCtx cx = make_ctx<T>(g, s_aln, x, y);
+            const QuadPlan pl4 = make_plan(g, cx);
+            int dc, di, seen;
+            walk_plan<T>(g, s_aln, s_inv, cx, pl4, gl, G, dc, di, seen);
+            dc = group_sum<G>(dc, gmask);
+            di = group_sum<G>(di, gmask);
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) seen |= __shfl_xor_sync(gmask, seen, off, G);
+            if (gl == 0) {
+                special_terms(g, cx, seen, dc, di);
+                s_x[grp] = x; s_y[grp] = y; s_dc[grp] = dc; s_di[grp] = di;
             }
-            if (gl == 0) { s_x[grp] = x; s_y[grp] = y; s_dc[grp] = dc; s_di[grp] = di; }
         }
         __syncthreads();
         // ---- phase 2: warp 0 resolves the round in order
         if (threadIdx.x < 32) {
             const int c = lane;
             const bool valid = c < nvalid;
-            const int x = s_x[c], y = s_y[c], dc = s_dc[c], di = s_di[c];
-            ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, valid ? x : 0, valid ? y : 0);
-            int start = 0, consumed = nvalid, acc_lane = -1;
+            const int x = s_x[c], y = s_y[c];
+            int dc = s_dc[c], di = s_di[c];
+            ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, x, y);
+            // what this proposal's score depended on (for the conflict test)
+            int ax = (int)(s_aln[x] & MASK), ay = (int)(s_aln[y] & MASK);
+            const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+            const bool xr = x < g.n1, yr = y < g.n1;
+            const uint4 n1x = xr ? __ldg(g.sig1 + x) : zero4, n1y = yr ? __ldg(g.sig1 + y) : zero4;
+            uint4 n2x = __ldg(g.sig2 + ax), n2y = __ldg(g.sig2 + ay);
+            // conf bit i: committing proposal i (< c) would make this lane's score stale.  All
+            // pairs are tested up front, so the loads overlap instead of stalling every commit.
+            unsigned conf = 0u;
+#pragma unroll 4
+            for (int i = 0; i < nvalid - 1; ++i) {
+                const int xi = __shfl_sync(0xffffffffu, x, i), yi = __shfl_sync(0xffffffffu, y, i);
+                const int axi = __shfl_sync(0xffffffffu, ax, i), ayi = __shfl_sync(0xffffffffu, ay, i);
+                if (c > i && commit_conflicts(g, x, y, ax, ay, n1x, n1y, n2x, n2y, xi, yi, axi, ayi))
+                    conf |= 1u << i;
+            }
+
+            int start = 0;
+            unsigned ev = 0u, acc_mask = 0u, dirty_mask = 0u;
+            bool need_decide = true, acc = false;
+            double ub = 0.0, ug = 0.0;
+            Scalars nw = cur;
+            const unsigned vmask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
             for (;;) {
-                const Scalars nw = apply_delta(cur, dc, di, sd);
-                double unused;
-                const bool acc = judge_move(ob, obj, cur, nullptr, nw, g.E1, nullptr, false, unused);
-                double ub, ug;
-                undo_accumulators(nw, sd, ub, ug);
-                const bool pert = !acc && (__double_as_longlong(ub) != __double_as_longlong(cur.bits) ||
-                                           __double_as_longlong(ug) != __double_as_longlong(cur.goc));
-                const unsigned ev = __ballot_sync(0xffffffffu, valid && c >= start && (acc || pert));
-                if (ev == 0) break;
-                const int e = __ffs(ev) - 1;
+                if (need_decide) {
+                    nw = apply_delta(cur, dc, di, sd);
+                    double unused;
+                    acc = judge_move(ob, obj, cur, nullptr, nw, g.E1, nullptr, false, unused);
+                    undo_accumulators(nw, sd, ub, ug);
+                    const bool pert = !acc && (__double_as_longlong(ub) != __double_as_longlong(cur.bits) ||
+                                               __double_as_longlong(ug) != __double_as_longlong(cur.goc));
+                    ev = __ballot_sync(0xffffffffu, acc || pert);
+                    need_decide = false;
+                }
+                // next thing that needs attention: an accept / perturbing reject, or a proposal
+                // whose score went stale (dirty) and must be re-scored before it is judged
+                const unsigned pending = (ev | dirty_mask) & vmask & (start >= 32 ? 0u : ~((1u << start) - 1u));
+                if (pending == 0u) break;
+                const int e = __ffs(pending) - 1;
+                if ((dirty_mask >> e) & 1u) {
+                    // re-score proposal e against the current state, the whole warp on its lists
+                    const int xe = __shfl_sync(0xffffffffu, x, e), ye = __shfl_sync(0xffffffffu, y, e);
+                    const SwapCtx cx = make_ctx<T>(g, s_aln, xe, ye);
+                    const QuadPlan pl4 = make_plan(g, cx);
+                    int rdc, rdi, seen;
+                    walk_plan<T>(g, s_aln, s_inv, cx, pl4, lane, 32, rdc, rdi, seen);
+                    rdc = warp_sum<int>(rdc);
+                    rdi = warp_sum<int>(rdi);
+                    seen = (int)__reduce_or_sync(0xffffffffu, (unsigned)seen);
+                    special_terms(g, cx, seen, rdc, rdi);
+                    if (c == e) {
+                        dc = rdc; di = rdi;
+                        sd = score_delta<T>(g, S, Gt, s_aln, x, y);
+                        ax = cx.ax; ay = cx.ay;
+                        n2x = __ldg(g.sig2 + ax); n2y = __ldg(g.sig2 + ay);
+                    }
+                    // proposal e now has (possibly) new images: refresh bit e of the later lanes
+                    if (c > e) {
+                        conf &= ~(1u << e);
+                        if (commit_conflicts(g, x, y, ax, ay, n1x, n1y, n2x, n2y, xe, ye, cx.ax, cx.ay)) conf |= 1u << e;
+                    }
+                    dirty_mask &= ~(1u << e);
+                    start = e;            // judge it now
+                    need_decide = true;
+                    continue;
+                }
                 const bool e_acc = __shfl_sync(0xffffffffu, (int)acc, e) != 0;
                 if (e_acc) {
                     // commit proposal e: doSwap's state change, Alignment.cpp:496-504,516-519
@@ -899,23 +988,34 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                         s_inv[ry & MASK] = (T)((uint32_t)x | (ry & FLAG));
                         s_inv[rx & MASK] = (T)((uint32_t)y | (rx & FLAG));
                     }
-                    cur.C = __shfl_sync(0xffffffffu, nw.C, e);
-                    cur.I = __shfl_sync(0xffffffffu, nw.I, e);
-                    cur.size = __shfl_sync(0xffffffffu, nw.size, e);
-                    cur.bits = __shfl_sync(0xffffffffu, nw.bits, e);
-                    cur.goc = __shfl_sync(0xffffffffu, nw.goc, e);
-                    consumed = e + 1;
-                    acc_lane = e;
+                    Scalars nx;
+                    nx.C = __shfl_sync(0xffffffffu, nw.C, e);
+                    nx.I = __shfl_sync(0xffffffffu, nw.I, e);
+                    nx.size = __shfl_sync(0xffffffffu, nw.size, e);
+                    nx.bits = __shfl_sync(0xffffffffu, nw.bits, e);
+                    nx.goc = __shfl_sync(0xffffffffu, nw.goc, e);
+                    const bool changed = nx.C != cur.C || nx.I != cur.I || nx.size != cur.size ||
+                                         __double_as_longlong(nx.bits) != __double_as_longlong(cur.bits) ||
+                                         __double_as_longlong(nx.goc) != __double_as_longlong(cur.goc);
+                    cur = nx;
+                    acc_mask |= 1u << e;
                     n_acc++;
-                    break;
+                    // later proposals whose scores this commit makes stale (precomputed pair tests)
+                    const bool dirty = ((conf >> e) & 1u) != 0u;
+                    dirty_mask |= __ballot_sync(0xffffffffu, dirty && c > e) & vmask;
+                    start = e + 1;
+                    if (changed) need_decide = true;   // later decisions see new current objectives
+                    __syncwarp();
+                } else {
+                    // rejected, but the undo left different accumulator bits: carry them forward
+                    cur.bits = __shfl_sync(0xffffffffu, ub, e);
+                    cur.goc = __shfl_sync(0xffffffffu, ug, e);
+                    start = e + 1;
+                    need_decide = true;
                 }
-                // rejected, but the undo left different accumulator bits: carry them forward
-                cur.bits = __shfl_sync(0xffffffffu, ub, e);
-                cur.goc = __shfl_sync(0xffffffffu, ug, e);
-                start = e + 1;
             }
-            if (accepted && c < consumed) accepted[(size_t)pl * iters + pos + c] = (c == acc_lane) ? 1 : 0;
-            if (c == 0) s_pos = pos + consumed;
+            if (accepted && valid) accepted[(size_t)pl * iters + pos + c] = (unsigned char)((acc_mask >> c) & 1u);
+            if (c == 0) s_pos = pos + nvalid;
         }
         __syncthreads();
     }
