@@ -219,7 +219,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from optnetaligncpp_b200 import engine
+    from optnetaligncpp_b200 import engine, islands
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -250,7 +250,6 @@ def run_ours(args):
     o_imp = torch.empty((P, K), dtype=torch.uint8, device=dev)
     o_nimp = torch.zeros((P,), dtype=torch.int32, device=dev)
     fit_local = torch.empty((P, M), dtype=torch.float64, device=dev)
-    fit_all = torch.empty((world * P, M), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step(seed, ev=None):
@@ -267,7 +266,7 @@ def run_ours(args):
             ev[2].record(stream)
         e.export_fitness_dev(fit_local.data_ptr())
         if world > 1:
-            dist.all_gather_into_tensor(fit_all, fit_local)
+            islands.all_gather_objectives(fit_local, world * P, world)
         if ev:
             ev[3].record(stream)
 

@@ -91,6 +91,10 @@ void* ona_host_alloc(long long bytes);
 void ona_host_free(void* p);
 /* number of engine kernels launched so far (bench.py's gpu_launches) */
 long long ona_kernel_launches(const ona_engine* e);
+/* Replaces: passing a different fitnessNames vector to computeFitness / correctHillClimb
+ * (Alignment.cpp:559, localSearch.cpp:18): switch the objective list of an existing engine.
+ * Cached objective rows of all slots are recomputed from their counters. */
+int ona_set_objectives(ona_engine* e, const int* objectives, int num_objectives);
 /* global index of slot 0 (island offset); only keys the on-device proposal RNG */
 int ona_set_island_offset(ona_engine* e, long long first_global_individual);
 
@@ -159,6 +163,11 @@ int ona_swap_deltas_dev(ona_engine* e, int first, int count, int K, const int* x
                         unsigned long long seed, int obj, int* conserved_dev, int* induced_dev,
                         double* bitscore_dev, double* goc_dev, double* fitness_dev,
                         unsigned char* improved_dev, double* snd_dev, int* num_improved_dev);
+/* Replaces: one scan of steepestAscentHillClimb (localSearch.cpp:130-188): swapNormalizedDelta
+ * of EVERY (x,y) in [0,n1) x [0,n2) against slot `slot` (all objectives), arg-max with the
+ * reference's tie rule (first maximum in x-major order; only values > -1 can win, :134,141).
+ * No state is modified; best_x = best_y = -1 and best_delta = -1 when nothing wins. */
+int ona_steepest_step(ona_engine* e, int slot, double* best_delta, int* best_x, int* best_y);
 /* the proposals the device RNG generates, for host-side checking */
 int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long long seed,
                       long long start_index, int* xy);

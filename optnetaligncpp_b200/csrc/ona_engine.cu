@@ -268,13 +268,15 @@ int launch_deltas_flat(ona_engine* e, int first, int count, int K, const int* xy
 
 template <typename T>
 int launch_deltas_sorted(ona_engine* e, int first, int count, int K, const int* xy_dev,
-                         unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
+                         unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks,
+                         int grid_x0 = -1) {
     const size_t smem = state_smem(e);
     int rc = set_smem(k_swap_deltas_sorted<T>, smem);
     if (rc) return rc;
     dim3 grid(chunks, count);
     k_swap_deltas_sorted<T><<<grid, kSortThreads, smem, e->stream>>>(
-        e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag);
+        e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag,
+        grid_x0);
     e->launches++;
     CU(cudaGetLastError());
     return ONA_OK;
@@ -602,6 +604,29 @@ int ona_set_island_offset(ona_engine* e, long long off) {
     return ONA_OK;
 }
 
+int ona_set_objectives(ona_engine* e, const int* objectives, int M) {
+    if (!e || !objectives || M <= 0 || M > ONA_MAX_OBJECTIVES) return fail(ONA_ERR_INVALID, "need 1..10 objectives");
+    for (int j = 0; j < M; ++j)
+        if (objectives[j] < 0 || objectives[j] > 9) return fail(ONA_ERR_INVALID, "unknown objective id");
+    LOCK(e);
+    CU(cudaStreamSynchronize(e->stream));
+    const bool resize = M != e->ob.M;
+    e->ob.M = M;
+    for (int j = 0; j < M; ++j) e->ob.names[j] = objectives[j];
+    if (e->P > 0) {
+        if (resize) {
+            cudaFree(e->pop.fit);
+            e->pop.fit = nullptr;
+            CU(cudaMalloc(&e->pop.fit, (size_t)e->P * M * 8));
+        }
+        k_refresh_fitness<<<(e->P + 127) / 128, 128, 0, e->stream>>>(e->g, e->ob, e->pop, 0, e->P);
+        e->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    return ONA_OK;
+}
+
 int ona_pop_resize(ona_engine* e, int P) {
     if (!e || P < 0) return fail(ONA_ERR_INVALID, "bad population size");
     LOCK(e);
@@ -887,6 +912,45 @@ int ona_swap_deltas_dev(ona_engine* e, int first, int count, int K, const int* x
     DeltaSummary sum{};
     sum.num_improved = num_improved_dev;
     return launch_deltas(e, first, count, K, xy_dev, seed, obj, out, sum, pick_chunks(e, count, K));
+}
+
+int ona_steepest_step(ona_engine* e, int slot, double* best_delta, int* best_x, int* best_y) {
+    TRY(check_range(e, slot, 1));
+    LOCK(e);
+    const int n1 = e->g.n1, n2 = e->g.n2;
+    const int slab = std::max(1, std::min(n1, (1 << 28) / n2));  // rows of the grid per launch
+    double bv = -1.0;  // localSearch.cpp:134,141: bestDelta starts at -1 and only a larger value wins
+    int bx = -1, by = -1;
+    std::vector<double> hv;
+    std::vector<long long> hi;
+    for (int x0 = 0; x0 < n1; x0 += slab) {
+        const int nx = std::min(slab, n1 - x0);
+        const int K = nx * n2;
+        const int chunks = std::max(1, (K + kSortCap - 1) / kSortCap);
+        CU(e->t_d4.need((size_t)chunks));
+        CU(e->t_l0.need((size_t)chunks));
+        DevDeltaOut out{};
+        DeltaSummary sum{};
+        sum.block_best = e->t_d4.p;
+        sum.block_arg = e->t_l0.p;
+        if (e->small_ids) TRY(launch_deltas_sorted<uint16_t>(e, slot, 1, K, nullptr, 0ull, -1, out, sum, chunks, x0));
+        else TRY(launch_deltas_sorted<uint32_t>(e, slot, 1, K, nullptr, 0ull, -1, out, sum, chunks, x0));
+        hv.resize(chunks);
+        hi.resize(chunks);
+        TRY(d2h(e, hv.data(), e->t_d4.p, (size_t)chunks));
+        TRY(d2h(e, hi.data(), e->t_l0.p, (size_t)chunks));
+        CU(cudaStreamSynchronize(e->stream));
+        for (int c = 0; c < chunks; ++c)
+            if (hi[c] >= 0 && hv[c] > bv) {  // chunks are in (x,y) order: the first maximum wins
+                bv = hv[c];
+                bx = x0 + (int)(hi[c] / n2);
+                by = (int)(hi[c] % n2);
+            }
+    }
+    if (best_delta) *best_delta = bv;
+    if (best_x) *best_x = bx;
+    if (best_y) *best_y = by;
+    return ONA_OK;
 }
 
 int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long long seed,

@@ -615,7 +615,7 @@ template <typename T>
 __global__ void __launch_bounds__(kSortThreads, ONA_SORT_MINBLOCKS)
 k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first, int K,
                      const int* __restrict__ xy, unsigned long long seed, long long island_offset,
-                     int obj, DevDeltaOut out, DeltaSummary sum, int* __restrict__ err_flag) {
+                     int obj, DevDeltaOut out, DeltaSummary sum, int* __restrict__ err_flag, int grid_x0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int2 s_xy[kSortCap];                 // proposals of this pass, original order
     __shared__ int2 s_res[kSortCap];                // (dcons, dind), original order
@@ -662,6 +662,10 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                         atomicOr(err_flag, 1);  // reported by the host entry point as ONA_ERR_INVALID
                         x = 0; y = 0;
                     }
+                } else if (grid_x0 >= 0) {
+                    // exhaustive grid of steepestAscentHillClimb (localSearch.cpp:136-147), x-major
+                    x = grid_x0 + c / g.n2;
+                    y = c - (c / g.n2) * g.n2;
                 } else {
                     rng_proposal(ikey, (unsigned long long)c, g.n1, g.n2, x, y);
                 }

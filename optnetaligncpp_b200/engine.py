@@ -21,9 +21,9 @@ SEED_NONE, SEED_TRUE, SEED_REFCOMPAT, SUM_SEQUENTIAL = 0, 1, 2, 16
 EXPORTS = [
     "ona_device_count", "ona_engine_create", "ona_engine_destroy", "ona_last_error",
     "ona_set_stream", "ona_synchronize", "ona_host_alloc", "ona_host_free", "ona_kernel_launches",
-    "ona_set_island_offset", "ona_pop_resize", "ona_pop_upload", "ona_pop_download",
+    "ona_set_island_offset", "ona_set_objectives", "ona_pop_resize", "ona_pop_upload", "ona_pop_download",
     "ona_pop_set_counters", "ona_pop_get_counters", "ona_full_fitness", "ona_full_fitness_dev",
-    "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_rng_proposals", "ona_hill_climb",
+    "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_steepest_step", "ona_rng_proposals", "ona_hill_climb",
     "ona_apply_swaps", "ona_export_fitness_dev",
 ]
 
@@ -76,6 +76,7 @@ def load_library(build_if_missing=True):
     L.ona_kernel_launches.restype = ll
     L.ona_kernel_launches.argtypes = [vp]
     L.ona_set_island_offset.argtypes = [vp, ll]
+    L.ona_set_objectives.argtypes = [vp, vp, ci]
     L.ona_pop_resize.argtypes = [vp, ci]
     L.ona_pop_upload.argtypes = [vp, ci, ci, vp, vp]
     L.ona_pop_download.argtypes = [vp, ci, ci, vp, vp, vp]
@@ -86,6 +87,7 @@ def load_library(build_if_missing=True):
     L.ona_swap_deltas.argtypes = [vp, ci, ci, ci, vp, ci] + [vp] * 7
     L.ona_swap_deltas_rng.argtypes = [vp, ci, ci, ci, C.c_ulonglong, ci, vp, vp, vp]
     L.ona_swap_deltas_dev.argtypes = [vp, ci, ci, ci, vp, C.c_ulonglong, ci] + [vp] * 8
+    L.ona_steepest_step.argtypes = [vp, ci, vp, vp, vp]
     L.ona_rng_proposals.argtypes = [vp, ci, ci, ci, C.c_ulonglong, ll, vp]
     L.ona_hill_climb.argtypes = [vp, ci, ci, ll, vp, C.c_ulonglong, vp, vp, vp]
     L.ona_apply_swaps.argtypes = [vp, ci, ci, ci, vp]
@@ -177,6 +179,11 @@ class Engine:
     def set_island_offset(self, first_global):
         self._check(self.L.ona_set_island_offset(self.h, int(first_global)))
 
+    def set_objectives(self, objectives):
+        self.objectives = _i32(objectives)
+        self.M = len(self.objectives)
+        self._check(self.L.ona_set_objectives(self.h, _ptr(self.objectives), self.M))
+
     # ---- population
     def resize(self, P):
         self._check(self.L.ona_pop_resize(self.h, int(P)))
@@ -264,6 +271,12 @@ class Engine:
                                                int(obj), vp(cons or 0), vp(ind or 0), vp(bits or 0),
                                                vp(goc or 0), vp(fit or 0), vp(improved or 0),
                                                vp(snd or 0), vp(num_improved or 0)))
+
+    def steepest_step(self, slot=0):
+        """one exhaustive scan of steepestAscentHillClimb: (best swapNormalizedDelta, x, y)."""
+        d, x, y = C.c_double(), C.c_int(), C.c_int()
+        self._check(self.L.ona_steepest_step(self.h, int(slot), C.byref(d), C.byref(x), C.byref(y)))
+        return d.value, x.value, y.value
 
     def rng_proposals(self, K, seed, first=0, count=None, start=0):
         count = self.P - first if count is None else count

@@ -1,0 +1,82 @@
+// Small driver in the shape of the reference's hillclimber.cpp:52-79, written against the
+// reference's UNCHANGED headers and linked against the drop-in Alignment.cpp / localSearch.cpp
+// of this directory (plus the reference's own Network.cpp, blastinfo.cpp, goc.cpp, nsga-ii.cpp).
+// It is what tests/test_gpu_dropin.py runs to show that reference callers work unchanged:
+//
+//   dropin_demo net1 net2 sim|- annos1|- annos2|- seed iters nthreads out_prefix
+//
+// Per thread t: Alignment(net1,net2,bit,goc); shuf(mt19937(seed+t)); computeFitness;
+// correctHillClimb(mt19937(seed+1000+t), iters, obj=-1); then mutate + a crossover with thread
+// 0's result; prints counters/objectives and writes <out_prefix>_<t>.aln via Alignment::save.
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <thread>
+#include <vector>
+
+#include "Alignment.h"
+#include "blastinfo.h"
+#include "goc.h"
+#include "localSearch.h"
+
+using namespace std;
+
+int main(int argc, char** argv) {
+    if (argc < 10) {
+        cerr << "usage: dropin_demo net1 net2 sim|- annos1|- annos2|- seed iters nthreads out_prefix" << endl;
+        return 2;
+    }
+    try {
+        Network* net1 = new Network(argv[1]);
+        Network* net2 = new Network(argv[2]);
+        const string sim = argv[3], a1 = argv[4], a2 = argv[5];
+        BLASTDict* bit = sim == "-" ? nullptr : loadBLASTInfo(net1, net2, sim);
+        GOCDict* goc = (a1 == "-" || a2 == "-") ? nullptr : loadGOC(net1, net2, a1, a2);
+        const int seed = atoi(argv[6]), iters = atoi(argv[7]), nthreads = atoi(argv[8]);
+        const string prefix = argv[9];
+        vector<fitnessName> names;  // argParsing.h:212-271 push order
+        names.push_back(S3Fit);
+        if (bit) names.push_back(BitscoreSumFit);
+        if (goc) names.push_back(GOCFit);
+
+        vector<Alignment*> alns(nthreads, nullptr);
+        vector<thread> ts;
+        for (int t = 0; t < nthreads; t++) {
+            ts.push_back(thread([&, t]() {
+                RandGenT g(seed + t);
+                Alignment* aln = new Alignment(net1, net2, bit, goc);
+                aln->shuf(g, false, false, true);
+                aln->computeFitness(names);
+                RandGenT h(seed + 1000 + t);
+                correctHillClimb(h, aln, true, iters, names);
+                alns[t] = aln;
+            }));
+        }
+        for (auto& th : ts) th.join();
+        for (int t = 0; t < nthreads; t++) {
+            Alignment* aln = alns[t];
+            printf("climb %d cons %d ind %d bits %.17g goc %.17g", t, aln->currConservedCount,
+                   aln->currInducedCount, bit ? aln->currBitscore : 0.0, goc ? aln->currGOC : 0.0);
+            for (double f : aln->fitness) printf(" %.17g", f);
+            printf("\n");
+            aln->save(prefix + "_" + to_string(t) + ".aln");
+        }
+        // operators that precede the hot loop for every child (steadystate.cpp:222-232)
+        for (int t = 0; t < nthreads; t++) {
+            RandGenT g(seed + 2000 + t), m(seed + 3000 + t);
+            Alignment child(g, 0.1f, *alns[t], *alns[0], true);
+            child.mutate(m, 0.005f, true);
+            child.computeFitness(names);
+            printf("child %d cons %d ind %d bits %.17g goc %.17g ics %.17g", t, child.currConservedCount,
+                   child.currInducedCount, bit ? child.currBitscore : 0.0, goc ? child.currGOC : 0.0, child.ics());
+            for (double f : child.fitness) printf(" %.17g", f);
+            printf("\n");
+        }
+        Alignment probe(*alns[0]);
+        printf("snd %.17g\n", swapNormalizedDelta(probe, names, 3, 7));
+    } catch (exception& e) {
+        cerr << "error: " << e.what() << endl;
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,196 @@
+// Drop-in replacement for the reference's localSearch.cpp: implements the reference's
+// UNCHANGED header localSearch.h on top of the B200 engine's C ABI.  Each function cites the
+// reference lines whose behaviour it reproduces (/root/reference/localSearch.cpp).
+#include "localSearch.h"
+
+#include <chrono>
+#include <cmath>
+#include <iostream>
+
+#include "nsga-ii.h"
+#include "ona_host.hpp"
+
+using namespace std;
+
+namespace {
+
+// correctHillClimb is called concurrently by the reference's worker threads, each on its own
+// Alignment (steadystate.cpp:132-303, nsgaiimain.cpp:194-238).  Calls that arrive together and
+// agree on (engine, objective list, iteration count) are combined into ONE batched GPU climb,
+// one CTA per alignment: the first caller becomes the leader, waits a moment for company,
+// runs the batch and wakes the others.
+struct Request {
+    Alignment* aln;
+    const vector<fitnessName>* names;
+    vector<int> xy;
+    int obj;
+    long long iters;
+    bool done = false;
+    string error;
+};
+
+class Batcher {
+public:
+    void submit(ona_host::Context& ctx, Request& r) {
+        unique_lock<mutex> lk(mu_);
+        queue_.push_back(&r);
+        while (!r.done) {
+            if (leader_) {  // somebody else is driving the GPU: wait to be served (or to take over)
+                cv_.wait(lk);
+                continue;
+            }
+            leader_ = true;
+            cv_.wait_for(lk, chrono::microseconds(200));  // give concurrent callers a moment to join
+            vector<Request*> batch;
+            for (Request* q : queue_)
+                if (q->iters == queue_.front()->iters && *q->names == *queue_.front()->names) batch.push_back(q);
+            for (Request* q : batch) queue_.erase(find(queue_.begin(), queue_.end(), q));
+            lk.unlock();
+            run(ctx, batch);
+            lk.lock();
+            for (Request* q : batch) q->done = true;
+            leader_ = false;
+            cv_.notify_all();
+        }
+        lk.unlock();
+        if (!r.error.empty()) throw runtime_error(r.error);
+    }
+
+private:
+    static void run(ona_host::Context& ctx, vector<Request*>& batch) {
+        try {
+            lock_guard<mutex> lk(ctx.lock());
+            ctx.use_objectives(*batch[0]->names);
+            vector<Alignment*> alns;
+            vector<int> objs, xy;
+            for (Request* q : batch) {
+                alns.push_back(q->aln);
+                objs.push_back(q->obj);
+                xy.insert(xy.end(), q->xy.begin(), q->xy.end());
+            }
+            ctx.upload(alns);
+            ona_host::check(ona_hill_climb(ctx.engine(), 0, (int)alns.size(), batch[0]->iters, xy.data(), 0ull,
+                                           objs.data(), nullptr, nullptr));
+            ctx.download(alns);
+            for (Request* q : batch) q->aln->computeFitness(*q->names);
+        } catch (const exception& ex) {
+            for (Request* q : batch) q->error = ex.what();
+        }
+    }
+    mutex mu_;
+    condition_variable cv_;
+    vector<Request*> queue_;
+    bool leader_ = false;
+};
+
+Batcher& batcher_for(ona_host::Context& ctx) {
+    static mutex mu;
+    static map<ona_host::Context*, Batcher*> all;
+    lock_guard<mutex> lk(mu);
+    Batcher*& b = all[&ctx];
+    if (!b) b = new Batcher();
+    return *b;
+}
+
+}  // namespace
+
+// localSearch.cpp:18-55.  The proposals are drawn from the caller's PRNG with the reference's
+// own two distributions in the reference's order (:21-28), so the generator ends in the same
+// state and the climb follows the same trajectory; the accept/undo loop runs on the GPU with
+// the reference's exact sequential semantics (ona_hill_climb).
+void correctHillClimb(RandGenT& prng, Alignment* aln, bool total, int maxIters,
+                      const vector<fitnessName>& fitnessNames, int obj) {
+    (void)total;  // unused by the reference as well
+    if (maxIters <= 0) return;
+    auto randNonDummyIndex = uniform_int_distribution<int>(0, aln->actualSize - 1);
+    auto randIndex = uniform_int_distribution<int>(0, (int)aln->aln.size() - 2);
+    Request r;
+    r.aln = aln;
+    r.names = &fitnessNames;
+    r.obj = obj;
+    r.iters = maxIters;
+    r.xy.resize(2 * (size_t)maxIters);
+    for (int i = 0; i < maxIters; i++) {
+        node x = randNonDummyIndex(prng);
+        node y = randIndex(prng);
+        if (y >= x) y++;
+        r.xy[2 * i] = x;
+        r.xy[2 * i + 1] = y;
+    }
+    ona_host::Context& ctx = ona_host::context_for(*aln);
+    batcher_for(ctx).submit(ctx, r);
+}
+
+// localSearch.cpp:60-84
+void proportionalSearch(RandGenT& prng, Alignment* aln, bool total, int iters,
+                        const vector<fitnessName>& fitnessNames, int obj, double proportion) {
+    auto prob = uniform_real_distribution<double>(0, 1);
+    auto randObj = uniform_int_distribution<int>(0, (int)fitnessNames.size() - 1);
+    for (int i = 0; i < iters; i++) {
+        if (prob(prng) < proportion) {
+            correctHillClimb(prng, aln, total, 500, fitnessNames, obj);
+        } else {
+            int robj = obj;
+            while (robj == obj) robj = randObj(prng);
+            correctHillClimb(prng, aln, total, 500, fitnessNames, robj);
+        }
+    }
+}
+
+// localSearch.cpp:88-120.  One candidate against the alignment's current state; the state is
+// left exactly as it was (the reference's swap/un-swap can leave an ulp-level residue in the
+// fp64 accumulators, SURVEY H3 -- not reproduced here).
+double swapNormalizedDelta(Alignment& aln, const vector<fitnessName>& fitnessNames, node x, node y) {
+    ona_host::Context& ctx = ona_host::context_for(aln);
+    lock_guard<mutex> lk(ctx.lock());
+    ctx.use_objectives(fitnessNames);
+    vector<Alignment*> one{&aln};
+    ctx.upload(one);
+    const int xy[2] = {x, y};
+    double snd = 0.0;
+    ona_host::check(ona_swap_deltas(ctx.engine(), 0, 1, 1, xy, -1, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                    nullptr, &snd));
+    return snd;
+}
+
+// localSearch.cpp:122-203.  The reference splits the n1 x n2 grid over nthreads CPU threads;
+// here every scan is one pass of the swap-delta kernel over the whole grid.
+void steepestAscentHillClimb(Alignment* aln, vector<fitnessName>& fitnessNames, int nthreads, bool verbose) {
+    (void)nthreads;
+    ona_host::Context& ctx = ona_host::context_for(*aln);
+    int numiters = 0;
+    for (;;) {
+        double best = -1.0;
+        int bx = -1, by = -1;
+        {
+            lock_guard<mutex> lk(ctx.lock());
+            ctx.use_objectives(fitnessNames);
+            vector<Alignment*> one{aln};
+            ctx.upload(one);
+            ona_host::check(ona_steepest_step(ctx.engine(), 0, &best, &bx, &by));
+        }
+        if (best <= 0.0) break;  // :190
+        aln->doSwap(bx, by);
+        aln->computeFitness(fitnessNames);
+        if (verbose) {
+            reportStats({aln}, fitnessNames, true, false);
+            cout << (++numiters) << " swaps performed." << endl;
+        }
+    }
+}
+
+// localSearch.cpp:298-330 -- ring buffer of the last 500 delta vectors
+VelocityTracker::VelocityTracker() : nextSpot(0), size(0), recentDeltas(500) {}
+void VelocityTracker::reportDelta(const vector<double>& in) {
+    recentDeltas[nextSpot] = in;
+    nextSpot = (nextSpot + 1) % 500;
+    if (size < 500) size++;
+}
+vector<double> VelocityTracker::getRecentVel() const {
+    vector<double> mean(recentDeltas[0].size(), 0.0);
+    for (int i = 0; i < size; i++)
+        for (size_t j = 0; j < recentDeltas[i].size(); j++) mean[j] += recentDeltas[i][j];
+    const double n = double(size);
+    for (double& v : mean) v /= n;
+    return mean;
+}

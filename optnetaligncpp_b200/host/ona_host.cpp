@@ -1,0 +1,163 @@
+// see ona_host.hpp
+#include "ona_host.hpp"
+
+#include <cstdlib>
+#include <memory>
+#include <tuple>
+
+namespace ona_host {
+
+namespace {
+std::mutex g_mu;
+std::map<std::tuple<const Network*, const Network*, const BLASTDict*, const GOCDict*>,
+         std::unique_ptr<Context>> g_ctx;
+
+// Network::adjList -> CSR in adjList order (Network.cpp:89-92)
+void to_csr(const Network* n, std::vector<int>& rp, std::vector<int>& col) {
+    rp.assign(1, 0);
+    col.clear();
+    for (const auto& row : n->adjList) {
+        col.insert(col.end(), row.begin(), row.end());
+        rp.push_back((int)col.size());
+    }
+}
+}  // namespace
+
+Context::Context(const Network* net1, const Network* net2, const BLASTDict* bit, const GOCDict* goc) {
+    n1_ = (int)net1->nodeToNodeName.size();
+    n2_ = (int)net2->nodeToNodeName.size();
+    std::vector<int> rp1, c1, rp2, c2;
+    to_csr(net1, rp1, c1);
+    to_csr(net2, rp2, c2);
+    ona_problem pr{};
+    pr.n1 = n1_;
+    pr.n2 = n2_;
+    pr.num_edges1 = (long long)net1->edges.size();  // EC / S3 denominator term (Alignment.cpp:536,541)
+    pr.rowptr1 = rp1.data(); pr.col1 = c1.data();
+    pr.rowptr2 = rp2.data(); pr.col2 = c2.data();
+    // BLASTDict / GOCDict are dense row-major n1 x n2 doubles (blastinfo.cpp:20, goc.cpp:23)
+    if (bit) pr.bitscores.dense = &(*bit)[0][0];
+    if (goc) pr.gocs.dense = &(*goc)[0][0];
+    names_ = {ONA_ICS};
+    pr.objectives = names_.data();
+    pr.num_objectives = 1;
+    int device = 0;
+    if (const char* d = std::getenv("ONA_DEVICE")) device = std::atoi(d);
+    check(ona_engine_create(device, &pr, &e_));
+}
+
+Context::~Context() { ona_engine_destroy(e_); }
+
+void Context::use_objectives(const std::vector<fitnessName>& names) {
+    std::vector<int> v(names.begin(), names.end());
+    if (v == names_ || v.empty()) return;
+    check(ona_set_objectives(e_, v.data(), (int)v.size()));
+    names_ = v;
+}
+
+void Context::ensure_slots(int count) {
+    if (count <= slots_) return;
+    int want = slots_ ? slots_ : 16;
+    while (want < count) want *= 2;
+    check(ona_pop_resize(e_, want));
+    slots_ = want;
+}
+
+void Context::upload(const std::vector<Alignment*>& alns) {
+    const int n = (int)alns.size();
+    ensure_slots(n);
+    h_aln_.resize((size_t)n * n2_);
+    h_mask_.resize((size_t)n * n2_);
+    std::vector<int> cons(n), ind(n);
+    std::vector<double> bits(n), goc(n);
+    bool any_off = false;
+    for (int p = 0; p < n; ++p) {
+        const Alignment& a = *alns[p];
+        for (int i = 0; i < n2_; ++i) {
+            h_aln_[(size_t)p * n2_ + i] = a.aln[i];
+            const unsigned char m = a.alnMask[i] ? 1 : 0;
+            h_mask_[(size_t)p * n2_ + i] = m;
+            any_off |= !m;
+        }
+        cons[p] = a.currConservedCount;
+        ind[p] = a.currInducedCount;
+        bits[p] = a.bitscores ? a.currBitscore : 0.0;
+        goc[p] = a.gocs ? a.currGOC : 0.0;
+    }
+    check(ona_pop_upload(e_, 0, n, h_aln_.data(), any_off ? h_mask_.data() : nullptr));
+    check(ona_pop_set_counters(e_, 0, n, cons.data(), ind.data(), bits.data(), goc.data()));
+}
+
+void Context::download(const std::vector<Alignment*>& alns) {
+    const int n = (int)alns.size();
+    h_aln_.resize((size_t)n * n2_);
+    h_inv_.resize((size_t)n * n2_);
+    h_mask_.resize((size_t)n * n2_);
+    std::vector<int> cons(n), ind(n);
+    std::vector<double> bits(n), goc(n);
+    check(ona_pop_download(e_, 0, n, h_aln_.data(), h_inv_.data(), h_mask_.data()));
+    check(ona_pop_get_counters(e_, 0, n, cons.data(), ind.data(), bits.data(), goc.data(), nullptr, nullptr));
+    for (int p = 0; p < n; ++p) {
+        Alignment& a = *alns[p];
+        for (int i = 0; i < n2_; ++i) {
+            a.aln[i] = h_aln_[(size_t)p * n2_ + i];
+            a.alnInv[i] = h_inv_[(size_t)p * n2_ + i];
+            a.alnMask[i] = h_mask_[(size_t)p * n2_ + i] != 0;
+        }
+        a.currConservedCount = cons[p];
+        a.currInducedCount = ind[p];
+        if (a.bitscores) a.currBitscore = bits[p];
+        if (a.gocs) a.currGOC = goc[p];
+    }
+}
+
+Context& context_for(const Network* n1, const Network* n2, const BLASTDict* bit, const GOCDict* goc) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_tuple(n1, n2, bit, goc);
+    auto it = g_ctx.find(key);
+    if (it == g_ctx.end()) it = g_ctx.emplace(key, std::unique_ptr<Context>(new Context(n1, n2, bit, goc))).first;
+    return *it->second;
+}
+Context& context_for(const Alignment& a) { return context_for(a.net1, a.net2, a.bitscores, a.gocs); }
+
+Scratch score_from_scratch(const Alignment& a) {
+    Context& c = context_for(a);
+    std::lock_guard<std::mutex> lk(c.lock());
+    std::vector<Alignment*> one{const_cast<Alignment*>(&a)};
+    c.ensure_slots(1);
+    // only the permutation and mask matter here; the cached counters are left alone
+    std::vector<int> aln(a.aln.begin(), a.aln.end());
+    std::vector<unsigned char> mask(a.alnMask.size());
+    bool any_off = false;
+    for (size_t i = 0; i < mask.size(); ++i) {
+        mask[i] = a.alnMask[i] ? 1 : 0;
+        any_off |= !mask[i];
+    }
+    check(ona_pop_upload(c.engine(), 0, 1, aln.data(), any_off ? mask.data() : nullptr));
+    Scratch s{};
+    check(ona_full_fitness(c.engine(), 0, 1, ONA_SEED_NONE | ONA_SUM_SEQUENTIAL, &s.cons_true, &s.cons_refseed,
+                           &s.induced, &s.bits, &s.goc, &s.size, nullptr));
+    return s;
+}
+
+void seed_counters(Alignment& a) {
+    // Alignment.cpp:437-446: currBitscore = sumBLAST(); currGOC = sumGOC();
+    // currConservedCount = ics()*denom (truncated, H1); currInducedCount = (int)denom
+    const Scratch s = score_from_scratch(a);
+    if (a.bitscores) a.currBitscore = s.bits;
+    if (a.gocs) a.currGOC = s.goc;
+    a.currConservedCount = s.cons_refseed;
+    a.currInducedCount = s.induced;
+}
+
+void apply_swaps(Alignment& a, const std::vector<int>& xy) {
+    if (xy.empty()) return;
+    Context& c = context_for(a);
+    std::lock_guard<std::mutex> lk(c.lock());
+    std::vector<Alignment*> one{&a};
+    c.upload(one);
+    check(ona_apply_swaps(c.engine(), 0, 1, (int)(xy.size() / 2), xy.data()));
+    c.download(one);
+}
+
+}  // namespace ona_host

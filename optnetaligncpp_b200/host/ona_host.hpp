@@ -1,0 +1,75 @@
+// C++ host mirror of the reference's Alignment / localSearch interface on top of the C ABI
+// (include/ona_b200.h).  Shared plumbing of the two drop-in translation units
+//   host/Alignment.cpp   -- replaces the reference's Alignment.cpp
+//   host/localSearch.cpp -- replaces the reference's localSearch.cpp
+// which implement the reference's UNCHANGED headers (Alignment.h, localSearch.h), so that
+// steadystate.cpp / nsgaiimain.cpp / hillclimber.cpp / nsga-ii.cpp / Archive.cpp compile and
+// link against them as they are.
+//
+// Design: a host Alignment object stays the source of truth (the reference copies, assigns
+// and deletes Alignments freely: steadystate.cpp:204-219, Archive.cpp:30-66).  For every
+// batched operation the object's permutation, mask and cached counters are uploaded into a
+// scratch slot of the engine, the GPU does the graph work, and the results are copied back.
+// One engine exists per (net1, net2, bitscores, gocs) tuple and per GPU; its objective list
+// follows the fitnessNames vector of the call.
+#pragma once
+#include <condition_variable>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "Alignment.h"
+#include "../../include/ona_b200.h"
+
+namespace ona_host {
+
+// non-zero C-ABI codes become exceptions again (the reference reports errors by throwing)
+inline void check(int rc) {
+    if (rc != ONA_OK) throw std::runtime_error(std::string("ona_b200: ") + ona_last_error());
+}
+
+class Context {
+public:
+    Context(const Network* n1, const Network* n2, const BLASTDict* bit, const GOCDict* goc);
+    ~Context();
+    ona_engine* engine() { return e_; }
+    int n1() const { return n1_; }
+    int n2() const { return n2_; }
+    // make `names` the engine's objective list (no-op when unchanged); caller holds lock()
+    void use_objectives(const std::vector<fitnessName>& names);
+    // scratch slots [0, count) of the engine, grown on demand; caller holds lock()
+    void ensure_slots(int count);
+    std::mutex& lock() { return mu_; }
+
+    // upload `alns` into slots 0..n-1 (permutation, mask, cached counters)
+    void upload(const std::vector<Alignment*>& alns);
+    // copy slots 0..n-1 back into the objects (permutation, inverse, mask, counters)
+    void download(const std::vector<Alignment*>& alns);
+
+private:
+    ona_engine* e_ = nullptr;
+    int n1_ = 0, n2_ = 0, slots_ = 0;
+    std::vector<int> names_;
+    std::mutex mu_;
+    std::vector<int> h_aln_, h_inv_;
+    std::vector<unsigned char> h_mask_;
+};
+
+// the engine of the networks / score tables an Alignment borrows (created on first use)
+Context& context_for(const Alignment& a);
+Context& context_for(const Network* n1, const Network* n2, const BLASTDict* bit, const GOCDict* goc);
+
+// from-scratch counters of one alignment (Alignment.cpp:437-446 idiom) on the GPU
+struct Scratch {
+    int cons_true, cons_refseed, induced;
+    double bits, goc, size;
+};
+Scratch score_from_scratch(const Alignment& a);
+// seed a's cached counters from scratch exactly like the reference's constructors / shuf
+void seed_counters(Alignment& a);
+// apply an ordered list of doSwap(x,y) to `a` on the GPU (incremental counter updates)
+void apply_swaps(Alignment& a, const std::vector<int>& xy);
+
+}  // namespace ona_host

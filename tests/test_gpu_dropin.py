@@ -1,0 +1,74 @@
+"""GPU: reference callers work unchanged on the drop-in Alignment.cpp / localSearch.cpp.
+
+optnetaligncpp_b200/host/_build/dropin_demo is a driver in the shape of the reference's
+hillclimber.cpp, compiled against the reference's UNCHANGED headers and loader sources and
+linked with this repo's replacement translation units (built in the dev container, where the
+reference tree is).  It must reproduce, bit for bit, what the unmodified reference
+(oracle/_ref) computes for the same seeds: shuf -> computeFitness -> correctHillClimb (several
+host threads, combined into one batched GPU climb) -> UPMX crossover -> mutate -> ics()."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from optnetaligncpp_b200 import synth
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEMO = os.path.join(ROOT, "optnetaligncpp_b200", "host", "_build", "dropin_demo")
+
+
+@pytest.mark.skipif(not os.path.exists(DEMO) or not ref.available(),
+                    reason="drop-in demo / compiled reference not built (dev container only)")
+@pytest.mark.parametrize("with_goc", [False, True])
+def test_dropin_matches_reference(with_goc):
+    pair = synth.make_pair(n1=400, n2=520, m1=2000, m2=2300, max_deg=60, seed=41,
+                           annotations=with_goc, n_terms=200, bit_density=0.01)
+    d = tempfile.mkdtemp()
+    paths = synth.write_text(pair, os.path.join(d, "w"))
+    seed, iters, nthreads = 77, 4000, 3
+    a1 = paths.get("annos1", "-") if with_goc else "-"
+    a2 = paths.get("annos2", "-") if with_goc else "-"
+    out = subprocess.run([DEMO, paths["net1"], paths["net2"], paths["sim"], a1, a2, str(seed), str(iters),
+                          str(nthreads), os.path.join(d, "out")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = [l.split() for l in out.stdout.strip().splitlines()]
+
+    n1, n2 = ref.Net(paths["net1"]), ref.Net(paths["net2"])
+    B = ref.Dict.load_blast(n1, n2, paths["sim"])
+    G = ref.Dict.load_goc(n1, n2, a1, a2) if with_goc else None
+    names = [6, 2] + ([5] if with_goc else [])
+    climbed = []
+    for t in range(nthreads):
+        a = ref.Aln(n1, n2, B, G)
+        a.shuf(seed + t)
+        a.correct_hill_climb(seed + 1000 + t, iters, names)
+        climbed.append(a)
+        got = lines[t]
+        assert got[0] == "climb" and int(got[1]) == t
+        c = a.counters()
+        assert (int(got[3]), int(got[5])) == (c[0], c[1])
+        assert float(got[7]) == c[2] and float(got[9]) == c[3]
+        assert [float(v) for v in got[10:]] == list(a.compute_fitness(names))
+        # Alignment::save output == the reference's permutation
+        al = a.state()[0]
+        saved = [l.split() for l in open(os.path.join(d, "out_%d.aln" % t))]
+        assert len(saved) == pair.n1
+        assert all(int(u[1:]) == i and int(v[1:]) == al[i] for i, (u, v) in enumerate(saved))
+    for t in range(nthreads):
+        child = ref.Aln.crossover(seed + 2000 + t, 0.1, climbed[t], climbed[0], True)
+        child.mutate(seed + 3000 + t, 0.005, True)
+        got = lines[nthreads + t]
+        assert got[0] == "child"
+        c = child.counters()
+        assert (int(got[3]), int(got[5])) == (c[0], c[1])
+        assert float(got[7]) == c[2] and float(got[9]) == c[3]
+        assert float(got[11]) == child.ics()
+        assert [float(v) for v in got[12:]] == list(child.compute_fitness(names))
+    snd = climbed[0].swap_normalized_delta(names, 3, 7)
+    got = float(lines[2 * nthreads][1])
+    assert got == snd or (np.isnan(got) and np.isnan(snd))

@@ -336,3 +336,26 @@ def test_error_behaviour():
     # empty inputs are no-ops
     e.hill_climb(iters=0)
     e.swap_deltas(np.empty((2, 0, 2), np.int32))
+
+
+def test_steepest_step_matches_exhaustive_oracle_scan():
+    """ona_steepest_step == the arg-max of swapNormalizedDelta over the whole n1 x n2 grid with
+    the reference's tie rule (localSearch.cpp:130-188)."""
+    pair = synth.make_pair(n1=60, n2=80, m1=220, m2=260, max_deg=20, seed=6, bit_density=0.05)
+    S = synth.dense_bits(pair)
+    prob = port.Problem(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2, S, None)
+    names = [engine.S3, engine.BITSCORE_SUM]
+    aln, _ = synth.random_population(pair, 2, seed=3)
+    e = engine.Engine.from_pair(pair, names)
+    e.upload(aln)
+    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL)
+    for p in range(2):
+        o = port.Aln(prob, aln[p])
+        o.compute_fitness(names)
+        grid = np.stack(np.meshgrid(np.arange(pair.n1), np.arange(pair.n2), indexing="ij"), -1).reshape(-1, 2)
+        rec = o.swap_delta_records(grid, names, want_snd=True)
+        best, bx, by = -1.0, -1, -1
+        for (x, y), v in zip(grid, rec["snd"]):
+            if v > best:
+                best, bx, by = v, int(x), int(y)
+        assert e.steepest_step(p) == (best, bx, by)
