@@ -52,7 +52,7 @@ struct DevBuf {  // grow-only device scratch
 
 }  // namespace
 
-constexpr int kPipeSlices = 8;
+constexpr int kPipeSlices = 32;  // upper bound; the default number of slices is pipe_slices
 
 struct ona_engine {
     int device = 0;
@@ -67,6 +67,7 @@ struct ona_engine {
     DevObjectives ob{};
     bool small_ids = false;  // n2 < 32768: uint16 shared-memory state
     int group = 8;           // lanes per candidate in the hill-climb kernel's phase 1
+    int pipe_slices = 8;     // host-buffer pipeline depth of ona_swap_deltas
     int delta_group = -1;    // swap-delta kernel: -1 = degree-sorted (default), 0 = flat walk, else lanes per candidate
     int sm_count = 148;
     size_t smem_optin = 0;
@@ -540,6 +541,7 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
         if (v == 4 || v == 8 || v == 16) e->group = v;
         if (v == -1 || v == 0 || v == 1 || v == 4 || v == 8 || v == 16 || v == 32) e->delta_group = v;
     }
+    if (const char* ps = getenv("ONA_PIPE_SLICES")) e->pipe_slices = std::max(1, std::min(kPipeSlices, atoi(ps)));
     if (cudaMalloc(&e->d_flag, sizeof(int)) != cudaSuccess) return bail(fail(ONA_ERR_CUDA, "cudaMalloc"));
     if (cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking) != cudaSuccess ||
@@ -805,7 +807,7 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
     // Software pipeline over slices of the individuals: H2D of slice i+1 (copy-in stream) overlaps
     // the kernel of slice i (engine stream) and the D2H of slice i-1 (copy-out stream); PCIe is
     // full duplex, so with pinned host buffers the call costs about max(H2D, kernel, D2H).
-    const int slices = std::min(count, kPipeSlices);
+    const int slices = std::min(count, e->pipe_slices);
     CU(cudaEventRecord(e->ev_k[0], e->stream));           // copy-in must follow the flag reset / prior work
     CU(cudaStreamWaitEvent(e->s_in, e->ev_k[0], 0));
     for (int sidx = 0; sidx < slices; ++sidx) {

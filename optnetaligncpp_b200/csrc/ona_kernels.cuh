@@ -608,7 +608,10 @@ constexpr int kSortThreads = ONA_SORT_THREADS;
 constexpr int kSortPer = ONA_SORT_PER_THREAD;
 constexpr int kSortCap = kSortThreads * kSortPer;  // candidates per CTA pass
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kHubQuads = 16;                      // more quads than this: walked by a whole warp
+#ifndef ONA_HUB_QUADS
+#define ONA_HUB_QUADS 16
+#endif
+constexpr int kHubQuads = ONA_HUB_QUADS;           // more quads than this: walked by a whole warp
 constexpr int kSortBins = kHubQuads + 2;           // 0..kHubQuads exact, last bin = hubs
 
 template <typename T>
