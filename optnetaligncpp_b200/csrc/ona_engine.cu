@@ -81,6 +81,8 @@ struct ona_engine {
     DevBuf<double> t_d0, t_d1, t_d2, t_d3, t_d4, t_seq;
     DevBuf<unsigned char> t_u0, t_mask;
     DevBuf<long long> t_l0;
+    DevBuf<FullPartial> t_part;
+    DevBuf<unsigned int> t_ticket;
     int* d_flag = nullptr;
     // copy streams + events of the host-buffer pipeline (ona_swap_deltas)
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -232,8 +234,18 @@ int launch_full(ona_engine* e, int first, int count, int seed_mode, int sequenti
         CU(e->t_seq.need((size_t)count * 2 * e->g.n1));
         seq = e->t_seq.p;
     }
-    k_full_fitness<T><<<count, 512, smem, e->stream>>>(e->g, e->S, e->G, e->ob, e->pop, first,
-                                                      seed_mode, sequential, seq, out);
+    // parts per individual: about two waves of CTAs, but at least ~4k edges per part
+    int parts = std::max(1, (2 * e->sm_count * 2 + count - 1) / count);
+    parts = std::min(parts, std::max(1, (e->g.ne1 + e->g.ne2) / 8192));
+    parts = std::min(parts, 32);
+    CU(e->t_part.need((size_t)count * parts));
+    if (e->t_ticket.cap < (size_t)count) {
+        CU(e->t_ticket.need((size_t)count));
+        CU(cudaMemsetAsync(e->t_ticket.p, 0, e->t_ticket.cap * sizeof(unsigned int), e->stream));
+    }
+    dim3 grid(parts, count);
+    k_full_fitness<T><<<grid, 512, smem, e->stream>>>(e->g, e->S, e->G, e->ob, e->pop, first, seed_mode,
+                                                     sequential, seq, e->t_part.p, e->t_ticket.p, out);
     e->launches++;
     CU(cudaGetLastError());
     return ONA_OK;
@@ -564,6 +576,7 @@ void ona_engine_destroy(ona_engine* e) {
     e->t_i0.release(); e->t_i1.release(); e->t_i2.release(); e->t_xy.release();
     e->t_d0.release(); e->t_d1.release(); e->t_d2.release(); e->t_d3.release(); e->t_d4.release();
     e->t_seq.release(); e->t_u0.release(); e->t_mask.release(); e->t_l0.release();
+    e->t_part.release(); e->t_ticket.release();
     if (e->d_flag) cudaFree(e->d_flag);
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);

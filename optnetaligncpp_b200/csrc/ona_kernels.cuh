@@ -94,71 +94,109 @@ struct FullOut {
     double* fit;
 };
 
+// partial results of one part of one individual, reduced by the last part to finish
+struct FullPartial {
+    int c, ind, sz, pad;
+    double sb, sg;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(512)
 k_full_fitness(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first,
-               int seed_mode, int sequential, double* __restrict__ seq_scratch, FullOut out) {
+               int seed_mode, int sequential, double* __restrict__ seq_scratch,
+               FullPartial* __restrict__ partials, unsigned int* __restrict__ tickets, FullOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s_aln, *s_inv;
     __shared__ double red_d[32];
     __shared__ int red_i[32];
+    __shared__ bool s_last;
     constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
-    const int pl = blockIdx.x, p = first + pl;
+    // grid = (parts, individuals): each part takes a contiguous slice of every loop, so that a
+    // small population still fills the SMs; the last part to finish folds the partials in part
+    // order (deterministic) and finalises
+    const int part = blockIdx.x, parts = gridDim.x;
+    const int pl = blockIdx.y, p = first + pl;
     State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
     __syncthreads();
 
     int c = 0, ind = 0, sz = 0;
-    for (int e = threadIdx.x; e < g.ne1; e += blockDim.x) {
-        const uint32_t ru = s_aln[__ldg(g.eu1 + e)], rv = s_aln[__ldg(g.ev1 + e)];
-        if (!((ru | rv) & FLAG)) c += probe(g, (int)(ru & MASK), (int)(rv & MASK));
+    {
+        const int lo = (int)((long long)g.ne1 * part / parts), hi = (int)((long long)g.ne1 * (part + 1) / parts);
+#pragma unroll 4
+        for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+            const uint32_t ru = s_aln[__ldg(g.eu1 + e)], rv = s_aln[__ldg(g.ev1 + e)];
+            if (!((ru | rv) & FLAG)) c += probe(g, (int)(ru & MASK), (int)(rv & MASK));
+        }
     }
-    for (int e = threadIdx.x; e < g.ne2; e += blockDim.x) {
-        const uint32_t iu = s_inv[__ldg(g.eu2 + e)], iv = s_inv[__ldg(g.ev2 + e)];
-        ind += (iu < (uint32_t)g.n1 && iv < (uint32_t)g.n1) ? 1 : 0;
+    {
+        const int lo = (int)((long long)g.ne2 * part / parts), hi = (int)((long long)g.ne2 * (part + 1) / parts);
+#pragma unroll 4
+        for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+            const uint32_t iu = s_inv[__ldg(g.eu2 + e)], iv = s_inv[__ldg(g.ev2 + e)];
+            ind += (iu < (uint32_t)g.n1 && iv < (uint32_t)g.n1) ? 1 : 0;
+        }
     }
     double sb = 0.0, sg = 0.0;
     double* seq_b = seq_scratch ? seq_scratch + (size_t)pl * 2 * g.n1 : nullptr;
     double* seq_g = seq_b ? seq_b + g.n1 : nullptr;
-    for (int i = threadIdx.x; i < g.n1; i += blockDim.x) {
-        const uint32_t r = s_aln[i];
-        const bool m = !(r & FLAG);
-        sz += m ? 1 : 0;
-        double vb = 0.0, vg = 0.0;
-        if (m) {
-            if (S.kind) vb = table_lookup(S, i, (int)(r & MASK));
-            if (Gt.kind) vg = table_lookup(Gt, i, (int)(r & MASK));
-        }
-        if (sequential) {
-            seq_b[i] = vb;
-            seq_g[i] = vg;
-        } else {
-            sb += vb;
-            sg += vg;
+    {
+        const int lo = (int)((long long)g.n1 * part / parts), hi = (int)((long long)g.n1 * (part + 1) / parts);
+#pragma unroll 2
+        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const uint32_t r = s_aln[i];
+            const bool m = !(r & FLAG);
+            sz += m ? 1 : 0;
+            double vb = 0.0, vg = 0.0;
+            if (m) {
+                if (S.kind) vb = table_lookup(S, i, (int)(r & MASK));
+                if (Gt.kind) vg = table_lookup(Gt, i, (int)(r & MASK));
+            }
+            if (sequential) {
+                seq_b[i] = vb;
+                seq_g[i] = vg;
+            } else {
+                sb += vb;
+                sg += vg;
+            }
         }
     }
     c = block_sum<int>(c, red_i);
     ind = block_sum<int>(ind, red_i);
     sz = block_sum<int>(sz, red_i);
+    sb = block_sum<double>(sb, red_d);
+    sg = block_sum<double>(sg, red_d);
+    if (threadIdx.x == 0) {
+        FullPartial fp;
+        fp.c = c; fp.ind = ind; fp.sz = sz; fp.pad = 0; fp.sb = sb; fp.sg = sg;
+        partials[(size_t)pl * parts + part] = fp;
+        __threadfence();
+        s_last = atomicAdd(tickets + pl, 1u) == (unsigned)(parts - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     __shared__ double s_seq[2];
     if (sequential) {
-        __syncthreads();
         // the reference's index-order fp64 sums (masked-off terms were skipped there; adding
         // their +0.0 here leaves every partial sum unchanged)
         if (threadIdx.x == 0 || threadIdx.x == 32) {
-            const double* src = threadIdx.x == 0 ? seq_b : seq_g;
+            const volatile double* src = threadIdx.x == 0 ? seq_b : seq_g;
             double acc = 0.0;
             if ((threadIdx.x == 0 && S.kind) || (threadIdx.x == 32 && Gt.kind))
                 for (int i = 0; i < g.n1; ++i) acc += src[i];
             s_seq[threadIdx.x == 0 ? 0 : 1] = acc;
         }
         __syncthreads();
-        sb = s_seq[0];
-        sg = s_seq[1];
-    } else {
-        sb = block_sum<double>(sb, red_d);
-        sg = block_sum<double>(sg, red_d);
     }
     if (threadIdx.x == 0) {
+        tickets[pl] = 0;  // ready for the next launch
+        c = 0; ind = 0; sz = 0; sb = 0.0; sg = 0.0;
+        const volatile FullPartial* fp = partials + (size_t)pl * parts;
+        for (int q = 0; q < parts; ++q) {
+            c += fp[q].c; ind += fp[q].ind; sz += fp[q].sz;
+            sb += fp[q].sb; sg += fp[q].sg;
+        }
+        if (sequential) { sb = s_seq[0]; sg = s_seq[1]; }
         // currConservedCount = ics()*denom, truncated (Alignment.cpp:445); ics()==0 when denom==0
         const double denom = (double)ind;
         const double ics = denom == 0.0 ? 0.0 : __ddiv_rn((double)c, denom);
@@ -849,6 +887,12 @@ __device__ __forceinline__ bool commit_conflicts(const DevGraph& g, int xj, int 
     return dirty;
 }
 
+// what one proposal of the round published for the pair tests and the resolve
+struct RoundSlot {
+    int x, y, ax, ay, dc, di;
+    uint4 n1x, n1y, n2x, n2y;  // Bloom signatures of N1(x), N1(y), N2(a_x), N2(a_y)
+};
+
 template <typename T, int G>
 __global__ void __launch_bounds__(kRound * G)
 k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first,
@@ -858,9 +902,11 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
              int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s_aln, *s_inv;
-    __shared__ int s_x[kRound], s_y[kRound], s_dc[kRound], s_di[kRound];
+    __shared__ RoundSlot s_slot[kRound];
+    __shared__ unsigned s_conf[kRound];
     __shared__ long long s_pos;
     constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
+    constexpr int kWarps = kRound * G / 32;
 
     const int pl = blockIdx.x, p = first + pl;
     State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
@@ -868,8 +914,9 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
     const int obj = force_obj != -3 ? force_obj : (objs ? objs[pl] : -1);
     const unsigned long long ikey = rng_individual_key(seed, (unsigned long long)(island_offset + p));
     const int grp = threadIdx.x / G, gl = threadIdx.x % G;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
     // scalars live in warp 0's registers (replicated over its lanes)
     Scalars cur;
@@ -882,7 +929,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
         const long long pos = s_pos;
         if (pos >= iters) break;
         const int nvalid = (int)min((long long)kRound, iters - pos);
-        // ---- phase 1: group `grp` scores proposal pos+grp against the current state
+        // ---- phase 1a: group `grp` scores proposal pos+grp against the current state
         {
             int x = 0, y = 0;
             if (grp < nvalid) {
@@ -906,38 +953,49 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
             di = group_sum<G>(di, gmask);
 #pragma unroll
             for (int off = G / 2; off > 0; off >>= 1) seen |= __shfl_xor_sync(gmask, seen, off, G);
+            RoundSlot& sl = s_slot[grp];
             if (gl == 0) {
                 special_terms(g, cx, seen, dc, di);
-                s_x[grp] = x; s_y[grp] = y; s_dc[grp] = dc; s_di[grp] = di;
+                sl.x = x; sl.y = y; sl.ax = cx.ax; sl.ay = cx.ay; sl.dc = dc; sl.di = di;
+                s_conf[grp] = 0u;
+            } else if (gl == 1) {
+                sl.n1x = cx.xr ? __ldg(g.sig1 + x) : zero4;
+            } else if (gl == 2) {
+                sl.n1y = cx.yr ? __ldg(g.sig1 + y) : zero4;
+            } else if (gl == 3) {
+                sl.n2x = __ldg(g.sig2 + cx.ax);
+                sl.n2y = __ldg(g.sig2 + cx.ay);
             }
+        }
+        __syncthreads();
+        // ---- phase 1b: all warps build the pair masks.  conf[j] bit i (i < j): committing
+        //      proposal i would make proposal j's score stale
+        {
+            const int j = lane;
+            const RoundSlot& sj = s_slot[j];
+            unsigned bits = 0u;
+            for (int i = warp; i < nvalid - 1; i += kWarps) {
+                const RoundSlot& si = s_slot[i];
+                if (j > i && j < nvalid &&
+                    commit_conflicts(g, sj.x, sj.y, sj.ax, sj.ay, sj.n1x, sj.n1y, sj.n2x, sj.n2y, si.x, si.y, si.ax, si.ay))
+                    bits |= 1u << i;
+            }
+            if (bits) atomicOr(&s_conf[j], bits);
         }
         __syncthreads();
         // ---- phase 2: warp 0 resolves the round in order
         if (threadIdx.x < 32) {
             const int c = lane;
             const bool valid = c < nvalid;
-            const int x = s_x[c], y = s_y[c];
-            int dc = s_dc[c], di = s_di[c];
+            RoundSlot& me = s_slot[c];
+            const int x = me.x, y = me.y;
+            int dc = me.dc, di = me.di;
             ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, x, y);
-            // what this proposal's score depended on (for the conflict test)
-            int ax = (int)(s_aln[x] & MASK), ay = (int)(s_aln[y] & MASK);
-            const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-            const bool xr = x < g.n1, yr = y < g.n1;
-            const uint4 n1x = xr ? __ldg(g.sig1 + x) : zero4, n1y = yr ? __ldg(g.sig1 + y) : zero4;
-            uint4 n2x = __ldg(g.sig2 + ax), n2y = __ldg(g.sig2 + ay);
-            // conf bit i: committing proposal i (< c) would make this lane's score stale.  All
-            // pairs are tested up front, so the loads overlap instead of stalling every commit.
-            unsigned conf = 0u;
-#pragma unroll 4
-            for (int i = 0; i < nvalid - 1; ++i) {
-                const int xi = __shfl_sync(0xffffffffu, x, i), yi = __shfl_sync(0xffffffffu, y, i);
-                const int axi = __shfl_sync(0xffffffffu, ax, i), ayi = __shfl_sync(0xffffffffu, ay, i);
-                if (c > i && commit_conflicts(g, x, y, ax, ay, n1x, n1y, n2x, n2y, xi, yi, axi, ayi))
-                    conf |= 1u << i;
-            }
+            unsigned conf = s_conf[c];
+            const unsigned lt_mask = (1u << c) - 1u;
 
             int start = 0;
-            unsigned ev = 0u, acc_mask = 0u, dirty_mask = 0u;
+            unsigned ev = 0u, ties = 0u, acc_mask = 0u, dirty_mask = 0u;
             bool need_decide = true, acc = false;
             double ub = 0.0, ug = 0.0;
             Scalars nw = cur;
@@ -950,12 +1008,18 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     undo_accumulators(nw, sd, ub, ug);
                     const bool pert = !acc && (__double_as_longlong(ub) != __double_as_longlong(cur.bits) ||
                                                __double_as_longlong(ug) != __double_as_longlong(cur.goc));
+                    // a tie: accepted and leaves every counter / accumulator bit as it is
+                    const bool tie = acc && nw.C == cur.C && nw.I == cur.I && nw.size == cur.size &&
+                                     __double_as_longlong(nw.bits) == __double_as_longlong(cur.bits) &&
+                                     __double_as_longlong(nw.goc) == __double_as_longlong(cur.goc);
                     ev = __ballot_sync(0xffffffffu, acc || pert);
+                    ties = __ballot_sync(0xffffffffu, tie);
                     need_decide = false;
                 }
                 // next thing that needs attention: an accept / perturbing reject, or a proposal
                 // whose score went stale (dirty) and must be re-scored before it is judged
-                const unsigned pending = (ev | dirty_mask) & vmask & (start >= 32 ? 0u : ~((1u << start) - 1u));
+                const unsigned from = start >= 32 ? 0u : ~((1u << start) - 1u);
+                const unsigned pending = (ev | dirty_mask) & vmask & from;
                 if (pending == 0u) break;
                 const int e = __ffs(pending) - 1;
                 if ((dirty_mask >> e) & 1u) {
@@ -972,17 +1036,46 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     if (c == e) {
                         dc = rdc; di = rdi;
                         sd = score_delta<T>(g, S, Gt, s_aln, x, y);
-                        ax = cx.ax; ay = cx.ay;
-                        n2x = __ldg(g.sig2 + ax); n2y = __ldg(g.sig2 + ay);
+                        me.ax = cx.ax; me.ay = cx.ay;
+                        me.n2x = __ldg(g.sig2 + cx.ax); me.n2y = __ldg(g.sig2 + cx.ay);
                     }
+                    __syncwarp();
                     // proposal e now has (possibly) new images: refresh bit e of the later lanes
                     if (c > e) {
                         conf &= ~(1u << e);
-                        if (commit_conflicts(g, x, y, ax, ay, n1x, n1y, n2x, n2y, xe, ye, cx.ax, cx.ay)) conf |= 1u << e;
+                        const RoundSlot& se = s_slot[e];
+                        if (commit_conflicts(g, x, y, me.ax, me.ay, me.n1x, me.n1y, me.n2x, me.n2y, se.x, se.y, se.ax, se.ay))
+                            conf |= 1u << e;
                     }
                     dirty_mask &= ~(1u << e);
                     start = e;            // judge it now
                     need_decide = true;
+                    continue;
+                }
+                if ((ties >> e) & 1u) {
+                    // a run of tie accepts: nothing they do changes a later decision, so all of
+                    // them up to the next non-tie event (or the first proposal that one of them
+                    // makes stale) are committed at once
+                    const unsigned other = ((ev & ~ties) | dirty_mask) & vmask & from;   // non-tie events ahead
+                    const int ne = other ? __ffs(other) - 1 : 32;
+                    const unsigned below_ne = ne >= 32 ? 0xffffffffu : ((1u << ne) - 1u);
+                    const unsigned run = ties & vmask & from & below_ne;
+                    // proposals (of any kind) that an earlier tie of the run makes stale
+                    const unsigned stale = __ballot_sync(0xffffffffu, (conf & run & lt_mask) != 0u) & vmask & from;
+                    const int jd = stale ? __ffs(stale) - 1 : 32;
+                    const unsigned commit = run & (jd >= 32 ? 0xffffffffu : ((1u << jd) - 1u));
+                    if ((commit >> c) & 1u) {  // disjoint positions and images: parallel commits are race-free
+                        const uint32_t rx = s_aln[x], ry = s_aln[y];
+                        s_aln[x] = (T)ry;
+                        s_aln[y] = (T)rx;
+                        s_inv[ry & MASK] = (T)((uint32_t)x | (ry & FLAG));
+                        s_inv[rx & MASK] = (T)((uint32_t)y | (rx & FLAG));
+                    }
+                    acc_mask |= commit;
+                    n_acc += __popc(commit);
+                    dirty_mask |= __ballot_sync(0xffffffffu, (conf & commit & lt_mask) != 0u) & vmask;
+                    start = min(jd, ne);
+                    __syncwarp();
                     continue;
                 }
                 const bool e_acc = __shfl_sync(0xffffffffu, (int)acc, e) != 0;
@@ -995,23 +1088,17 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                         s_inv[ry & MASK] = (T)((uint32_t)x | (ry & FLAG));
                         s_inv[rx & MASK] = (T)((uint32_t)y | (rx & FLAG));
                     }
-                    Scalars nx;
-                    nx.C = __shfl_sync(0xffffffffu, nw.C, e);
-                    nx.I = __shfl_sync(0xffffffffu, nw.I, e);
-                    nx.size = __shfl_sync(0xffffffffu, nw.size, e);
-                    nx.bits = __shfl_sync(0xffffffffu, nw.bits, e);
-                    nx.goc = __shfl_sync(0xffffffffu, nw.goc, e);
-                    const bool changed = nx.C != cur.C || nx.I != cur.I || nx.size != cur.size ||
-                                         __double_as_longlong(nx.bits) != __double_as_longlong(cur.bits) ||
-                                         __double_as_longlong(nx.goc) != __double_as_longlong(cur.goc);
-                    cur = nx;
+                    cur.C = __shfl_sync(0xffffffffu, nw.C, e);
+                    cur.I = __shfl_sync(0xffffffffu, nw.I, e);
+                    cur.size = __shfl_sync(0xffffffffu, nw.size, e);
+                    cur.bits = __shfl_sync(0xffffffffu, nw.bits, e);
+                    cur.goc = __shfl_sync(0xffffffffu, nw.goc, e);
                     acc_mask |= 1u << e;
                     n_acc++;
                     // later proposals whose scores this commit makes stale (precomputed pair tests)
-                    const bool dirty = ((conf >> e) & 1u) != 0u;
-                    dirty_mask |= __ballot_sync(0xffffffffu, dirty && c > e) & vmask;
+                    dirty_mask |= __ballot_sync(0xffffffffu, ((conf >> e) & 1u) != 0u && c > e) & vmask;
                     start = e + 1;
-                    if (changed) need_decide = true;   // later decisions see new current objectives
+                    need_decide = true;   // later decisions see new current objectives
                     __syncwarp();
                 } else {
                     // rejected, but the undo left different accumulator bits: carry them forward
