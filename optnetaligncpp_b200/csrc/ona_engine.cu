@@ -67,6 +67,7 @@ struct ona_engine {
     DevObjectives ob{};
     bool small_ids = false;  // n2 < 32768: uint16 shared-memory state
     int group = 8;           // lanes per candidate in the hill-climb kernel's phase 1
+    bool group_forced = false;
     int pipe_slices = 8;     // host-buffer pipeline depth of ona_swap_deltas
     int delta_group = -1;    // swap-delta kernel: -1 = degree-sorted (default), 0 = flat walk, else lanes per candidate
     int sm_count = 148;
@@ -353,7 +354,11 @@ int launch_climb_tg(ona_engine* e, int first, int count, long long iters, const 
 int launch_climb(ona_engine* e, int first, int count, long long iters, const int* xy_dev,
                  unsigned long long seed, const int* objs_dev, int force_obj,
                  unsigned char* acc_dev, long long* nacc_dev) {
-    const int G = (e->group == 4 || e->group == 16) ? e->group : 8;
+    // lanes per proposal: 8 by default; 4 (128-thread CTAs, twice as many resident individuals)
+    // when the batch is large enough to fill the SMs several times over
+    int G = e->group;
+    if (G != 4 && G != 16) G = 8;
+    if (!e->group_forced && count > 3 * e->sm_count) G = 4;
     if (e->small_ids) {
         if (G == 4) return launch_climb_tg<uint16_t, 4>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
         if (G == 16) return launch_climb_tg<uint16_t, 16>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
@@ -550,7 +555,7 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
     e->pop.n2p = (pr->n2 + 1 + 3) / 4 * 4;  // + the dummy slot n2
     if (const char* gs = getenv("ONA_GROUP")) {
         const int v = atoi(gs);
-        if (v == 4 || v == 8 || v == 16) e->group = v;
+        if (v == 4 || v == 8 || v == 16) { e->group = v; e->group_forced = true; }
         if (v == -1 || v == 0 || v == 1 || v == 4 || v == 8 || v == 16 || v == 32) e->delta_group = v;
     }
     if (const char* ps = getenv("ONA_PIPE_SLICES")) e->pipe_slices = std::max(1, std::min(kPipeSlices, atoi(ps)));

@@ -874,17 +874,30 @@ __device__ __forceinline__ bool bloom_has(const uint4& sg, int id) {
 __device__ __forceinline__ bool commit_conflicts(const DevGraph& g, int xj, int yj, int axj, int ayj,
                                                  const uint4& n1x, const uint4& n1y, const uint4& n2x,
                                                  const uint4& n2y, int xi, int yi, int axi, int ayi) {
-    bool dirty = (xj == xi) | (xj == yi) | (yj == xi) | (yj == yi);
+    const bool same = (xj == xi) | (xj == yi) | (yj == xi) | (yj == yi);
     const bool xir = xi < g.n1, yir = yi < g.n1;
-    if (xir && bloom_has(n1x, xi)) dirty |= ((__ldg(g.adj1 + (size_t)xj * g.W1 + (xi >> 5)) >> (xi & 31)) & 1u) != 0u;
-    if (yir && bloom_has(n1x, yi)) dirty |= ((__ldg(g.adj1 + (size_t)xj * g.W1 + (yi >> 5)) >> (yi & 31)) & 1u) != 0u;
-    if (xir && bloom_has(n1y, xi)) dirty |= ((__ldg(g.adj1 + (size_t)yj * g.W1 + (xi >> 5)) >> (xi & 31)) & 1u) != 0u;
-    if (yir && bloom_has(n1y, yi)) dirty |= ((__ldg(g.adj1 + (size_t)yj * g.W1 + (yi >> 5)) >> (yi & 31)) & 1u) != 0u;
-    if (bloom_has(n2x, axi)) dirty |= probe(g, axj, axi) != 0;
-    if (bloom_has(n2x, ayi)) dirty |= probe(g, axj, ayi) != 0;
-    if (bloom_has(n2y, axi)) dirty |= probe(g, ayj, axi) != 0;
-    if (bloom_has(n2y, ayi)) dirty |= probe(g, ayj, ayi) != 0;
-    return dirty;
+    // all eight Bloom tests first, then the (rare) exact probes as independent predicated loads
+    const bool h0 = xir & bloom_has(n1x, xi), h1 = yir & bloom_has(n1x, yi);
+    const bool h2 = xir & bloom_has(n1y, xi), h3 = yir & bloom_has(n1y, yi);
+    const bool h4 = bloom_has(n2x, axi), h5 = bloom_has(n2x, ayi);
+    const bool h6 = bloom_has(n2y, axi), h7 = bloom_has(n2y, ayi);
+    if (!(h0 | h1 | h2 | h3 | h4 | h5 | h6 | h7)) return same;
+    const uint32_t* r1x = g.adj1 + (size_t)xj * g.W1;
+    const uint32_t* r1y = g.adj1 + (size_t)yj * g.W1;
+    const uint32_t* r2x = g.adj2 + (size_t)axj * g.W;
+    const uint32_t* r2y = g.adj2 + (size_t)ayj * g.W;
+    unsigned w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u, w4 = 0u, w5 = 0u, w6 = 0u, w7 = 0u;
+    if (h0) w0 = __ldg(r1x + (xi >> 5));
+    if (h1) w1 = __ldg(r1x + (yi >> 5));
+    if (h2) w2 = __ldg(r1y + (xi >> 5));
+    if (h3) w3 = __ldg(r1y + (yi >> 5));
+    if (h4) w4 = __ldg(r2x + (axi >> 5));
+    if (h5) w5 = __ldg(r2x + (ayi >> 5));
+    if (h6) w6 = __ldg(r2y + (axi >> 5));
+    if (h7) w7 = __ldg(r2y + (ayi >> 5));
+    const unsigned hit = ((w0 >> (xi & 31)) | (w1 >> (yi & 31)) | (w2 >> (xi & 31)) | (w3 >> (yi & 31)) |
+                          (w4 >> (axi & 31)) | (w5 >> (ayi & 31)) | (w6 >> (axi & 31)) | (w7 >> (ayi & 31))) & 1u;
+    return same | (hit != 0u);
 }
 
 // what one proposal of the round published for the pair tests and the resolve

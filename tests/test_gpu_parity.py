@@ -359,3 +359,69 @@ def test_steepest_step_matches_exhaustive_oracle_scan():
             if v > best:
                 best, bx, by = v, int(x), int(y)
         assert e.steepest_step(p) == (best, bx, by)
+
+
+def test_human_scale_pair_matches_oracle():
+    """C4 shape (n1 = n2 = 20 000, 200 k edges each, --ics --blastsum): no dummy positions, so the
+    induced count is constant and ICS follows EC; a sample of the population against the oracle."""
+    pair = synth.make_pair(n1=20000, n2=20000, m1=200000, m2=200000, seed=synth.DEFAULT_SEED + 4,
+                           bit_density=2e-4)
+    S = synth.dense_bits(pair)                       # untouched pages stay virtual
+    prob = port.Problem(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2, S, None)
+    names = [engine.ICS, engine.BITSCORE_SUM]
+    P, K, iters = 6, 3000, 3000
+    aln, _ = synth.random_population(pair, P, seed=21)
+    e = engine.Engine.from_pair(pair, names)
+    e.upload(aln)
+    r = e.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
+    xy = synth.random_candidates(pair, P, K, seed=22)
+    d = e.swap_deltas(xy, want=("cons", "ind", "bits", "fit", "improved"))
+    hxy = synth.random_candidates(pair, P, iters, seed=23)
+    acc, _ = e.hill_climb(xy=hxy, want_accepted=True)
+    a, _, _ = e.download()
+    c = e.counters()
+    for p in range(P):
+        o = port.Aln(prob, aln[p])
+        assert (r["cons_ref"][p], r["ind"][p], r["bits"][p]) == o.counters()[:3]
+        assert r["cons_true"][p] == o.conserved_true()
+        rec = o.swap_delta_records(xy[p], names)
+        for k in ("cons", "ind", "improved"):
+            assert np.array_equal(d[k][p], rec[k]), k
+        assert np.array_equal(d["bits"][p], rec["bits"]) and np.array_equal(d["fit"][p], rec["fit"], equal_nan=True)
+        assert (d["ind"][p] == r["ind"][p]).all()            # n1 == n2: I never changes
+        assert np.array_equal(acc[p], o.hill_climb_replay(hxy[p], names, want_accepted=True))
+        assert np.array_equal(a[p], o.state()[0])
+        assert (c["cons"][p], c["ind"][p], c["bits"][p]) == o.counters()[:3]
+
+
+def test_goc_objective_yeast_fly_shape():
+    """C3 shape: the yeast-fly pair with GO annotations (dense 6000 x 8000 Jaccard table on the
+    device) and the GOC objective; sampled individuals against the oracle, fp64 accumulators
+    bit for bit (incremental updates in the reference's order)."""
+    pair = synth.make_pair(seed=synth.DEFAULT_SEED + 1, annotations=True)
+    G = synth.dense_goc(pair)
+    S = synth.dense_bits(pair)
+    prob = port.Problem(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2, S, G)
+    names = [engine.S3, engine.BITSCORE_SUM, engine.GOC]
+    P, K, iters = 4, 4000, 8000
+    aln, _ = synth.random_population(pair, P, seed=31)
+    e = engine.Engine.from_pair(pair, names, use_goc=True, goc_dense=G)
+    e.upload(aln)
+    r = e.full_fitness(seed_mode=engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL)
+    xy = synth.random_candidates(pair, P, K, seed=32)
+    d = e.swap_deltas(xy)
+    hxy = synth.random_candidates(pair, P, iters, seed=33)
+    acc, _ = e.hill_climb(xy=hxy, want_accepted=True)
+    a, _, _ = e.download()
+    c = e.counters()
+    for p in range(P):
+        o = port.Aln(prob, aln[p])
+        assert (r["cons_ref"][p], r["ind"][p], r["bits"][p], r["goc"][p]) == o.counters()
+        rec = o.swap_delta_records(xy[p], names, want_snd=True)
+        for k in ("cons", "ind", "improved"):
+            assert np.array_equal(d[k][p], rec[k]), k
+        for k in ("bits", "goc", "fit", "snd"):
+            assert np.array_equal(d[k][p], rec[k], equal_nan=True), k
+        assert np.array_equal(acc[p], o.hill_climb_replay(hxy[p], names, want_accepted=True))
+        assert np.array_equal(a[p], o.state()[0])
+        assert (c["cons"][p], c["ind"][p], c["bits"][p], c["goc"][p]) == o.counters()
