@@ -193,82 +193,6 @@ __device__ __forceinline__ double objective(int name, const Scalars& s, unsigned
 }
 
 // ------------------------------------------------------ topology delta (S1,S2,S4)
-// One candidate swap (x,y) evaluated by a group of G lanes (gl = lane in group) against
-// the packed state in shared memory.  Returns this lane's PARTIAL (dcons, dind); the
-// caller sums over the group.  No state is modified.
-//
-//   dcons = (cc'(x,-1) + cc'(y,x)) - (cc(x,-1) + cc(y,x))      Alignment.cpp:492-493,506-507,516
-//   dind  = (ic'(a_x,-1) + ic'(a_y,a_x)) - (ic(a_x,-1) + ic(a_y,a_x))   :494-495,509-510,518
-// with primes = after exchanging the images AND mask bits of x and y (:496-504).
-template <typename T, int G>
-__device__ __forceinline__ void topo_delta(const DevGraph& g, const T* s_aln, const T* s_inv,
-                                           int x, int y, int gl,
-                                           int& dc, int& di) {
-    constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
-    dc = 0;
-    di = 0;
-    if (x == y) return;  // doSwap(x,x): every term cancels (conservedCount n1==ignore, :795)
-    const uint32_t rx = s_aln[x], ry = s_aln[y];
-    const int ax = (int)(rx & MASK), ay = (int)(ry & MASK);
-    const int mx = (rx & FLAG) ? 0 : 1, my = (ry & FLAG) ? 0 : 1;
-    const bool xr = x < g.n1, yr = y < g.n1;
-    const uint32_t* __restrict__ rowx = g.adj2 + (size_t)ax * (size_t)g.W;
-    const uint32_t* __restrict__ rowy = g.adj2 + (size_t)ay * (size_t)g.W;
-
-    if (xr) {  // conservedCount(x, ., ., -1) before and after
-        const int b = __ldg(g.rp1 + x), e = __ldg(g.rp1 + x + 1);
-        for (int k = b + gl; k < e; k += G) {
-            const int t = __ldg(g.col1 + k);
-            const uint32_t rt = s_aln[t];
-            int it = (int)(rt & MASK), mt = (rt & FLAG) ? 0 : 1;
-            int it2 = it, mt2 = mt;
-            if (t == x) { it2 = ay; mt2 = my; }
-            else if (t == y) { it2 = ax; mt2 = mx; }
-            const int o = mx & mt & (int)((__ldg(rowx + (it >> 5)) >> (it & 31)) & 1u);
-            const int n = my & mt2 & (int)((__ldg(rowy + (it2 >> 5)) >> (it2 & 31)) & 1u);
-            dc += n - o;
-        }
-    }
-    if (yr) {  // conservedCount(y, ., ., ignore = x)
-        const int b = __ldg(g.rp1 + y), e = __ldg(g.rp1 + y + 1);
-        for (int k = b + gl; k < e; k += G) {
-            const int t = __ldg(g.col1 + k);
-            if (t == x) continue;
-            const uint32_t rt = s_aln[t];
-            int it = (int)(rt & MASK), mt = (rt & FLAG) ? 0 : 1;
-            int it2 = it, mt2 = mt;
-            if (t == y) { it2 = ax; mt2 = mx; }
-            const int o = my & mt & (int)((__ldg(rowy + (it >> 5)) >> (it & 31)) & 1u);
-            const int n = mx & mt2 & (int)((__ldg(rowx + (it2 >> 5)) >> (it2 & 31)) & 1u);
-            dc += n - o;
-        }
-    }
-    // "alive" = pre-image is a real, unmasked node of net1 (inducedCount guard, :813,:820)
-    const int Lx_old = (xr ? 1 : 0) & mx, Lx_new = (yr ? 1 : 0) & mx;
-    const int Ly_old = (yr ? 1 : 0) & my, Ly_new = (xr ? 1 : 0) & my;
-    if (Lx_old != Lx_new || Ly_old != Ly_new) {  // otherwise the induced subgraph is unchanged
-        {
-            const int b = __ldg(g.rp2 + ax), e = __ldg(g.rp2 + ax + 1);
-            for (int k = b + gl; k < e; k += G) {
-                const int v = __ldg(g.col2 + k);
-                const int ao = ((uint32_t)s_inv[v] < (uint32_t)g.n1) ? 1 : 0;
-                const int an = (v == ax) ? Lx_new : (v == ay) ? Ly_new : ao;
-                di += (Lx_new & an) - (Lx_old & ao);
-            }
-        }
-        {
-            const int b = __ldg(g.rp2 + ay), e = __ldg(g.rp2 + ay + 1);
-            for (int k = b + gl; k < e; k += G) {
-                const int v = __ldg(g.col2 + k);
-                if (v == ax) continue;  // ignore = a_x (:495,:510)
-                const int ao = ((uint32_t)s_inv[v] < (uint32_t)g.n1) ? 1 : 0;
-                const int an = (v == ay) ? Ly_new : ao;
-                di += (Ly_new & an) - (Ly_old & ao);
-            }
-        }
-    }
-}
-
 // ---- quad-CSR walkers (the sorted swap-delta kernel) -------------------------------------
 // Per-candidate context: images, masks and "alive" flags before/after the exchange.
 struct SwapCtx {

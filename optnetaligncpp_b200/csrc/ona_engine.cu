@@ -69,7 +69,6 @@ struct ona_engine {
     int group = 8;           // lanes per candidate in the hill-climb kernel's phase 1
     bool group_forced = false;
     int pipe_slices = 8;     // host-buffer pipeline depth of ona_swap_deltas
-    int delta_group = -1;    // swap-delta kernel: -1 = degree-sorted (default), 0 = flat walk, else lanes per candidate
     int sm_count = 148;
     size_t smem_optin = 0;
 
@@ -252,34 +251,6 @@ int launch_full(ona_engine* e, int first, int count, int seed_mode, int sequenti
     return ONA_OK;
 }
 
-template <typename T, int G>
-int launch_deltas_tg(ona_engine* e, int first, int count, int K, const int* xy_dev,
-                     unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
-    const size_t smem = state_smem(e);
-    int rc = set_smem(k_swap_deltas<T, G>, smem);
-    if (rc) return rc;
-    dim3 grid(chunks, count);
-    k_swap_deltas<T, G><<<grid, 256, smem, e->stream>>>(e->g, e->S, e->G, e->ob, e->pop, first, K,
-                                                       xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag);
-    e->launches++;
-    CU(cudaGetLastError());
-    return ONA_OK;
-}
-
-template <typename T>
-int launch_deltas_flat(ona_engine* e, int first, int count, int K, const int* xy_dev,
-                       unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
-    const size_t smem = state_smem(e);
-    int rc = set_smem(k_swap_deltas_flat<T>, smem);
-    if (rc) return rc;
-    dim3 grid(chunks, count);
-    k_swap_deltas_flat<T><<<grid, kFlatWarps * 32, smem, e->stream>>>(
-        e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag);
-    e->launches++;
-    CU(cudaGetLastError());
-    return ONA_OK;
-}
-
 template <typename T>
 int launch_deltas_sorted(ona_engine* e, int first, int count, int K, const int* xy_dev,
                          unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks,
@@ -296,44 +267,19 @@ int launch_deltas_sorted(ona_engine* e, int first, int count, int K, const int* 
     return ONA_OK;
 }
 
-template <typename T>
-int launch_deltas_t(ona_engine* e, int first, int count, int K, const int* xy_dev,
-                    unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
-    if (e->delta_group == -1)
-        return launch_deltas_sorted<T>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
-    if (e->delta_group == 0)
-        return launch_deltas_flat<T>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
-    switch (e->delta_group) {
-        case 1: return launch_deltas_tg<T, 1>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
-        case 4: return launch_deltas_tg<T, 4>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
-        case 16: return launch_deltas_tg<T, 16>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
-        case 32: return launch_deltas_tg<T, 32>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
-        default: return launch_deltas_tg<T, 8>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
-    }
-}
-
-// chunks per individual (grid.x).  The sorted kernel works in passes of kSortCap candidates,
-// so a chunk is a whole number of passes unless that would leave SMs idle.
+// chunks per individual (grid.x).  The kernel works in passes of kSortCap candidates, so a
+// chunk is a whole number of passes unless that would leave SMs idle.
 int pick_chunks(const ona_engine* e, int count, int K) {
-    const size_t smem = state_smem(e) + 1024;
-    int per_sm = (int)std::min<size_t>(8, std::max<size_t>(1, (e->smem_optin ? 233472 : 101376) / smem));
-    const int resident = e->sm_count * per_sm;
-    if (e->delta_group == -1) {
-        int chunks = std::max(1, (K + kSortCap - 1) / kSortCap);
-        while ((long long)chunks * count < 2LL * e->sm_count && K / (chunks * 2) >= 64) chunks *= 2;
-        return chunks;
-    }
-    int chunks = std::max(1, (2 * resident + count - 1) / count);
-    const int max_chunks = std::max(1, (K + 255) / 256);  // at least one pass of 256 candidates per CTA
-    chunks = std::min(chunks, max_chunks);
+    int chunks = std::max(1, (K + kSortCap - 1) / kSortCap);
+    while ((long long)chunks * count < 2LL * e->sm_count && K / (chunks * 2) >= 64) chunks *= 2;
     return chunks;
 }
 
 int launch_deltas(ona_engine* e, int first, int count, int K, const int* xy_dev,
                   unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
     if (e->small_ids)
-        return launch_deltas_t<uint16_t>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
-    return launch_deltas_t<uint32_t>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+        return launch_deltas_sorted<uint16_t>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+    return launch_deltas_sorted<uint32_t>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
 }
 
 template <typename T, int G>
@@ -556,7 +502,6 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
     if (const char* gs = getenv("ONA_GROUP")) {
         const int v = atoi(gs);
         if (v == 4 || v == 8 || v == 16) { e->group = v; e->group_forced = true; }
-        if (v == -1 || v == 0 || v == 1 || v == 4 || v == 8 || v == 16 || v == 32) e->delta_group = v;
     }
     if (const char* ps = getenv("ONA_PIPE_SLICES")) e->pipe_slices = std::max(1, std::min(kPipeSlices, atoi(ps)));
     if (cudaMalloc(&e->d_flag, sizeof(int)) != cudaSuccess) return bail(fail(ONA_ERR_CUDA, "cudaMalloc"));

@@ -249,374 +249,15 @@ __global__ void k_recount_size(DevGraph g, DevPop pop, int first, int count) {
     (void)count;
 }
 
-// --------------------------------------------------------------------------------
-// S1-S7: batched, state-preserving swap deltas.
-// grid = (chunks, individuals); each CTA stages its individual's packed aln/inv in shared
-// memory and scores a contiguous chunk of that individual's K candidates.
-//   phase 1 (topology): groups of G lanes walk the <= 4 neighbour lists of one candidate
-//                       (lanes stride the CSR rows -> coalesced column loads, gathers hit
-//                       shared memory, adjacency tests are single-word probes of the
-//                       L2-resident bit matrix), then shuffle-reduce the integer deltas;
-//   phase 2 (per lane): one candidate per lane -- <= 8 score-table lookups, the objectives
-//                       in the reference's fp64 operation order, accept bit, coalesced stores.
-// --------------------------------------------------------------------------------
+// per-individual summaries of the swap-delta kernel (null = not wanted)
 struct DeltaSummary {
     int* num_improved;    // [count] (atomic)
     double* block_best;   // [count][chunks] best swapNormalizedDelta in the chunk
     long long* block_arg; // [count][chunks] candidate index of the best (lowest index on ties)
 };
 
-template <typename T, int G>
-__global__ void __launch_bounds__(256)
-k_swap_deltas(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first, int K,
-              const int* __restrict__ xy, unsigned long long seed, long long island_offset,
-              int obj, DevDeltaOut out, DeltaSummary sum, int* __restrict__ err_flag) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *s_aln, *s_inv;
-    __shared__ double s_bestv[8];
-    __shared__ long long s_besti[8];
-    const int pl = blockIdx.y, p = first + pl;
-    State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
-
-    Scalars cur;
-    cur.C = pop.cons[p]; cur.I = pop.ind[p]; cur.size = pop.size[p];
-    cur.bits = pop.bits[p]; cur.goc = pop.goc[p];
-    __shared__ double s_curfit[kMaxObj];
-    if (threadIdx.x < ob.M) s_curfit[threadIdx.x] = objective(ob.names[threadIdx.x], cur, g.E1);
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int per = (K + gridDim.x - 1) / gridDim.x;
-    const int lo = blockIdx.x * per, hi = min(K, lo + per);
-    const unsigned long long ikey = rng_individual_key(seed, (unsigned long long)(island_offset + p));
-    constexpr int NG = 32 / G;  // candidates evaluated concurrently per warp in phase 1
-    const int grp = lane / G, gl = lane % G;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
-
-    int n_imp = 0;
-    double bestv = -2.0;
-    long long besti = -1;
-
-    for (int base = lo + warp * 32; base < hi; base += nwarps * 32) {
-        const int c = base + lane;
-        const bool valid = c < hi;
-        int x = 0, y = 0;
-        if (valid) {
-            if (xy) {
-                const int2 v = __ldg(reinterpret_cast<const int2*>(xy) + (size_t)pl * K + c);
-                x = v.x; y = v.y;
-                if ((unsigned)x >= (unsigned)g.n2 || (unsigned)y >= (unsigned)g.n2) {
-                    atomicOr(err_flag, 1);  // reported by the host entry point as ONA_ERR_INVALID
-                    x = 0; y = 0;
-                }
-            } else {
-                rng_proposal(ikey, (unsigned long long)c, g.n1, g.n2, x, y);
-            }
-        }
-        // ---- phase 1
-        int my_dc = 0, my_di = 0;
-        if (G == 1) {
-            topo_delta<T, 1>(g, s_aln, s_inv, x, y, 0, my_dc, my_di);
-        } else {
-#pragma unroll 1
-            for (int sub = 0; sub < G; ++sub) {
-                const int ci = sub * NG + grp;
-                const int cx = __shfl_sync(0xffffffffu, x, ci), cy = __shfl_sync(0xffffffffu, y, ci);
-                int dc, di;
-                topo_delta<T, G>(g, s_aln, s_inv, cx, cy, gl, dc, di);
-                dc = group_sum<G>(dc, gmask);
-                di = group_sum<G>(di, gmask);
-                __syncwarp();
-                const int rdc = __shfl_sync(0xffffffffu, dc, (lane % NG) * G);
-                const int rdi = __shfl_sync(0xffffffffu, di, (lane % NG) * G);
-                if (lane / NG == sub) { my_dc = rdc; my_di = rdi; }
-            }
-        }
-        // ---- phase 2
-        if (valid) {
-            const ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, x, y);
-            const Scalars nw = apply_delta(cur, my_dc, my_di, sd);
-            const size_t o = (size_t)pl * K + c;
-            const bool want_snd = out.snd || sum.block_best;
-            double v;
-            const bool imp = judge_move(ob, obj, cur, s_curfit, nw, g.E1,
-                                        out.fit ? out.fit + o * ob.M : nullptr, want_snd, v);
-            if (out.cons) out.cons[o] = nw.C;
-            if (out.ind) out.ind[o] = nw.I;
-            if (out.bits) out.bits[o] = nw.bits;
-            if (out.goc) out.goc[o] = nw.goc;
-            if (out.improved) out.improved[o] = imp ? 1 : 0;
-            n_imp += imp ? 1 : 0;
-            if (want_snd) {
-                if (out.snd) out.snd[o] = v;
-                if (v > bestv) { bestv = v; besti = c; }  // strict >, first wins (localSearch.cpp:141)
-            }
-        }
-    }
-    if (sum.num_improved) {
-        n_imp = warp_sum<int>(n_imp);
-        if (lane == 0 && n_imp) atomicAdd(sum.num_improved + pl, n_imp);
-    }
-    if (sum.block_best) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bestv, off);
-            const long long oi = __shfl_xor_sync(0xffffffffu, besti, off);
-            if (oi >= 0 && (besti < 0 || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
-        }
-        if (lane == 0) { s_bestv[warp] = bestv; s_besti[warp] = besti; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < nwarps; ++w) {
-                const double ov = s_bestv[w];
-                const long long oi = s_besti[w];
-                if (oi >= 0 && (besti < 0 || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
-            }
-            sum.block_best[(size_t)pl * gridDim.x + blockIdx.x] = bestv;
-            sum.block_arg[(size_t)pl * gridDim.x + blockIdx.x] = besti;
-        }
-    }
-}
-
 // --------------------------------------------------------------------------------
-// S1-S7, load-balanced form (the default): a warp takes 32 candidates at a time.
-//   A. one candidate per lane: images, masks and the <= 4 neighbour-list extents
-//      (N1(x), N1(y), and for real<->dummy swaps N2(a_x), N2(a_y));
-//   B. the 32 candidates' lists are concatenated into ONE flat item list that the warp
-//      walks 32 items per step -- consecutive lanes read consecutive CSR columns
-//      (coalesced), every lane is busy whatever the degree skew, and a hub costs the warp
-//      deg/32 steps instead of stalling one group for deg/G.  Per item: one CSR column
-//      load, one shared-memory gather of the packed state, two single-word probes of the
-//      L2-resident net2 bit matrix (or one alive test for the induced lists).  Item
-//      contributions are combined with a segmented warp scan and accumulated per candidate;
-//   C. one candidate per lane again: <= 8 score-table lookups, objectives in the
-//      reference's fp64 order, accept bit, coalesced stores.
-// --------------------------------------------------------------------------------
-struct __align__(16) CandRec {
-    int offs;            // first flat item of this candidate
-    int e0, e1, e2;      // list ends inside the candidate: [0,e0) N1(x) [e0,e1) N1(y) [e1,e2) N2(a_x) [e2,..) N2(a_y)
-    int b0, b1, b2, b3;  // CSR start of each list minus the list's first item index: k = b[l] + j
-    int x, y;
-    uint32_t ax, ay;     // images, bit 31 set = mask bit off
-};
-
-#ifndef ONA_FLAT_WARPS
-#define ONA_FLAT_WARPS 8
-#endif
-#ifndef ONA_FLAT_MINBLOCKS
-#define ONA_FLAT_MINBLOCKS 4
-#endif
-constexpr int kFlatWarps = ONA_FLAT_WARPS;
-
-template <typename T>
-__global__ void __launch_bounds__(kFlatWarps * 32, ONA_FLAT_MINBLOCKS)
-k_swap_deltas_flat(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first, int K,
-                   const int* __restrict__ xy, unsigned long long seed, long long island_offset,
-                   int obj, DevDeltaOut out, DeltaSummary sum, int* __restrict__ err_flag) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ CandRec s_rec_all[kFlatWarps][32];
-    __shared__ int2 s_acc_all[kFlatWarps][32];
-    __shared__ unsigned char s_r2c_all[kFlatWarps][32];
-    __shared__ double s_bestv[kFlatWarps];
-    __shared__ long long s_besti[kFlatWarps];
-    constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
-    T *s_aln, *s_inv;
-    const int pl = blockIdx.y, p = first + pl;
-    State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
-
-    Scalars cur;
-    cur.C = pop.cons[p]; cur.I = pop.ind[p]; cur.size = pop.size[p];
-    cur.bits = pop.bits[p]; cur.goc = pop.goc[p];
-    __shared__ double s_curfit[kMaxObj];
-    if (threadIdx.x < ob.M) s_curfit[threadIdx.x] = objective(ob.names[threadIdx.x], cur, g.E1);
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    CandRec* s_rec = s_rec_all[warp];
-    int2* s_acc = s_acc_all[warp];
-    unsigned char* s_r2c = s_r2c_all[warp];
-    const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
-    const int per = (K + gridDim.x - 1) / gridDim.x;
-    const int lo = blockIdx.x * per, hi = min(K, lo + per);
-    const unsigned long long ikey = rng_individual_key(seed, (unsigned long long)(island_offset + p));
-
-    int n_imp = 0;
-    double bestv = -2.0;
-    long long besti = -1;
-
-    for (int base = lo + warp * 32; base < hi; base += nwarps * 32) {
-        const int c = base + lane;
-        const bool valid = c < hi;
-        int x = 0, y = 0;
-        if (valid) {
-            if (xy) {
-                const int2 v = __ldg(reinterpret_cast<const int2*>(xy) + (size_t)pl * K + c);
-                x = v.x; y = v.y;
-                if ((unsigned)x >= (unsigned)g.n2 || (unsigned)y >= (unsigned)g.n2) {
-                    atomicOr(err_flag, 1);  // reported by the host entry point as ONA_ERR_INVALID
-                    x = 0; y = 0;
-                }
-            } else {
-                rng_proposal(ikey, (unsigned long long)c, g.n1, g.n2, x, y);
-            }
-        }
-        // ---- A: per-lane candidate record
-        const uint32_t rx = s_aln[x], ry = s_aln[y];
-        const int ax = (int)(rx & MASK), ay = (int)(ry & MASK);
-        const int mx = (rx & FLAG) ? 0 : 1, my = (ry & FLAG) ? 0 : 1;
-        const bool xr = x < g.n1, yr = y < g.n1;
-        const int Lx_old = (xr ? 1 : 0) & mx, Lx_new = (yr ? 1 : 0) & mx;
-        const int Ly_old = (yr ? 1 : 0) & my, Ly_new = (xr ? 1 : 0) & my;
-        int b0 = 0, b1 = 0, b2 = 0, b3 = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-        if (x != y) {  // doSwap(x,x): every term cancels
-            if (xr) { b0 = __ldg(g.rp1 + x); d0 = __ldg(g.rp1 + x + 1) - b0; }
-            if (yr) { b1 = __ldg(g.rp1 + y); d1 = __ldg(g.rp1 + y + 1) - b1; }
-            if (Lx_old != Lx_new || Ly_old != Ly_new) {  // else the induced subgraph is unchanged
-                b2 = __ldg(g.rp2 + ax); d2 = __ldg(g.rp2 + ax + 1) - b2;
-                b3 = __ldg(g.rp2 + ay); d3 = __ldg(g.rp2 + ay + 1) - b3;
-            }
-        }
-        const int tot = d0 + d1 + d2 + d3;
-        int incl = tot;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += o;
-        }
-        const int offs = incl - tot;
-        const int T_items = __shfl_sync(0xffffffffu, incl, 31);
-        const bool nonempty = tot > 0;
-        const unsigned nemask = __ballot_sync(0xffffffffu, nonempty);
-        if (nonempty) s_r2c[__popc(nemask & lt_mask)] = (unsigned char)lane;
-        {
-            CandRec r;
-            r.offs = offs; r.e0 = d0; r.e1 = d0 + d1; r.e2 = d0 + d1 + d2;
-            r.b0 = b0; r.b1 = b1 - r.e0; r.b2 = b2 - r.e1; r.b3 = b3 - r.e2;
-            r.x = x; r.y = y;
-            r.ax = (uint32_t)ax | (mx ? 0u : kGFlag);
-            r.ay = (uint32_t)ay | (my ? 0u : kGFlag);
-            int4* dst = reinterpret_cast<int4*>(&s_rec[lane]);
-            dst[0] = make_int4(r.offs, r.e0, r.e1, r.e2);
-            dst[1] = make_int4(r.b0, r.b1, r.b2, r.b3);
-            dst[2] = make_int4(r.x, r.y, (int)r.ax, (int)r.ay);
-        }
-        s_acc[lane] = make_int2(0, 0);
-        __syncwarp();
-
-        // ---- B: flat item walk, 32 items per step
-        int base_rank = 0;
-        for (int it0 = 0; it0 < T_items; it0 += 32) {
-            const int it = it0 + lane;
-            const unsigned sb = (nonempty && offs >= it0 && offs < it0 + 32) ? (1u << (offs - it0)) : 0u;
-            const unsigned wm = __reduce_or_sync(0xffffffffu, sb);  // candidates starting in this window
-            int contrib = 0, cand = 0;
-            if (it < T_items) {
-                cand = s_r2c[base_rank + __popc(wm & le_mask) - 1];
-                const int4* src = reinterpret_cast<const int4*>(&s_rec[cand]);
-                const int4 q0 = src[0], q1 = src[1], q2 = src[2];
-                const int j = it - q0.x;
-                const int l = (j >= q0.y ? 1 : 0) + (j >= q0.z ? 1 : 0) + (j >= q0.w ? 1 : 0);
-                const int k = (l == 0 ? q1.x : l == 1 ? q1.y : l == 2 ? q1.z : q1.w) + j;
-                const int v = __ldg((l < 2 ? g.col1 : g.col2) + k);
-                const int cx = q2.x, cy = q2.y;
-                const int cax = (int)((uint32_t)q2.z & kGMask), cay = (int)((uint32_t)q2.w & kGMask);
-                const int cmx = ((uint32_t)q2.z & kGFlag) ? 0 : 1, cmy = ((uint32_t)q2.w & kGFlag) ? 0 : 1;
-                if (l < 2) {
-                    // conservedCount terms, Alignment.cpp:799-803, before and after the exchange
-                    const uint32_t rt = s_aln[v];
-                    const int it_ = (int)(rt & MASK), mt = (rt & FLAG) ? 0 : 1;
-                    int it2 = it_, mt2 = mt;
-                    if (v == cx) { it2 = cay; mt2 = cmy; }
-                    else if (v == cy) { it2 = cax; mt2 = cmx; }
-                    const int rowO = l == 0 ? cax : cay, rowN = l == 0 ? cay : cax;
-                    const int mO = l == 0 ? cmx : cmy, mN = l == 0 ? cmy : cmx;
-                    const int o = mO & mt & probe(g, rowO, it_);
-                    const int n = mN & mt2 & probe(g, rowN, it2);
-                    contrib = (l == 1 && v == cx) ? 0 : (n - o);  // ignore = x (:493,:507)
-                } else {
-                    // inducedCount terms, Alignment.cpp:818-822
-                    const bool cxr = cx < g.n1, cyr = cy < g.n1;
-                    const int cLx_old = (cxr ? 1 : 0) & cmx, cLx_new = (cyr ? 1 : 0) & cmx;
-                    const int cLy_old = (cyr ? 1 : 0) & cmy, cLy_new = (cxr ? 1 : 0) & cmy;
-                    const int ao = ((uint32_t)s_inv[v] < (uint32_t)g.n1) ? 1 : 0;
-                    const int an = (v == cax) ? cLx_new : (v == cay) ? cLy_new : ao;
-                    int d;
-                    if (l == 2) d = (cLx_new & an) - (cLx_old & ao);
-                    else d = (v == cax) ? 0 : ((cLy_new & an) - (cLy_old & ao));  // ignore = a_x (:495,:510)
-                    contrib = d << 16;
-                }
-            }
-            base_rank += __popc(wm);
-            // segmented inclusive scan of the packed (dcons | dind << 16) contributions
-            const unsigned heads = wm | 1u;
-            const int seg_start = 31 - __clz((int)(heads & le_mask));
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, contrib, off);
-                if (lane - off >= seg_start) contrib += o;
-            }
-            const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u) || (it + 1 >= T_items);
-            if (it < T_items && tail) {
-                const int dc = (int)(short)(contrib & 0xffff);
-                const int di = (contrib - dc) >> 16;
-                int2 a = s_acc[cand];
-                a.x += dc; a.y += di;
-                s_acc[cand] = a;
-            }
-            __syncwarp();
-        }
-        const int2 accv = s_acc[lane];
-        const int my_dc = accv.x, my_di = accv.y;
-        __syncwarp();
-
-        // ---- C: one candidate per lane
-        if (valid) {
-            const ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, x, y);
-            const Scalars nw = apply_delta(cur, my_dc, my_di, sd);
-            const size_t o = (size_t)pl * K + c;
-            const bool want_snd = out.snd || sum.block_best;
-            double v;
-            const bool imp = judge_move(ob, obj, cur, s_curfit, nw, g.E1,
-                                        out.fit ? out.fit + o * ob.M : nullptr, want_snd, v);
-            if (out.cons) out.cons[o] = nw.C;
-            if (out.ind) out.ind[o] = nw.I;
-            if (out.bits) out.bits[o] = nw.bits;
-            if (out.goc) out.goc[o] = nw.goc;
-            if (out.improved) out.improved[o] = imp ? 1 : 0;
-            n_imp += imp ? 1 : 0;
-            if (want_snd) {
-                if (out.snd) out.snd[o] = v;
-                if (v > bestv) { bestv = v; besti = c; }  // strict >, first wins (localSearch.cpp:141)
-            }
-        }
-    }
-    if (sum.num_improved) {
-        n_imp = warp_sum<int>(n_imp);
-        if (lane == 0 && n_imp) atomicAdd(sum.num_improved + pl, n_imp);
-    }
-    if (sum.block_best) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bestv, off);
-            const long long oi = __shfl_xor_sync(0xffffffffu, besti, off);
-            if (oi >= 0 && (besti < 0 || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
-        }
-        if (lane == 0) { s_bestv[warp] = bestv; s_besti[warp] = besti; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < nwarps; ++w) {
-                const double ov = s_bestv[w];
-                const long long oi = s_besti[w];
-                if (oi >= 0 && (besti < 0 || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
-            }
-            sum.block_best[(size_t)pl * gridDim.x + blockIdx.x] = bestv;
-            sum.block_arg[(size_t)pl * gridDim.x + blockIdx.x] = besti;
-        }
-    }
-}
-
-// --------------------------------------------------------------------------------
-// S1-S7, degree-sorted form (the default).  PPI degree distributions are heavy-tailed
+// S1-S7: batched, state-preserving swap deltas (degree-sorted walk).  PPI degree distributions are heavy-tailed
 // (median 6, max ~250 here), so candidates of one warp have wildly different amounts of
 // neighbour-list work.  Each CTA therefore takes a pass of kSortCap candidates of its
 // individual and
