@@ -187,6 +187,18 @@ int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const i
                    unsigned long long seed, const int* objs, unsigned char* accepted,
                    long long* num_accepted);
 
+/* Throughput form of the hill climb (north_star item 3: "thousands of candidates per individual
+ * at once; accepted swaps are applied in-kernel").  Per individual, rounds of 1024 proposals
+ * are scored against the round's base state; each is accepted or rejected against the base
+ * objectives exactly like one correctHillClimb iteration would (localSearch.cpp:32-47); a
+ * conflict-free subset of the accepted ones (deterministic rule: include/..., csrc kernel
+ * header) is applied and the next round starts from the new state.  Integer counters stay exact
+ * (equal to a from-scratch count); fp64 accumulators agree with sequential application to
+ * <= 1e-9 relative.  NOT trajectory-identical to the reference: proposals that conflict inside
+ * a round are dropped.  Arguments as ona_hill_climb; num_applied [count] out (may be NULL). */
+int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters, const int* xy,
+                           unsigned long long seed, const int* objs, long long* num_applied);
+
 /* Replaces: a run of unconditional Alignment::doSwap calls -- the swap part of
  * Alignment::mutate (Alignment.cpp:456-465) and of UPMX crossover (:197-252) given a
  * host-generated ordered swap list.  xy is [count][nswaps][2]; entries with x < 0 are

@@ -83,6 +83,7 @@ struct ona_engine {
     DevBuf<long long> t_l0;
     DevBuf<FullPartial> t_part;
     DevBuf<unsigned int> t_ticket;
+    DevBuf<unsigned short> t_claims;
     int* d_flag = nullptr;
     // copy streams + events of the host-buffer pipeline (ona_swap_deltas)
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -270,6 +271,7 @@ int launch_deltas_sorted(ona_engine* e, int first, int count, int K, const int* 
 // chunks per individual (grid.x).  The kernel works in passes of kSortCap candidates, so a
 // chunk is a whole number of passes unless that would leave SMs idle.
 int pick_chunks(const ona_engine* e, int count, int K) {
+    // one pass per CTA measured best (more, smaller CTAs overlap their phases better)
     int chunks = std::max(1, (K + kSortCap - 1) / kSortCap);
     while ((long long)chunks * count < 2LL * e->sm_count && K / (chunks * 2) >= 64) chunks *= 2;
     return chunks;
@@ -526,7 +528,7 @@ void ona_engine_destroy(ona_engine* e) {
     e->t_i0.release(); e->t_i1.release(); e->t_i2.release(); e->t_xy.release();
     e->t_d0.release(); e->t_d1.release(); e->t_d2.release(); e->t_d3.release(); e->t_d4.release();
     e->t_seq.release(); e->t_u0.release(); e->t_mask.release(); e->t_l0.release();
-    e->t_part.release(); e->t_ticket.release();
+    e->t_part.release(); e->t_ticket.release(); e->t_claims.release();
     if (e->d_flag) cudaFree(e->d_flag);
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
@@ -971,6 +973,59 @@ int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const i
     TRY(launch_climb(e, first, count, iters, xy_dev, seed, objs_dev, -3, acc_dev, e->t_l0.p));
     TRY(d2h(e, accepted, acc_dev, n));
     TRY(d2h(e, num_accepted, e->t_l0.p, (size_t)count));
+    return finish_checked(e, "proposal outside [0,n2)");
+}
+
+int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters, const int* xy,
+                           unsigned long long seed, const int* objs, long long* num_applied) {
+    TRY(check_range(e, first, count));
+    if (iters < 0) return fail(ONA_ERR_INVALID, "iters < 0");
+    if (count == 0 || iters == 0) {
+        if (num_applied) std::fill(num_applied, num_applied + count, 0ll);
+        return ONA_OK;
+    }
+    if (objs)
+        for (int i = 0; i < count; ++i)
+            if (objs[i] < -1 || objs[i] >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
+    const size_t n = (size_t)count * (size_t)iters;
+    LOCK(e);
+    CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
+    const int* xy_dev = nullptr;
+    if (xy) {
+        CU(e->t_xy.need(2 * n));
+        TRY(h2d(e, e->t_xy.p, xy, 2 * n));
+        xy_dev = e->t_xy.p;
+    }
+    const int* objs_dev = nullptr;
+    if (objs) {
+        CU(e->t_i0.need((size_t)count));
+        TRY(h2d(e, e->t_i0.p, objs, (size_t)count));
+        objs_dev = e->t_i0.p;
+    }
+    CU(e->t_l0.need((size_t)count));
+    // claim arrays (4 x n2 x u16) live in shared memory next to the staged state when they fit
+    const size_t claim_bytes = (size_t)4 * e->g.n2 * 2;
+    size_t smem = state_smem(e) + claim_bytes;
+    unsigned short* claims_global = nullptr;
+    if (smem + 40 * 1024 > e->smem_optin) {
+        smem = state_smem(e);
+        CU(e->t_claims.need((size_t)count * 4 * e->g.n2));
+        claims_global = e->t_claims.p;
+    }
+    if (e->small_ids) {
+        TRY(set_smem(k_hill_climb_batched<uint16_t>, smem));
+        k_hill_climb_batched<uint16_t><<<count, kSortThreads, smem, e->stream>>>(
+            e->g, e->S, e->G, e->ob, e->pop, first, iters, xy_dev, seed, e->island_offset, objs_dev, claims_global,
+            e->t_l0.p, e->d_flag);
+    } else {
+        TRY(set_smem(k_hill_climb_batched<uint32_t>, smem));
+        k_hill_climb_batched<uint32_t><<<count, kSortThreads, smem, e->stream>>>(
+            e->g, e->S, e->G, e->ob, e->pop, first, iters, xy_dev, seed, e->island_offset, objs_dev, claims_global,
+            e->t_l0.p, e->d_flag);
+    }
+    e->launches++;
+    CU(cudaGetLastError());
+    TRY(d2h(e, num_applied, e->t_l0.p, (size_t)count));
     return finish_checked(e, "proposal outside [0,n2)");
 }
 

@@ -293,6 +293,57 @@ constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kHubQuads = ONA_HUB_QUADS;           // more quads than this: walked by a whole warp
 constexpr int kSortBins = kHubQuads + 2;           // 0..kHubQuads exact, last bin = hubs
 
+// Counting sort of one pass by work key (quads to walk), longest first: per-(virtual-)warp
+// histograms by ballots (no shared-memory atomics), an exclusive scan over (bin descending,
+// warp ascending) by warp 0, then the scatter.  key[j] belongs to candidate j*kSortThreads+tid
+// (-1 = beyond the pass).  On return s_order[pos] = candidate, *s_nhub = number of hubs (they
+// come first) and *s_next = 0 (the work-unit counter).  All threads of the CTA must call.
+__device__ __forceinline__ void sort_pass(const int (&key)[kSortPer], unsigned short (*s_cnt)[kSortBins],
+                                          unsigned short* s_order, int* s_nhub, int* s_next) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int rank[kSortPer];
+#pragma unroll
+    for (int j = 0; j < kSortPer; ++j) {
+        const int k = key[j];
+        int r = 0;
+#pragma unroll
+        for (int b = 0; b < kSortBins; ++b) {
+            const unsigned m = __ballot_sync(0xffffffffu, k == b);
+            if (k == b) r = __popc(m & lt_mask);
+            if (lane == 0) s_cnt[j * kSortWarps + warp][b] = (unsigned short)__popc(m);
+        }
+        rank[j] = r;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int running = 0;
+        constexpr int NV = kSortWarps * kSortPer;
+        for (int b = kSortBins - 1; b >= 0; --b) {
+            for (int v0 = 0; v0 < NV; v0 += 32) {
+                const int v = v0 + lane;
+                const int cnt = v < NV ? (int)s_cnt[v][b] : 0;
+                int incl = cnt;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += o;
+                }
+                if (v < NV) s_cnt[v][b] = (unsigned short)(running + incl - cnt);
+                running += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (b == kSortBins - 1 && lane == 0) { *s_nhub = running; *s_next = 0; }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSortPer; ++j) {
+        const int i = j * kSortThreads + threadIdx.x;
+        if (key[j] >= 0) s_order[(int)s_cnt[j * kSortWarps + warp][key[j]] + rank[j]] = (unsigned short)i;
+    }
+    __syncthreads();
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kSortThreads, ONA_SORT_MINBLOCKS)
 k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first, int K,
@@ -330,7 +381,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     for (int pass = lo; pass < hi; pass += kSortCap) {
         const int n = min(kSortCap, hi - pass);
         // ---- A: proposals + work count; per-virtual-warp histogram by ballots
-        int key[kSortPer], rank[kSortPer];
+        int key[kSortPer];
 #pragma unroll
         for (int j = 0; j < kSortPer; ++j) {
             const int i = j * kSortThreads + threadIdx.x;  // index inside the pass
@@ -354,45 +405,9 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                 s_xy[i] = make_int2(x, y);
             }
             const SwapCtx cx = make_ctx<T>(g, s_aln, x, y);
-            const int k = i < n ? min(make_plan(g, cx).e3, kSortBins - 1) : -1;
-            key[j] = k;
-            int r = 0;
-#pragma unroll
-            for (int b = 0; b < kSortBins; ++b) {
-                const unsigned m = __ballot_sync(0xffffffffu, k == b);
-                if (k == b) r = __popc(m & lt_mask);
-                if (lane == 0) s_cnt[j * kSortWarps + warp][b] = (unsigned short)__popc(m);
-            }
-            rank[j] = r;
+            key[j] = i < n ? min(make_plan(g, cx).e3, kSortBins - 1) : -1;
         }
-        __syncthreads();
-        // ---- B: exclusive scan over (bin descending, virtual warp ascending) by warp 0
-        if (warp == 0) {
-            int running = 0;
-            constexpr int NV = kSortWarps * kSortPer;
-            for (int b = kSortBins - 1; b >= 0; --b) {
-                for (int v0 = 0; v0 < NV; v0 += 32) {
-                    const int v = v0 + lane;
-                    const int cnt = v < NV ? (int)s_cnt[v][b] : 0;
-                    int incl = cnt;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const int o = __shfl_up_sync(0xffffffffu, incl, off);
-                        if (lane >= off) incl += o;
-                    }
-                    if (v < NV) s_cnt[v][b] = (unsigned short)(running + incl - cnt);
-                    running += __shfl_sync(0xffffffffu, incl, 31);
-                }
-                if (b == kSortBins - 1 && lane == 0) { s_nhub = running; s_next = 0; }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < kSortPer; ++j) {
-            const int i = j * kSortThreads + threadIdx.x;
-            if (key[j] >= 0) s_order[(int)s_cnt[j * kSortWarps + warp][key[j]] + rank[j]] = (unsigned short)i;
-        }
-        __syncthreads();
+        sort_pass(key, s_cnt, s_order, &s_nhub, &s_next);
         // ---- C: walk.  Warps pull work units, longest first: a hub (walked by the whole warp)
         //      or 32 consecutive sorted candidates (one per lane, equal loop lengths)
         const int nhub = s_nhub;
@@ -776,6 +791,253 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
         for (int j = 0; j < ob.M; ++j) pop.fit[(size_t)p * ob.M + j] = objective(ob.names[j], cur, g.E1);
         if (num_accepted) num_accepted[pl] = n_acc;
     }
+}
+
+// --------------------------------------------------------------------------------
+// Batched hill climb (north_star item 3): per individual, rounds of kSortCap proposals are
+// scored AT ONCE against the round's base state, the accept decisions are taken against the
+// base objectives (the reference's per-candidate decision), a conflict-free
+// subset of the accepted proposals is selected and applied in-kernel, and the next round
+// starts from the new state.  Selection (deterministic): with
+//   WP_j = {x_j, y_j}, WV_j = {a_x, a_y}              what applying j writes (aln / alnInv)
+//   RP_j = N1(x_j) u N1(y_j), RV_j = N2(a_x) u N2(a_y) (only when the induced lists were walked)
+//   wminP[n] / wminV[n] = lowest accepted j writing n,  rminP[n] / rminV[n] = lowest j reading n
+// proposal j is applied iff it is the lowest writer of everything it writes, nobody lower
+// reads what it writes, and nobody lower writes what it reads.  Applied proposals therefore
+// have disjoint write sets and untouched read sets: their integer deltas are exact and
+// additive, so the counters stay equal to a from-scratch count; fp64 accumulators are summed
+// by a fixed reduction tree (agree with the sequential order to <= 1e-9 relative).
+// This is the throughput mode; k_hill_climb is the trajectory-exact one.
+// --------------------------------------------------------------------------------
+constexpr unsigned short kNoClaim = 0xffffu;
+
+__device__ __forceinline__ void claim_min(unsigned short* a, int n, unsigned short j) {
+    unsigned short cur = a[n];
+    while (j < cur) {
+        const unsigned short prev = atomicCAS(a + n, cur, j);
+        if (prev == cur) break;
+        cur = prev;
+    }
+}
+
+// visit every neighbour id of the candidate's quad lists: f(list, id); list 0/1 = net1 lists
+// of x / y, 2/3 = net2 lists of a_x / a_y.  Padding ids (== n2) are skipped.
+template <typename F>
+__device__ __forceinline__ void for_each_neighbour(const DevGraph& g, const QuadPlan& p, int first,
+                                                   int stride, F f) {
+    for (int q = first; q < p.e3; q += stride) {
+        const int l = (q >= p.e0 ? 1 : 0) + (q >= p.e1 ? 1 : 0) + (q >= p.e2 ? 1 : 0);
+        const int idx = (l == 0 ? p.b0 : l == 1 ? p.b1 : l == 2 ? p.b2 : p.b3) + q;
+        const int4 t = __ldg((l < 2 ? g.cq1 : g.cq2) + idx);
+        if (t.x != g.n2) f(l, t.x);
+        if (t.y != g.n2) f(l, t.y);
+        if (t.z != g.n2) f(l, t.z);
+        if (t.w != g.n2) f(l, t.w);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSortThreads, 1)
+k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first,
+                     long long iters, const int* __restrict__ xy, unsigned long long seed,
+                     long long island_offset, const int* __restrict__ objs,
+                     unsigned short* __restrict__ claims_global, long long* __restrict__ num_applied,
+                     int* __restrict__ err_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int2 s_xy[kSortCap];
+    __shared__ int2 s_res[kSortCap];
+    __shared__ unsigned short s_order[kSortCap];
+    __shared__ unsigned short s_cnt[kSortWarps * kSortPer][kSortBins];
+    __shared__ unsigned int s_accept[kSortCap / 32], s_select[kSortCap / 32];
+    __shared__ int s_nhub, s_next;
+    __shared__ double red_d[32];
+    __shared__ int red_i[32];
+    __shared__ Scalars s_cur;
+    constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
+    T *s_aln, *s_inv;
+    const int pl = blockIdx.x, p = first + pl;
+    State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
+    // claim arrays: [wminP | rminP | wminV | rminV], n2 entries each; in shared memory right
+    // after the staged state when they fit, else in a per-individual global scratch
+    const size_t state_bytes = sizeof(T) == 2 ? (size_t)2 * pop.n2p * 2 : 0;
+    unsigned short* claims = claims_global ? claims_global + (size_t)pl * 4 * g.n2
+                                           : reinterpret_cast<unsigned short*>(smem_raw + state_bytes);
+    unsigned short* wminP = claims;
+    unsigned short* rminP = claims + g.n2;
+    unsigned short* wminV = claims + 2 * g.n2;
+    unsigned short* rminV = claims + 3 * g.n2;
+
+    const int obj = objs ? objs[pl] : -1;
+    const unsigned long long ikey = rng_individual_key(seed, (unsigned long long)(island_offset + p));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        Scalars c;
+        c.C = pop.cons[p]; c.I = pop.ind[p]; c.size = pop.size[p]; c.bits = pop.bits[p]; c.goc = pop.goc[p];
+        s_cur = c;
+    }
+    long long n_app = 0;
+    __syncthreads();
+
+    for (long long pos = 0; pos < iters; pos += kSortCap) {
+        const int n = (int)min((long long)kSortCap, iters - pos);
+        const Scalars cur = s_cur;
+        // ---- A: proposals, work keys, sort; reset the claim arrays
+        for (int i = threadIdx.x; i < 4 * g.n2; i += kSortThreads) claims[i] = kNoClaim;
+        if (threadIdx.x < kSortCap / 32) { s_accept[threadIdx.x] = 0u; s_select[threadIdx.x] = 0u; }
+        int key[kSortPer];
+#pragma unroll
+        for (int j = 0; j < kSortPer; ++j) {
+            const int i = j * kSortThreads + threadIdx.x;
+            int x = 0, y = 0;
+            if (i < n) {
+                if (xy) {
+                    const int2 v = __ldg(reinterpret_cast<const int2*>(xy) + (size_t)pl * iters + pos + i);
+                    x = v.x; y = v.y;
+                    if ((unsigned)x >= (unsigned)g.n2 || (unsigned)y >= (unsigned)g.n2) {
+                        atomicOr(err_flag, 1);
+                        x = 0; y = 0;
+                    }
+                } else {
+                    rng_proposal(ikey, (unsigned long long)(pos + i), g.n1, g.n2, x, y);
+                }
+                s_xy[i] = make_int2(x, y);
+            }
+            const SwapCtx cx = make_ctx<T>(g, s_aln, x, y);
+            key[j] = i < n ? min(make_plan(g, cx).e3, kSortBins - 1) : -1;
+        }
+        sort_pass(key, s_cnt, s_order, &s_nhub, &s_next);
+        const int nhub = s_nhub;
+        // ---- C: score (same walk as the swap-delta kernel)
+        for (;;) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(&s_next, 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u < nhub) {
+                const int i = s_order[u];
+                const int2 q = s_xy[i];
+                const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
+                const QuadPlan pl4 = make_plan(g, cx);
+                int dc, di, seen;
+                walk_plan<T>(g, s_aln, s_inv, cx, pl4, lane, 32, dc, di, seen);
+                dc = warp_sum<int>(dc);
+                di = warp_sum<int>(di);
+                seen = (int)__reduce_or_sync(0xffffffffu, (unsigned)seen);
+                if (lane == 0) {
+                    special_terms(g, cx, seen, dc, di);
+                    s_res[i] = make_int2(dc, di);
+                }
+                continue;
+            }
+            const int sp = nhub + (u - nhub) * 32 + lane;
+            if (sp - lane >= n) break;
+            if (sp < n) {
+                const int i = s_order[sp];
+                const int2 q = s_xy[i];
+                const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
+                const QuadPlan pl4 = make_plan(g, cx);
+                int dc, di, seen;
+                walk_plan<T>(g, s_aln, s_inv, cx, pl4, 0, 1, dc, di, seen);
+                if (seen) special_terms(g, cx, seen, dc, di);
+                s_res[i] = make_int2(dc, di);
+            }
+        }
+        __syncthreads();
+        // ---- D: decide every proposal against the round's base objectives
+#pragma unroll
+        for (int j = 0; j < kSortPer; ++j) {
+            const int i = j * kSortThreads + threadIdx.x;
+            bool acc = false;
+            if (i < n) {
+                const int2 q = s_xy[i];
+                const int2 r = s_res[i];
+                const ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, q.x, q.y);
+                const Scalars nw = apply_delta(cur, r.x, r.y, sd);
+                double unused;
+                acc = q.x != q.y && judge_move(ob, obj, cur, nullptr, nw, g.E1, nullptr, false, unused);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, acc);
+            if (lane == 0) s_accept[i >> 5] = m;
+        }
+        if (threadIdx.x == 0) s_next = 0;
+        __syncthreads();
+        // ---- E: accepted proposals claim what they write and read (lowest index wins)
+        for (int sp = threadIdx.x; sp < n; sp += kSortThreads) {
+            const int i = s_order[sp];
+            if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
+            const int2 q = s_xy[i];
+            const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
+            const QuadPlan pl4 = make_plan(g, cx);
+            const unsigned short j = (unsigned short)i;
+            claim_min(wminP, q.x, j); claim_min(wminP, q.y, j);
+            claim_min(wminV, cx.ax, j); claim_min(wminV, cx.ay, j);
+            for_each_neighbour(g, pl4, 0, 1, [&](int l, int id) { claim_min(l < 2 ? rminP : rminV, id, j); });
+        }
+        __syncthreads();
+        // ---- F: select the conflict-free subset
+        for (int sp = threadIdx.x; sp < n; sp += kSortThreads) {
+            const int i = s_order[sp];
+            if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
+            const int2 q = s_xy[i];
+            const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
+            const QuadPlan pl4 = make_plan(g, cx);
+            const unsigned short j = (unsigned short)i;
+            bool ok = wminP[q.x] == j && wminP[q.y] == j && wminV[cx.ax] == j && wminV[cx.ay] == j &&
+                      rminP[q.x] >= j && rminP[q.y] >= j && rminV[cx.ax] >= j && rminV[cx.ay] >= j;
+            for_each_neighbour(g, pl4, 0, 1, [&](int l, int id) { ok = ok && (l < 2 ? wminP : wminV)[id] >= j; });
+            if (ok) atomicOr(&s_select[i >> 5], 1u << (i & 31));
+        }
+        __syncthreads();
+        // ---- G: apply the selected proposals (disjoint writes), fold their deltas
+        int sum_dc = 0, sum_di = 0, sum_ds = 0, napp = 0;
+        double sum_db = 0.0, sum_dg = 0.0;
+#pragma unroll
+        for (int j = 0; j < kSortPer; ++j) {
+            const int i = j * kSortThreads + threadIdx.x;
+            if (i < n && ((s_select[i >> 5] >> (i & 31)) & 1u)) {
+                const int2 q = s_xy[i];
+                const int2 r = s_res[i];
+                const ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, q.x, q.y);
+                sum_dc += r.x; sum_di += r.y; sum_ds += sd.dsize;
+                sum_db += sd.dbx + sd.dby;
+                sum_dg += sd.dgx + sd.dgy;
+                napp++;
+            }
+        }
+        __syncthreads();  // every score_delta above read the base state
+#pragma unroll
+        for (int j = 0; j < kSortPer; ++j) {
+            const int i = j * kSortThreads + threadIdx.x;
+            if (i < n && ((s_select[i >> 5] >> (i & 31)) & 1u)) {
+                const int2 q = s_xy[i];
+                const uint32_t rx = s_aln[q.x], ry = s_aln[q.y];
+                s_aln[q.x] = (T)ry;
+                s_aln[q.y] = (T)rx;
+                s_inv[ry & MASK] = (T)((uint32_t)q.x | (ry & FLAG));
+                s_inv[rx & MASK] = (T)((uint32_t)q.y | (rx & FLAG));
+            }
+        }
+        sum_dc = block_sum<int>(sum_dc, red_i);
+        sum_di = block_sum<int>(sum_di, red_i);
+        sum_ds = block_sum<int>(sum_ds, red_i);
+        napp = block_sum<int>(napp, red_i);
+        sum_db = block_sum<double>(sum_db, red_d);
+        sum_dg = block_sum<double>(sum_dg, red_d);
+        if (threadIdx.x == 0) {
+            Scalars c = cur;
+            c.C += sum_dc; c.I += sum_di; c.size += sum_ds; c.bits += sum_db; c.goc += sum_dg;
+            s_cur = c;
+            n_app += napp;
+        }
+        __syncthreads();
+    }
+    State<T>::release(pop, p, s_aln, s_inv);
+    if (threadIdx.x == 0) {
+        const Scalars c = s_cur;
+        pop.cons[p] = c.C; pop.ind[p] = c.I; pop.size[p] = c.size; pop.bits[p] = c.bits; pop.goc[p] = c.goc;
+        for (int j = 0; j < ob.M; ++j) pop.fit[(size_t)p * ob.M + j] = objective(ob.names[j], c, g.E1);
+        if (num_applied) num_applied[pl] = n_app;
+    }
+    (void)warp;
 }
 
 // proposals of the device RNG, for host-side checking / replay

@@ -23,7 +23,7 @@ EXPORTS = [
     "ona_set_stream", "ona_synchronize", "ona_host_alloc", "ona_host_free", "ona_kernel_launches",
     "ona_set_island_offset", "ona_set_objectives", "ona_pop_resize", "ona_pop_upload", "ona_pop_download",
     "ona_pop_set_counters", "ona_pop_get_counters", "ona_full_fitness", "ona_full_fitness_dev",
-    "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_steepest_step", "ona_rng_proposals", "ona_hill_climb",
+    "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_steepest_step", "ona_rng_proposals", "ona_hill_climb", "ona_hill_climb_batched",
     "ona_apply_swaps", "ona_export_fitness_dev",
 ]
 
@@ -90,6 +90,7 @@ def load_library(build_if_missing=True):
     L.ona_steepest_step.argtypes = [vp, ci, vp, vp, vp]
     L.ona_rng_proposals.argtypes = [vp, ci, ci, ci, C.c_ulonglong, ll, vp]
     L.ona_hill_climb.argtypes = [vp, ci, ci, ll, vp, C.c_ulonglong, vp, vp, vp]
+    L.ona_hill_climb_batched.argtypes = [vp, ci, ci, ll, vp, C.c_ulonglong, vp, vp]
     L.ona_apply_swaps.argtypes = [vp, ci, ci, ci, vp]
     L.ona_export_fitness_dev.argtypes = [vp, ci, ci, vp]
     _LIB = L
@@ -298,6 +299,19 @@ class Engine:
         self._check(self.L.ona_hill_climb(self.h, first, count, int(iters), _ptr(xy), int(seed),
                                           _ptr(o), _ptr(acc), _ptr(nacc)))
         return acc, nacc
+
+    def hill_climb_batched(self, iters=None, xy=None, seed=0, objs=None, first=0, count=None):
+        """throughput hill climb: rounds of 1024 proposals scored at once, a conflict-free accepted
+        subset applied per round (see include/ona_b200.h).  Returns applied swaps per individual."""
+        if xy is not None:
+            xy = _i32(xy)
+            count, iters = xy.shape[0], xy.shape[1]
+        count = self.P - first if count is None else count
+        o = None if objs is None else _i32(np.broadcast_to(np.asarray(objs), (count,)))
+        napp = np.empty(count, np.int64)
+        self._check(self.L.ona_hill_climb_batched(self.h, first, count, int(iters), _ptr(xy), int(seed),
+                                                  _ptr(o), _ptr(napp)))
+        return napp
 
     def apply_swaps(self, xy, first=0):
         xy = _i32(xy)

@@ -425,3 +425,83 @@ def test_goc_objective_yeast_fly_shape():
         assert np.array_equal(acc[p], o.hill_climb_replay(hxy[p], names, want_accepted=True))
         assert np.array_equal(a[p], o.state()[0])
         assert (c["cons"][p], c["ind"][p], c["bits"][p], c["goc"][p]) == o.counters()
+
+
+def _batched_round_reference(pair, o, xy, names, obj):
+    """Host restatement of one round of ona_hill_climb_batched (selection rule in
+    include/ona_b200.h / csrc): decisions against the base state come from the oracle."""
+    n1, n2 = pair.n1, pair.n2
+    aln, _, mask = o.state()
+    rec = o.swap_delta_records(xy, names, obj=obj)
+    acc = [bool(rec["improved"][j]) and xy[j][0] != xy[j][1] for j in range(len(xy))]
+    BIG = 1 << 30
+    wP, rP, wV, rV = (np.full(n2, BIG) for _ in range(4))
+    sets = []
+    for j, (x, y) in enumerate(xy):
+        if not acc[j]:
+            sets.append(None)
+            continue
+        ax, ay = int(aln[x]), int(aln[y])
+        xr, yr, mx, my = x < n1, y < n1, bool(mask[x]), bool(mask[y])
+        RP = []
+        if xr:
+            RP += list(pair.col1[pair.rp1[x]:pair.rp1[x + 1]])
+        if yr:
+            RP += list(pair.col1[pair.rp1[y]:pair.rp1[y + 1]])
+        RV = []
+        if (xr and mx) != (yr and mx) or (yr and my) != (xr and my):
+            RV = list(pair.col2[pair.rp2[ax]:pair.rp2[ax + 1]]) + list(pair.col2[pair.rp2[ay]:pair.rp2[ay + 1]])
+        sets.append((x, y, ax, ay, RP, RV))
+        for n in (x, y):
+            wP[n] = min(wP[n], j)
+        for n in (ax, ay):
+            wV[n] = min(wV[n], j)
+        for n in RP:
+            rP[n] = min(rP[n], j)
+        for n in RV:
+            rV[n] = min(rV[n], j)
+    applied = 0
+    for j, st in enumerate(sets):
+        if st is None:
+            continue
+        x, y, ax, ay, RP, RV = st
+        ok = all(wP[n] == j and rP[n] >= j for n in (x, y)) and all(wV[n] == j and rV[n] >= j for n in (ax, ay))
+        ok = ok and all(wP[n] >= j for n in RP) and all(wV[n] >= j for n in RV)
+        if ok:
+            o.do_swap(int(x), int(y))
+            applied += 1
+    o.compute_fitness(names)
+    return applied
+
+
+@pytest.mark.parametrize("total", [True, False])
+def test_batched_hill_climb_rule_and_exact_counters(mid, total):
+    pair, S, G, prob = mid
+    names = [engine.S3, engine.BITSCORE_SUM, engine.GOC]
+    P, iters = 4, 2500                       # rounds of 1024, 1024, 452
+    aln, mask = synth.random_population(pair, P, seed=15, total=total)
+    e = engine.Engine.from_pair(pair, names, use_goc=True, goc_dense=G)
+    e.upload(aln, mask)
+    e.full_fitness(seed_mode=engine.SEED_TRUE | engine.SUM_SEQUENTIAL)
+    xy = synth.random_candidates(pair, P, iters, seed=16)
+    objs = np.array([-1, 0, -1, 2])
+    napp = e.hill_climb_batched(xy=xy, objs=objs)
+    a, inv, m = e.download()
+    c = e.counters()
+    scratch = e.full_fitness(seed_mode=engine.SEED_NONE | engine.SUM_SEQUENTIAL)
+    for p in range(P):
+        o = port.Aln(prob, aln[p], None if mask is None else mask[p])
+        o.set_counters(int(o.conserved_true()), o.counters()[1], o.counters()[2], o.counters()[3])
+        o.compute_fitness(names)
+        applied = 0
+        for r0 in range(0, iters, 1024):
+            applied += _batched_round_reference(pair, o, xy[p, r0:r0 + 1024], names, int(objs[p]))
+        st = o.state()
+        assert applied == napp[p] and applied > 0
+        assert np.array_equal(a[p], st[0]) and np.array_equal(inv[p], st[1]) and np.array_equal(m[p], st[2])
+        oc = o.counters()
+        assert (c["cons"][p], c["ind"][p]) == (oc[0], oc[1])
+        assert close(c["bits"][p], oc[2]) and close(c["goc"][p], oc[3])
+        # incremental == from scratch (the applied swaps' deltas are exact and additive)
+        assert c["cons"][p] == scratch["cons_true"][p] and c["ind"][p] == scratch["ind"][p]
+        assert close(c["bits"][p], scratch["bits"][p]) and close(c["goc"][p], scratch["goc"][p])
