@@ -1014,12 +1014,12 @@ int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters,
     }
     if (e->small_ids) {
         TRY(set_smem(k_hill_climb_batched<uint16_t>, smem));
-        k_hill_climb_batched<uint16_t><<<count, kSortThreads, smem, e->stream>>>(
+        k_hill_climb_batched<uint16_t><<<count, kBatThreads, smem, e->stream>>>(
             e->g, e->S, e->G, e->ob, e->pop, first, iters, xy_dev, seed, e->island_offset, objs_dev, claims_global,
             e->t_l0.p, e->d_flag);
     } else {
         TRY(set_smem(k_hill_climb_batched<uint32_t>, smem));
-        k_hill_climb_batched<uint32_t><<<count, kSortThreads, smem, e->stream>>>(
+        k_hill_climb_batched<uint32_t><<<count, kBatThreads, smem, e->stream>>>(
             e->g, e->S, e->G, e->ob, e->pop, first, iters, xy_dev, seed, e->island_offset, objs_dev, claims_global,
             e->t_l0.p, e->d_flag);
     }

@@ -298,27 +298,29 @@ constexpr int kSortBins = kHubQuads + 2;           // 0..kHubQuads exact, last b
 // warp ascending) by warp 0, then the scatter.  key[j] belongs to candidate j*kSortThreads+tid
 // (-1 = beyond the pass).  On return s_order[pos] = candidate, *s_nhub = number of hubs (they
 // come first) and *s_next = 0 (the work-unit counter).  All threads of the CTA must call.
-__device__ __forceinline__ void sort_pass(const int (&key)[kSortPer], unsigned short (*s_cnt)[kSortBins],
+template <int THREADS, int PER>
+__device__ __forceinline__ void sort_pass(const int (&key)[PER], unsigned short (*s_cnt)[kSortBins],
                                           unsigned short* s_order, int* s_nhub, int* s_next) {
+    constexpr int WARPS = THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    int rank[kSortPer];
+    int rank[PER];
 #pragma unroll
-    for (int j = 0; j < kSortPer; ++j) {
+    for (int j = 0; j < PER; ++j) {
         const int k = key[j];
         int r = 0;
 #pragma unroll
         for (int b = 0; b < kSortBins; ++b) {
             const unsigned m = __ballot_sync(0xffffffffu, k == b);
             if (k == b) r = __popc(m & lt_mask);
-            if (lane == 0) s_cnt[j * kSortWarps + warp][b] = (unsigned short)__popc(m);
+            if (lane == 0) s_cnt[j * WARPS + warp][b] = (unsigned short)__popc(m);
         }
         rank[j] = r;
     }
     __syncthreads();
     if (warp == 0) {
         int running = 0;
-        constexpr int NV = kSortWarps * kSortPer;
+        constexpr int NV = WARPS * PER;
         for (int b = kSortBins - 1; b >= 0; --b) {
             for (int v0 = 0; v0 < NV; v0 += 32) {
                 const int v = v0 + lane;
@@ -337,9 +339,9 @@ __device__ __forceinline__ void sort_pass(const int (&key)[kSortPer], unsigned s
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < kSortPer; ++j) {
-        const int i = j * kSortThreads + threadIdx.x;
-        if (key[j] >= 0) s_order[(int)s_cnt[j * kSortWarps + warp][key[j]] + rank[j]] = (unsigned short)i;
+    for (int j = 0; j < PER; ++j) {
+        const int i = j * THREADS + threadIdx.x;
+        if (key[j] >= 0) s_order[(int)s_cnt[j * WARPS + warp][key[j]] + rank[j]] = (unsigned short)i;
     }
     __syncthreads();
 }
@@ -369,7 +371,6 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int per = (K + gridDim.x - 1) / gridDim.x;
     const int lo = blockIdx.x * per, hi = min(K, lo + per);
     const unsigned long long ikey = rng_individual_key(seed, (unsigned long long)(island_offset + p));
@@ -407,7 +408,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             const SwapCtx cx = make_ctx<T>(g, s_aln, x, y);
             key[j] = i < n ? min(make_plan(g, cx).e3, kSortBins - 1) : -1;
         }
-        sort_pass(key, s_cnt, s_order, &s_nhub, &s_next);
+        sort_pass<kSortThreads, kSortPer>(key, s_cnt, s_order, &s_nhub, &s_next);
         // ---- C: walk.  Warps pull work units, longest first: a hub (walked by the whole warp)
         //      or 32 consecutive sorted candidates (one per lane, equal loop lengths)
         const int nhub = s_nhub;
@@ -836,19 +837,26 @@ __device__ __forceinline__ void for_each_neighbour(const DevGraph& g, const Quad
     }
 }
 
+#ifndef ONA_BAT_THREADS
+#define ONA_BAT_THREADS 1024
+#endif
+constexpr int kBatThreads = ONA_BAT_THREADS;   // batched hill climb: one CTA per individual
+constexpr int kBatCap = 1024;                  // proposals per round
+constexpr int kBatPer = kBatCap / kBatThreads;
+
 template <typename T>
-__global__ void __launch_bounds__(kSortThreads, 1)
+__global__ void __launch_bounds__(kBatThreads, 1)
 k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first,
                      long long iters, const int* __restrict__ xy, unsigned long long seed,
                      long long island_offset, const int* __restrict__ objs,
                      unsigned short* __restrict__ claims_global, long long* __restrict__ num_applied,
                      int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int2 s_xy[kSortCap];
-    __shared__ int2 s_res[kSortCap];
-    __shared__ unsigned short s_order[kSortCap];
-    __shared__ unsigned short s_cnt[kSortWarps * kSortPer][kSortBins];
-    __shared__ unsigned int s_accept[kSortCap / 32], s_select[kSortCap / 32];
+    __shared__ int2 s_xy[kBatCap];
+    __shared__ int2 s_res[kBatCap];
+    __shared__ unsigned short s_order[kBatCap];
+    __shared__ unsigned short s_cnt[kBatThreads / 32 * kBatPer][kSortBins];
+    __shared__ unsigned int s_accept[kBatCap / 32], s_select[kBatCap / 32];
     __shared__ int s_nhub, s_next;
     __shared__ double red_d[32];
     __shared__ int red_i[32];
@@ -878,16 +886,16 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     long long n_app = 0;
     __syncthreads();
 
-    for (long long pos = 0; pos < iters; pos += kSortCap) {
-        const int n = (int)min((long long)kSortCap, iters - pos);
+    for (long long pos = 0; pos < iters; pos += kBatCap) {
+        const int n = (int)min((long long)kBatCap, iters - pos);
         const Scalars cur = s_cur;
         // ---- A: proposals, work keys, sort; reset the claim arrays
-        for (int i = threadIdx.x; i < 4 * g.n2; i += kSortThreads) claims[i] = kNoClaim;
-        if (threadIdx.x < kSortCap / 32) { s_accept[threadIdx.x] = 0u; s_select[threadIdx.x] = 0u; }
-        int key[kSortPer];
+        for (int i = threadIdx.x; i < 4 * g.n2; i += kBatThreads) claims[i] = kNoClaim;
+        if (threadIdx.x < kBatCap / 32) { s_accept[threadIdx.x] = 0u; s_select[threadIdx.x] = 0u; }
+        int key[kBatPer];
 #pragma unroll
-        for (int j = 0; j < kSortPer; ++j) {
-            const int i = j * kSortThreads + threadIdx.x;
+        for (int j = 0; j < kBatPer; ++j) {
+            const int i = j * kBatThreads + threadIdx.x;
             int x = 0, y = 0;
             if (i < n) {
                 if (xy) {
@@ -905,7 +913,7 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             const SwapCtx cx = make_ctx<T>(g, s_aln, x, y);
             key[j] = i < n ? min(make_plan(g, cx).e3, kSortBins - 1) : -1;
         }
-        sort_pass(key, s_cnt, s_order, &s_nhub, &s_next);
+        sort_pass<kBatThreads, kBatPer>(key, s_cnt, s_order, &s_nhub, &s_next);
         const int nhub = s_nhub;
         // ---- C: score (same walk as the swap-delta kernel)
         for (;;) {
@@ -944,8 +952,8 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
         __syncthreads();
         // ---- D: decide every proposal against the round's base objectives
 #pragma unroll
-        for (int j = 0; j < kSortPer; ++j) {
-            const int i = j * kSortThreads + threadIdx.x;
+        for (int j = 0; j < kBatPer; ++j) {
+            const int i = j * kBatThreads + threadIdx.x;
             bool acc = false;
             if (i < n) {
                 const int2 q = s_xy[i];
@@ -961,7 +969,7 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
         if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
         // ---- E: accepted proposals claim what they write and read (lowest index wins)
-        for (int sp = threadIdx.x; sp < n; sp += kSortThreads) {
+        for (int sp = threadIdx.x; sp < n; sp += kBatThreads) {
             const int i = s_order[sp];
             if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
             const int2 q = s_xy[i];
@@ -974,7 +982,7 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
         }
         __syncthreads();
         // ---- F: select the conflict-free subset
-        for (int sp = threadIdx.x; sp < n; sp += kSortThreads) {
+        for (int sp = threadIdx.x; sp < n; sp += kBatThreads) {
             const int i = s_order[sp];
             if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
             const int2 q = s_xy[i];
@@ -991,8 +999,8 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
         int sum_dc = 0, sum_di = 0, sum_ds = 0, napp = 0;
         double sum_db = 0.0, sum_dg = 0.0;
 #pragma unroll
-        for (int j = 0; j < kSortPer; ++j) {
-            const int i = j * kSortThreads + threadIdx.x;
+        for (int j = 0; j < kBatPer; ++j) {
+            const int i = j * kBatThreads + threadIdx.x;
             if (i < n && ((s_select[i >> 5] >> (i & 31)) & 1u)) {
                 const int2 q = s_xy[i];
                 const int2 r = s_res[i];
@@ -1005,8 +1013,8 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
         }
         __syncthreads();  // every score_delta above read the base state
 #pragma unroll
-        for (int j = 0; j < kSortPer; ++j) {
-            const int i = j * kSortThreads + threadIdx.x;
+        for (int j = 0; j < kBatPer; ++j) {
+            const int i = j * kBatThreads + threadIdx.x;
             if (i < n && ((s_select[i >> 5] >> (i & 31)) & 1u)) {
                 const int2 q = s_xy[i];
                 const uint32_t rx = s_aln[q.x], ry = s_aln[q.y];

@@ -17,3 +17,11 @@ t0 = time.perf_counter()
 _, nacc = e.hill_climb(iters=iters, seed=2)
 dt = time.perf_counter() - t0
 print("P=%d iters=%d: %.3e iterations/s, accept rate %.3f" % (P, iters, P * iters / dt, nacc.sum() / (P * iters)))
+
+e.upload(aln)
+e.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
+e.hill_climb_batched(iters=2048, seed=1)
+t0 = time.perf_counter()
+napp = e.hill_climb_batched(iters=iters * 10, seed=2)
+dt = time.perf_counter() - t0
+print("batched: P=%d iters=%d: %.3e proposals/s, applied fraction %.3f" % (P, iters * 10, P * iters * 10 / dt, napp.sum() / (P * iters * 10)))
