@@ -44,9 +44,18 @@ enum ona_objective {
 };
 #define ONA_MAX_OBJECTIVES 10
 
-/* BLASTDict / GOCDict (blastinfo.h:10, goc.h:12): either the dense row-major n1 x n2
- * matrix the reference holds (pass the multi_array's data()), or its non-zeros as COO
- * triples (later duplicates win, like the reference's assignment loop blastinfo.cpp:42).
+/* BLASTDict / GOCDict (blastinfo.h:10, goc.h:12) in one of three forms:
+ *   dense      the row-major n1 x n2 matrix the reference holds (pass the multi_array's data());
+ *   COO        its non-zeros as triples (later duplicates win, like the reference's assignment
+ *              loop blastinfo.cpp:42);
+ *   term sets  (GOC only) the annotation sets loadAnnotations returns (goc.cpp:55-89) as CSR:
+ *              ann_rowptr1/ann_terms1 for net1, ann_rowptr2/ann_terms2 for net2, every row sorted
+ *              ascending without duplicates (std::set<int> order).  The engine then builds the
+ *              dense Jaccard matrix double(|A n B|) / double(|A u B|) of loadGOC (goc.cpp:16-52)
+ *              on the device, replacing the reference's O(n1 n2 terms) host loop and the n1 x n2
+ *              host matrix.  A node is "annotated" when it has a row in the reference's map:
+ *              ann_present1/2 (bytes, may be NULL = "row non-empty") carry that; pairs with an
+ *              unannotated node stay 0, two annotated-but-empty nodes give 0/0 = NaN as in goc.cpp:47.
  * All-NULL = table absent (the reference's nullptr dict). */
 typedef struct ona_score_table {
     const double* dense;
@@ -54,6 +63,12 @@ typedef struct ona_score_table {
     const int* cols;
     const double* vals;
     long long nnz;
+    const int* ann_rowptr1;
+    const int* ann_terms1;
+    const int* ann_rowptr2;
+    const int* ann_terms2;
+    const unsigned char* ann_present1;
+    const unsigned char* ann_present2;
 } ona_score_table;
 
 /* Replaces: the immutable inputs an Alignment borrows -- const Network* net1/net2,

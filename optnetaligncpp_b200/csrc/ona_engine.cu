@@ -138,6 +138,42 @@ void unique_edges(int n, const int* rp, const int* col, std::vector<int>& eu, st
 int build_table(ona_engine* e, const ona_score_table& t, int n1, int n2, DevTable* out) {
     out->kind = 0;
     out->n2 = n2;
+    if (!t.dense && !(t.rows && t.cols && t.vals) && t.ann_rowptr1 && t.ann_rowptr2) {
+        // term-set form: build the dense Jaccard matrix on the device
+        const int m1 = t.ann_rowptr1[n1], m2 = t.ann_rowptr2[n2];
+        if ((m1 && !t.ann_terms1) || (m2 && !t.ann_terms2)) return fail(ONA_ERR_INVALID, "annotation terms missing");
+        for (int net = 0; net < 2; ++net) {
+            const int n = net ? n2 : n1;
+            const int* rp = net ? t.ann_rowptr2 : t.ann_rowptr1;
+            const int* tm = net ? t.ann_terms2 : t.ann_terms1;
+            if (rp[0] != 0) return fail(ONA_ERR_INVALID, "annotation rowptr[0] != 0");
+            for (int u = 0; u < n; ++u) {
+                if (rp[u + 1] < rp[u]) return fail(ONA_ERR_INVALID, "annotation rowptr not monotone");
+                for (int k = rp[u] + 1; k < rp[u + 1]; ++k)
+                    if (tm[k] <= tm[k - 1]) return fail(ONA_ERR_INVALID, "annotation rows must be sorted and unique");
+            }
+        }
+        const int *d_rp1, *d_t1, *d_rp2, *d_t2;
+        const unsigned char *d_p1 = nullptr, *d_p2 = nullptr;
+        int rc;
+        if ((rc = upload<int>(e, std::vector<int>(t.ann_rowptr1, t.ann_rowptr1 + n1 + 1), &d_rp1))) return rc;
+        if ((rc = upload<int>(e, std::vector<int>(t.ann_terms1, t.ann_terms1 + m1), &d_t1))) return rc;
+        if ((rc = upload<int>(e, std::vector<int>(t.ann_rowptr2, t.ann_rowptr2 + n2 + 1), &d_rp2))) return rc;
+        if ((rc = upload<int>(e, std::vector<int>(t.ann_terms2, t.ann_terms2 + m2), &d_t2))) return rc;
+        if (t.ann_present1 && (rc = upload<unsigned char>(e, std::vector<unsigned char>(t.ann_present1, t.ann_present1 + n1), &d_p1))) return rc;
+        if (t.ann_present2 && (rc = upload<unsigned char>(e, std::vector<unsigned char>(t.ann_present2, t.ann_present2 + n2), &d_p2))) return rc;
+        double* d = nullptr;
+        CU(cudaMalloc(&d, (size_t)n1 * (size_t)n2 * sizeof(double)));
+        e->owned.push_back(d);
+        dim3 grid((n2 + 255) / 256, n1);
+        k_build_jaccard<<<grid, 256, 0, e->stream>>>(n1, n2, d_rp1, d_t1, d_rp2, d_t2, d_p1, d_p2, d);
+        e->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(e->stream));
+        out->kind = 1;
+        out->dense = d;
+        return ONA_OK;
+    }
     if (!t.dense && !(t.rows && t.cols && t.vals)) return ONA_OK;
     const size_t cells = (size_t)n1 * (size_t)n2;
     std::vector<unsigned long long> keys;

@@ -51,6 +51,37 @@ __global__ void k_unpack_state(DevPop pop, int first, int count, int n2, int* __
 }
 
 // --------------------------------------------------------------------------------
+// GOC table construction: loadGOC's Jaccard matrix (goc.cpp:16-52) from the
+// per-node sorted term lists, one thread per (u,v) pair, merge intersection; writes along v
+// are coalesced.  present[] marks nodes that have a row in the reference's annotation map.
+// --------------------------------------------------------------------------------
+__global__ void k_build_jaccard(int n1, int n2, const int* __restrict__ rp1, const int* __restrict__ t1,
+                                const int* __restrict__ rp2, const int* __restrict__ t2,
+                                const unsigned char* __restrict__ present1,
+                                const unsigned char* __restrict__ present2, double* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int u = blockIdx.y;
+    if (v >= n2) return;
+    const int a0 = __ldg(rp1 + u), a1 = __ldg(rp1 + u + 1);
+    const int b0 = __ldg(rp2 + v), b1 = __ldg(rp2 + v + 1);
+    const bool pu = present1 ? present1[u] != 0 : a1 > a0;
+    const bool pv = present2 ? present2[v] != 0 : b1 > b0;
+    double val = 0.0;
+    if (pu && pv) {
+        int i = a0, j = b0, inter = 0;
+        while (i < a1 && j < b1) {
+            const int x = __ldg(t1 + i), y = __ldg(t2 + j);
+            inter += x == y ? 1 : 0;
+            i += x <= y ? 1 : 0;
+            j += y <= x ? 1 : 0;
+        }
+        const int uni = (a1 - a0) + (b1 - b0) - inter;
+        val = (double)inter / (double)uni;  // goc.cpp:44-47; 0/0 = NaN for two empty annotated rows
+    }
+    out[(size_t)u * n2 + v] = val;
+}
+
+// --------------------------------------------------------------------------------
 // Block reductions
 // --------------------------------------------------------------------------------
 template <typename V>

@@ -34,7 +34,9 @@ class OnaError(RuntimeError):
 
 class _ScoreTable(C.Structure):
     _fields_ = [("dense", C.c_void_p), ("rows", C.c_void_p), ("cols", C.c_void_p),
-                ("vals", C.c_void_p), ("nnz", C.c_longlong)]
+                ("vals", C.c_void_p), ("nnz", C.c_longlong),
+                ("ann_rowptr1", C.c_void_p), ("ann_terms1", C.c_void_p), ("ann_rowptr2", C.c_void_p),
+                ("ann_terms2", C.c_void_p), ("ann_present1", C.c_void_p), ("ann_present2", C.c_void_p)]
 
 
 class _Problem(C.Structure):
@@ -125,6 +127,20 @@ class Engine:
             st = _ScoreTable()
             if t is None:
                 pass
+            elif isinstance(t, dict):          # term sets: {"ann1": [arrays], "ann2": [arrays]}
+                arrs = []
+                for ann in (t["ann1"], t["ann2"]):
+                    rp = np.zeros(len(ann) + 1, np.int32)
+                    np.cumsum([len(a) for a in ann], out=rp[1:])
+                    tm = _i32(np.concatenate([np.asarray(a, np.int32) for a in ann] or [[]])) if rp[-1] else np.zeros(1, np.int32)
+                    arrs += [rp, tm]
+                keep += arrs
+                st.ann_rowptr1, st.ann_terms1, st.ann_rowptr2, st.ann_terms2 = (_ptr(a) for a in arrs)
+                for k, fld in (("present1", "ann_present1"), ("present2", "ann_present2")):
+                    if t.get(k) is not None:
+                        pr_ = np.ascontiguousarray(t[k], dtype=np.uint8)
+                        keep.append(pr_)
+                        setattr(st, fld, _ptr(pr_))
             elif isinstance(t, tuple):
                 r, c, v = _i32(t[0]), _i32(t[1]), np.ascontiguousarray(t[2], dtype=np.float64)
                 keep += [r, c, v]

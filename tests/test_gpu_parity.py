@@ -505,3 +505,31 @@ def test_batched_hill_climb_rule_and_exact_counters(mid, total):
         # incremental == from scratch (the applied swaps' deltas are exact and additive)
         assert c["cons"][p] == scratch["cons_true"][p] and c["ind"][p] == scratch["ind"][p]
         assert close(c["bits"][p], scratch["bits"][p]) and close(c["goc"][p], scratch["goc"][p])
+
+
+def test_goc_table_built_on_device_from_term_sets(mid):
+    """ona_score_table's term-set form: the engine builds loadGOC's Jaccard matrix (goc.cpp:16-52)
+    on the device; everything downstream must be bit-identical to handing it the dense matrix."""
+    pair, S, G, prob = mid
+    names = [engine.GOC, engine.S3]
+    P, K = 5, 2000
+    aln, _ = synth.random_population(pair, P, seed=51)
+    e_dense = engine.Engine.from_pair(pair, names, use_goc=True, goc_dense=G)
+    e_sets = engine.Engine(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2, names,
+                           bits=(pair.bit_rows, pair.bit_cols, pair.bit_vals),
+                           goc={"ann1": pair.ann1, "ann2": pair.ann2})
+    xy = synth.random_candidates(pair, P, K, seed=52)
+    res = []
+    for e in (e_dense, e_sets):
+        e.upload(aln)
+        r = e.full_fitness(seed_mode=engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL)
+        d = e.swap_deltas(xy, want=("goc", "fit", "improved"))
+        e.hill_climb(iters=3000, seed=5)
+        res.append((r, d, e.counters(), e.download()[0]))
+    (r0, d0, c0, a0), (r1, d1, c1, a1) = res
+    assert np.array_equal(r0["goc"], r1["goc"]) and np.array_equal(r0["fit"], r1["fit"])
+    for k in d0:
+        assert np.array_equal(d0[k], d1[k], equal_nan=True), k
+    assert np.array_equal(a0, a1) and np.array_equal(c0["goc"], c1["goc"])
+    for p in range(P):
+        assert r1["goc"][p] == port.Aln(prob, aln[p]).counters()[3]
