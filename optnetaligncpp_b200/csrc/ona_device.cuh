@@ -81,6 +81,10 @@ struct DevTable {
     unsigned long long cap_mask;
     int shift;  // 64 - log2(capacity)
     int n2;
+    // hash form only: per-row Bloom signature (3 x 32 bits) of the columns that hold a non-zero.
+    // Score tables are very sparse (0.1 %), so almost every lookup is answered "0.0" by the row
+    // signature -- one 16-byte load per row serves both lookups of that row -- without probing.
+    const uint4* rowsig;
 };
 constexpr unsigned long long kEmptyKey = ~0ull;
 
@@ -150,6 +154,25 @@ __device__ __forceinline__ double table_lookup(const DevTable& t, int r, int c) 
         if (s.x == kEmptyKey) return 0.0;
         h = (h + 1) & t.cap_mask;
     }
+}
+
+__device__ __forceinline__ bool sig_has(const uint4& sg, int id) {
+    const unsigned u = (unsigned)id;
+    return (((sg.x >> (u & 31u)) & (sg.y >> ((u >> 5) & 31u)) & (sg.z >> ((u >> 10) & 31u))) & 1u) != 0u;
+}
+// the two lookups S[r][c0], S[r][c1] of one row, each gated by a flag
+__device__ __forceinline__ void row_lookup2(const DevTable& t, int r, bool want0, int c0, bool want1, int c1,
+                                            double& v0, double& v1) {
+    v0 = 0.0;
+    v1 = 0.0;
+    if (t.kind == 2) {
+        if (!(want0 | want1)) return;
+        const uint4 sg = __ldg(t.rowsig + r);
+        want0 = want0 && sig_has(sg, c0);
+        want1 = want1 && sig_has(sg, c1);
+    }
+    if (want0) v0 = table_lookup(t, r, c0);
+    if (want1) v1 = table_lookup(t, r, c1);
 }
 
 // ---------------------------------------------------------------- objectives (S5)
@@ -385,28 +408,14 @@ __device__ __forceinline__ ScoreDelta score_delta(const DevGraph& g, const DevTa
     if (xr) d.dsize += (int)my - (int)mx;
     if (yr) d.dsize += (int)mx - (int)my;
     if (S.kind) {
-        if (xr) {
-            double o = mx ? table_lookup(S, x, ax) : 0.0;
-            double n = my ? table_lookup(S, x, ay) : 0.0;
-            d.dbx = n - o;
-        }
-        if (yr) {
-            double o = my ? table_lookup(S, y, ay) : 0.0;
-            double n = mx ? table_lookup(S, y, ax) : 0.0;
-            d.dby = n - o;
-        }
+        double o, n;
+        if (xr) { row_lookup2(S, x, mx, ax, my, ay, o, n); d.dbx = n - o; }
+        if (yr) { row_lookup2(S, y, my, ay, mx, ax, o, n); d.dby = n - o; }
     }
     if (Gt.kind) {
-        if (xr) {
-            double o = mx ? table_lookup(Gt, x, ax) : 0.0;
-            double n = my ? table_lookup(Gt, x, ay) : 0.0;
-            d.dgx = n - o;
-        }
-        if (yr) {
-            double o = my ? table_lookup(Gt, y, ay) : 0.0;
-            double n = mx ? table_lookup(Gt, y, ax) : 0.0;
-            d.dgy = n - o;
-        }
+        double o, n;
+        if (xr) { row_lookup2(Gt, x, mx, ax, my, ay, o, n); d.dgx = n - o; }
+        if (yr) { row_lookup2(Gt, y, my, ay, mx, ax, o, n); d.dgy = n - o; }
     }
     return d;
 }

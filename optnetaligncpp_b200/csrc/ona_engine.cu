@@ -233,8 +233,18 @@ int build_table(ona_engine* e, const ona_score_table& t, int n1, int n2, DevTabl
     else
         for (long long k = 0; k < t.nnz; ++k)
             put((unsigned long long)t.rows[k] * (unsigned long long)n2 + (unsigned long long)t.cols[k], t.vals[k]);
+    std::vector<uint4> rowsig(n1, make_uint4(0, 0, 0, 0));
+    for (const auto& sl : slots) {
+        if (sl.x == kEmptyKey) continue;
+        const int r = (int)(sl.x / (unsigned long long)n2), c = (int)(sl.x % (unsigned long long)n2);
+        rowsig[r].x |= 1u << (c & 31);
+        rowsig[r].y |= 1u << ((c >> 5) & 31);
+        rowsig[r].z |= 1u << ((c >> 10) & 31);
+    }
+    int rc = upload<uint4>(e, rowsig, &out->rowsig);
+    if (rc) return rc;
     const ulonglong2* d = nullptr;
-    int rc = upload<ulonglong2>(e, slots, &d);
+    rc = upload<ulonglong2>(e, slots, &d);
     if (rc) return rc;
     out->kind = 2;
     out->slots = d;
