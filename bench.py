@@ -81,7 +81,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -89,7 +89,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -106,20 +106,22 @@ class ClockSampler:
                 self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
-        sm, smax, reasons = [], 0.0, set()
+        sm, smax, reasons, loaded = [], 0.0, set(), []
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 smax = max(smax, float(r[2]))
+                if len(r) > 8 and float(r[8]) >= 10.0:
+                    loaded.append(float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                                     "sw_power_cap"), r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
-        busy = [v for v in sm if v > 0]
+        busy = loaded or [v for v in sm if v > 0]
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(loaded)}
 
 
 # ------------------------------------------------------------------ reference CPU arm
@@ -275,21 +277,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled every 20 ms from before the warm-up until the last
+    # GPU section of this run (timed steps, end-to-end leg, hill-climb extras)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.2)
     for w in range(max(args.warmup, 0)):
         step(seed=10_000 + w)
     barrier()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     launches0 = e.kernel_launches()
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
     barrier()
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
         step(seed=s, ev=evs[s])
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
     launches = e.kernel_launches() - launches0
     step_ms = [ev[0].elapsed_time(ev[3]) for ev in evs]
     delta_ms = [ev[0].elapsed_time(ev[1]) for ev in evs]
@@ -351,6 +354,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(hb_ms, op=dist.ReduceOp.MAX)
     hb_ms = float(hb_ms.item())
+    clocks = sampler.stop()
 
     if rank == 0:
         peak, peak_kind = hbm_peak()
