@@ -555,44 +555,46 @@ __device__ __forceinline__ bool bloom_has(const uint4& sg, int id) {
     return (((sg.x >> (u & 31u)) & (sg.y >> ((u >> 5) & 31u)) & (sg.z >> ((u >> 10) & 31u))) & 1u) != 0u;
 }
 
-// Does the score of proposal j = (xj,yj | images axj,ayj) read anything that committing
-// proposal i = (xi,yi | images axi,ayi) writes?  Its own positions, the net1 neighbourhoods of
-// its positions (aln[] gathers) and the net2 neighbourhoods of its images (alnInv[] gathers).
-// Bloom signatures first, the exact adjacency bit only on a hit.
-__device__ __forceinline__ bool commit_conflicts(const DevGraph& g, int xj, int yj, int axj, int ayj,
-                                                 const uint4& n1x, const uint4& n1y, const uint4& n2x,
-                                                 const uint4& n2y, int xi, int yi, int axi, int ayi) {
-    const bool same = (xj == xi) | (xj == yi) | (yj == xi) | (yj == yi);
-    const bool xir = xi < g.n1, yir = yi < g.n1;
-    // all eight Bloom tests first, then the (rare) exact probes as independent predicated loads
-    const bool h0 = xir & bloom_has(n1x, xi), h1 = yir & bloom_has(n1x, yi);
-    const bool h2 = xir & bloom_has(n1y, xi), h3 = yir & bloom_has(n1y, yi);
-    const bool h4 = bloom_has(n2x, axi), h5 = bloom_has(n2x, ayi);
-    const bool h6 = bloom_has(n2y, axi), h7 = bloom_has(n2y, ayi);
-    if (!(h0 | h1 | h2 | h3 | h4 | h5 | h6 | h7)) return same;
-    const uint32_t* r1x = g.adj1 + (size_t)xj * g.W1;
-    const uint32_t* r1y = g.adj1 + (size_t)yj * g.W1;
-    const uint32_t* r2x = g.adj2 + (size_t)axj * g.W;
-    const uint32_t* r2y = g.adj2 + (size_t)ayj * g.W;
-    unsigned w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u, w4 = 0u, w5 = 0u, w6 = 0u, w7 = 0u;
-    if (h0) w0 = __ldg(r1x + (xi >> 5));
-    if (h1) w1 = __ldg(r1x + (yi >> 5));
-    if (h2) w2 = __ldg(r1y + (xi >> 5));
-    if (h3) w3 = __ldg(r1y + (yi >> 5));
-    if (h4) w4 = __ldg(r2x + (axi >> 5));
-    if (h5) w5 = __ldg(r2x + (ayi >> 5));
-    if (h6) w6 = __ldg(r2y + (axi >> 5));
-    if (h7) w7 = __ldg(r2y + (ayi >> 5));
-    const unsigned hit = ((w0 >> (xi & 31)) | (w1 >> (yi & 31)) | (w2 >> (xi & 31)) | (w3 >> (yi & 31)) |
-                          (w4 >> (axi & 31)) | (w5 >> (ayi & 31)) | (w6 >> (axi & 31)) | (w7 >> (ayi & 31))) & 1u;
-    return same | (hit != 0u);
-}
-
 // what one proposal of the round published for the pair tests and the resolve
 struct RoundSlot {
     int x, y, ax, ay, dc, di;
     uint4 n1x, n1y, n2x, n2y;  // Bloom signatures of N1(x), N1(y), N2(a_x), N2(a_y)
 };
+
+// Does the score of proposal j read anything that committing proposal i writes?  Its own
+// positions, the net1 neighbourhoods of its positions (aln[] gathers) and the net2
+// neighbourhoods of its images (alnInv[] gathers).  Adjacency is symmetric, so each test asks
+// BOTH nodes' Bloom signatures (false-positive rate squared) before the exact adjacency bit is
+// loaded; the rare exact probes are independent predicated loads.
+__device__ __forceinline__ bool commit_conflicts(const DevGraph& g, const RoundSlot& j, const RoundSlot& i) {
+    const bool same = (j.x == i.x) | (j.x == i.y) | (j.y == i.x) | (j.y == i.y);
+    const bool xir = i.x < g.n1, yir = i.y < g.n1;
+    const bool h0 = xir & bloom_has(j.n1x, i.x) & bloom_has(i.n1x, j.x);
+    const bool h1 = yir & bloom_has(j.n1x, i.y) & bloom_has(i.n1y, j.x);
+    const bool h2 = xir & bloom_has(j.n1y, i.x) & bloom_has(i.n1x, j.y);
+    const bool h3 = yir & bloom_has(j.n1y, i.y) & bloom_has(i.n1y, j.y);
+    const bool h4 = bloom_has(j.n2x, i.ax) & bloom_has(i.n2x, j.ax);
+    const bool h5 = bloom_has(j.n2x, i.ay) & bloom_has(i.n2y, j.ax);
+    const bool h6 = bloom_has(j.n2y, i.ax) & bloom_has(i.n2x, j.ay);
+    const bool h7 = bloom_has(j.n2y, i.ay) & bloom_has(i.n2y, j.ay);
+    if (!(h0 | h1 | h2 | h3 | h4 | h5 | h6 | h7)) return same;
+    const uint32_t* r1x = g.adj1 + (size_t)j.x * g.W1;
+    const uint32_t* r1y = g.adj1 + (size_t)j.y * g.W1;
+    const uint32_t* r2x = g.adj2 + (size_t)j.ax * g.W;
+    const uint32_t* r2y = g.adj2 + (size_t)j.ay * g.W;
+    unsigned w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u, w4 = 0u, w5 = 0u, w6 = 0u, w7 = 0u;
+    if (h0) w0 = __ldg(r1x + (i.x >> 5));
+    if (h1) w1 = __ldg(r1x + (i.y >> 5));
+    if (h2) w2 = __ldg(r1y + (i.x >> 5));
+    if (h3) w3 = __ldg(r1y + (i.y >> 5));
+    if (h4) w4 = __ldg(r2x + (i.ax >> 5));
+    if (h5) w5 = __ldg(r2x + (i.ay >> 5));
+    if (h6) w6 = __ldg(r2y + (i.ax >> 5));
+    if (h7) w7 = __ldg(r2y + (i.ay >> 5));
+    const unsigned hit = ((w0 >> (i.x & 31)) | (w1 >> (i.y & 31)) | (w2 >> (i.x & 31)) | (w3 >> (i.y & 31)) |
+                          (w4 >> (i.ax & 31)) | (w5 >> (i.ay & 31)) | (w6 >> (i.ax & 31)) | (w7 >> (i.ay & 31))) & 1u;
+    return same | (hit != 0u);
+}
 
 template <typename T, int G>
 __global__ void __launch_bounds__(kRound * G)
@@ -677,9 +679,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
             unsigned bits = 0u;
             for (int i = warp; i < nvalid - 1; i += kWarps) {
                 const RoundSlot& si = s_slot[i];
-                if (j > i && j < nvalid &&
-                    commit_conflicts(g, sj.x, sj.y, sj.ax, sj.ay, sj.n1x, sj.n1y, sj.n2x, sj.n2y, si.x, si.y, si.ax, si.ay))
-                    bits |= 1u << i;
+                if (j > i && j < nvalid && commit_conflicts(g, sj, si)) bits |= 1u << i;
             }
             if (bits) atomicOr(&s_conf[j], bits);
         }
@@ -744,9 +744,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     // proposal e now has (possibly) new images: refresh bit e of the later lanes
                     if (c > e) {
                         conf &= ~(1u << e);
-                        const RoundSlot& se = s_slot[e];
-                        if (commit_conflicts(g, x, y, me.ax, me.ay, me.n1x, me.n1y, me.n2x, me.n2y, se.x, se.y, se.ax, se.ay))
-                            conf |= 1u << e;
+                        if (commit_conflicts(g, me, s_slot[e])) conf |= 1u << e;
                     }
                     dirty_mask &= ~(1u << e);
                     start = e;            // judge it now
