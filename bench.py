@@ -217,6 +217,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off, so that the pinned host
+    buffers of the end-to-end leg are allocated next to the GPU's PCIe root (first touch)."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------- our CUDA arm
 def run_ours(args):
     import torch
@@ -228,7 +248,12 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    # the JSON line must be the only thing on stdout: libraries (NCCL prints its version there)
+    # get stderr instead
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -416,7 +441,8 @@ def run_ours(args):
                 "full_fitness_evals_per_sec_with_ics": ff_ics,
                 "full_fitness_evals_per_sec_adjacency_recount": ff_adj,
                 "hill_climb_iters_per_sec": arm.hill_climb(20000)}
-        print(json.dumps(line), flush=True)
+        line["config"]["numa_node"] = numa
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
