@@ -281,10 +281,11 @@ int launch_full(ona_engine* e, int first, int count, int seed_mode, int sequenti
         CU(e->t_seq.need((size_t)count * 2 * e->g.n1));
         seq = e->t_seq.p;
     }
-    // parts per individual: about two waves of CTAs, but at least ~4k edges per part
-    int parts = std::max(1, (2 * e->sm_count * 2 + count - 1) / count);
+    // parts per individual: about 4.5 CTAs per SM in total (measured best), at least ~4k edges per part
+    int parts = std::max(1, (9 * e->sm_count / 2 + count - 1) / count);
     parts = std::min(parts, std::max(1, (e->g.ne1 + e->g.ne2) / 8192));
     parts = std::min(parts, 32);
+    if (const char* fp = getenv("ONA_FF_PARTS")) parts = std::max(1, std::min(32, atoi(fp)));
     CU(e->t_part.need((size_t)count * parts));
     if (e->t_ticket.cap < (size_t)count) {
         CU(e->t_ticket.need((size_t)count));
