@@ -226,6 +226,38 @@ int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* 
  * per-generation all-gather that feeds the host NSGA-II sort (nsga-ii.cpp:14-118). */
 int ona_export_fitness_dev(ona_engine* e, int first, int count, double* dst_dev);
 
+/* -------------------------------------------------------------- NSGA-II ranking
+ * Replaces, for one [P][M] matrix of objective rows (larger is better), the sequence
+ * nsgaiimain.cpp:157-175 runs every generation:
+ *     nonDominatedSort(all)          nsga-ii.cpp:14-66   (dominates, :121-134)
+ *     normalizeFitnesses(all)        nsga-ii.cpp:68-84
+ *     setCrowdingDists(front)        nsga-ii.cpp:89-118  on every front
+ * P and M are independent of the engine's problem and population (P <= 2^20, M <= 16).
+ *   fitness        [P][M]   in
+ *   has_norm       [P]      in, nullable: individual i already carries normalised values
+ *                           (norm_io row i) from an earlier generation -- normalizeFitnesses
+ *                           only appends (:79), so setCrowdingDists keeps using those
+ *   norm_io        [P][M]   in/out, nullable unless has_norm: fitnessNormalized[0..M)
+ *   dom_rank       [P]      out: Alignment::domRank
+ *   front_order    [P]      out: the fronts nonDominatedSort returns, flattened, members in the
+ *                           reference's order;  front f = [front_offsets[f], front_offsets[f+1])
+ *   front_offsets  [P+1]    out (n_fronts+1 entries are written);  n_fronts: out, required
+ *   order_after    [P]      out: the same fronts after setCrowdingDists' in-place sorts (ties are
+ *                           placed as libstdc++'s std::sort places them)
+ *   crowd_dist     [P]      out: Alignment::crowdDist (boundary members: DBL_MAX, :104-105)
+ * Every out pointer except n_fronts may be NULL.  Fitness values must not be NaN (the
+ * reference's std::sort is undefined on them).  Synchronous. */
+int ona_nsga2_rank(ona_engine* e, int P, int M, const double* fitness, const unsigned char* has_norm,
+                   double* norm_io, int* dom_rank, int* front_order, int* front_offsets, int* n_fronts,
+                   int* order_after, double* crowd_dist);
+/* Same with every array in device memory (e.g. the all-gathered objective rows of all islands);
+ * n_fronts stays a host pointer.  Runs on the engine's stream and returns after the last kernel
+ * has been launched; the peel loop synchronises with the host to learn the number of fronts. */
+int ona_nsga2_rank_dev(ona_engine* e, int P, int M, const double* fitness_dev,
+                       const unsigned char* has_norm_dev, double* norm_dev, int* dom_rank_dev,
+                       int* front_order_dev, int* front_offsets_dev, int* n_fronts,
+                       int* order_after_dev, double* crowd_dist_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ona_kernels.cuh"
+#include "ona_nsga2.cuh"
 
 using namespace ona;
 
@@ -84,6 +85,12 @@ struct ona_engine {
     DevBuf<FullPartial> t_part;
     DevBuf<unsigned int> t_ticket;
     DevBuf<unsigned short> t_claims;
+    // NSGA-II ranking (ona_nsga2_rank): dominance bit matrix, peel state, host-call staging
+    DevBuf<uint32_t> ns_dom, ns_front;
+    DevBuf<int> ns_count, ns_pos, ns_cnt, ns_rank, ns_order, ns_offsets, ns_after, ns_slot, ns_old;
+    DevBuf<unsigned long long> ns_keys;
+    DevBuf<double> ns_fit, ns_norm, ns_crowd, ns_colmax, ns_key;
+    DevBuf<unsigned char> ns_has;
     int* d_flag = nullptr;
     // copy streams + events of the host-buffer pipeline (ona_swap_deltas)
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -576,6 +583,11 @@ void ona_engine_destroy(ona_engine* e) {
     e->t_d0.release(); e->t_d1.release(); e->t_d2.release(); e->t_d3.release(); e->t_d4.release();
     e->t_seq.release(); e->t_u0.release(); e->t_mask.release(); e->t_l0.release();
     e->t_part.release(); e->t_ticket.release(); e->t_claims.release();
+    e->ns_dom.release(); e->ns_front.release(); e->ns_count.release(); e->ns_pos.release();
+    e->ns_cnt.release(); e->ns_rank.release(); e->ns_order.release(); e->ns_offsets.release();
+    e->ns_after.release(); e->ns_slot.release(); e->ns_old.release(); e->ns_keys.release();
+    e->ns_fit.release(); e->ns_norm.release(); e->ns_crowd.release(); e->ns_colmax.release();
+    e->ns_key.release(); e->ns_has.release();
     if (e->d_flag) cudaFree(e->d_flag);
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
@@ -1096,6 +1108,131 @@ int ona_export_fitness_dev(ona_engine* e, int first, int count, double* dst_dev)
     LOCK(e);
     CU(cudaMemcpyAsync(dst_dev, e->pop.fit + (size_t)first * e->ob.M, (size_t)count * e->ob.M * 8,
                        cudaMemcpyDeviceToDevice, e->stream));
+    return ONA_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ NSGA-II ranking
+namespace {
+
+// Everything on the device; nullable outputs fall back to engine scratch.  Synchronises with the
+// host once per batch of peel rounds (the number of fronts is data dependent).
+int nsga2_device(ona_engine* e, int P, int M, const double* d_fit, const unsigned char* d_has,
+                 double* d_norm, int* d_rank, int* d_order, int* d_offsets, int* n_fronts, int* d_after,
+                 double* d_crowd) {
+    const int W = (P + 31) / 32;
+    CU(e->ns_dom.need((size_t)P * W)); CU(e->ns_front.need(2 * (size_t)W));
+    CU(e->ns_count.need(P)); CU(e->ns_pos.need(P)); CU(e->ns_cnt.need(2)); CU(e->ns_keys.need(P));
+    CU(e->ns_colmax.need(M)); CU(e->ns_key.need(P)); CU(e->ns_slot.need(P)); CU(e->ns_old.need(P));
+    if (!d_norm) { CU(e->ns_norm.need((size_t)P * M)); d_norm = e->ns_norm.p; }
+    if (!d_rank) { CU(e->ns_rank.need(P)); d_rank = e->ns_rank.p; }
+    if (!d_order) { CU(e->ns_order.need(P)); d_order = e->ns_order.p; }
+    if (!d_offsets) { CU(e->ns_offsets.need((size_t)P + 2)); d_offsets = e->ns_offsets.p; }
+    if (!d_after) { CU(e->ns_after.need(P)); d_after = e->ns_after.p; }
+    if (!d_crowd) { CU(e->ns_crowd.need(P)); d_crowd = e->ns_crowd.p; }
+    cudaStream_t st = e->stream;
+    CU(cudaMemsetAsync(e->ns_count.p, 0, (size_t)P * sizeof(int), st));
+    CU(cudaMemsetAsync(e->ns_front.p, 0, 2 * (size_t)W * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(e->ns_cnt.p, 0, 2 * sizeof(int), st));
+    CU(cudaMemsetAsync(d_offsets, 0, ((size_t)P + 1) * sizeof(int), st));
+
+    const dim3 dgrid((P + kDomCand - 1) / kDomCand, (P + kDomRows - 1) / kDomRows);
+    k_nsga_dominators<<<dgrid, kDomCand, (size_t)M * (kDomCand + kDomRows) * sizeof(double), st>>>(
+        d_fit, P, M, W, e->ns_dom.p, e->ns_count.p);
+    k_nsga_colmax<<<M, 256, 0, st>>>(d_fit, P, M, e->ns_colmax.p);
+    k_nsga_normalize<<<(P * M + 255) / 256, 256, 0, st>>>(d_fit, d_has, e->ns_colmax.p, P, M, d_norm);
+    NsgaPeel s{e->ns_dom.p, e->ns_count.p, d_rank, e->ns_front.p, e->ns_pos.p, e->ns_keys.p,
+               e->ns_cnt.p, d_offsets, d_order, P, W};
+    k_nsga_seed<<<(P + 255) / 256, 256, 0, st>>>(s);
+    e->launches += 4;
+    CU(cudaGetLastError());
+
+    // rounds past the last front are no-ops, so they are launched in growing batches and the
+    // offsets read back after each batch: the first empty front ends the sort (:39)
+    std::vector<int> off((size_t)P + 2, 0);
+    int t = 0, nf = -1, batch = 8;
+    while (nf < 0) {
+        const int t0 = t;
+        for (int r = 0; r < batch && t < P; ++r, ++t) {
+            k_nsga_order<<<(P + 255) / 256, 256, 0, st>>>(s, t);
+            k_nsga_peel<<<(P + 7) / 8, 256, 0, st>>>(s, t);
+            e->launches += 2;
+        }
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(off.data() + t0, d_offsets + t0, (size_t)(t - t0 + 1) * sizeof(int),
+                           cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int f = t0; f < t && nf < 0; ++f)
+            if (off[f + 1] == off[f]) nf = std::max(f, 1);   // fronts(1): there is always a front 0
+            else if (off[f + 1] == P) nf = f + 1;
+        if (nf < 0 && t >= P) nf = t;
+        batch = std::min(batch * 2, 64);
+    }
+    *n_fronts = nf;
+    int maxfront = 1;
+    for (int f = 0; f < nf; ++f) maxfront = std::max(maxfront, off[f + 1] - off[f]);
+
+    CU(cudaMemcpyAsync(d_after, d_order, (size_t)P * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    NsgaCrowd c{d_norm, d_offsets, d_after, d_crowd, e->ns_key.p, e->ns_slot.p, e->ns_old.p, M,
+                std::min(maxfront, kCrowdSmemItems)};
+    const size_t smem = (size_t)c.cap * 16;
+    CU(cudaFuncSetAttribute(k_nsga_crowd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCrowdSmemItems * 16)));
+    k_nsga_crowd<<<nf, kCrowdThreads, smem, st>>>(c);
+    e->launches++;
+    CU(cudaGetLastError());
+    return ONA_OK;
+}
+
+int nsga2_args(ona_engine* e, int P, int M, const void* fitness, const int* n_fronts) {
+    if (!e) return fail(ONA_ERR_INVALID, "null engine");
+    if (P < 1 || P > (1 << 20)) return fail(ONA_ERR_INVALID, "population size out of range [1, 2^20]");
+    if (M < 1 || M > kNsgaMaxM) return fail(ONA_ERR_INVALID, "number of objectives out of range [1, 16]");
+    if (!fitness || !n_fronts) return fail(ONA_ERR_INVALID, "null fitness / n_fronts");
+    return ONA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ona_nsga2_rank_dev(ona_engine* e, int P, int M, const double* fitness_dev, const unsigned char* has_norm_dev,
+                       double* norm_dev, int* dom_rank_dev, int* front_order_dev, int* front_offsets_dev,
+                       int* n_fronts, int* order_after_dev, double* crowd_dist_dev) {
+    TRY(nsga2_args(e, P, M, fitness_dev, n_fronts));
+    if (has_norm_dev && !norm_dev) return fail(ONA_ERR_INVALID, "has_norm without norm values");
+    LOCK(e);
+    return nsga2_device(e, P, M, fitness_dev, has_norm_dev, norm_dev, dom_rank_dev, front_order_dev,
+                        front_offsets_dev, n_fronts, order_after_dev, crowd_dist_dev);
+}
+
+int ona_nsga2_rank(ona_engine* e, int P, int M, const double* fitness, const unsigned char* has_norm,
+                   double* norm_io, int* dom_rank, int* front_order, int* front_offsets, int* n_fronts,
+                   int* order_after, double* crowd_dist) {
+    TRY(nsga2_args(e, P, M, fitness, n_fronts));
+    if (has_norm && !norm_io) return fail(ONA_ERR_INVALID, "has_norm without norm values");
+    LOCK(e);
+    cudaStream_t st = e->stream;
+    const size_t PM = (size_t)P * M;
+    CU(e->ns_fit.need(PM)); CU(e->ns_norm.need(PM)); CU(e->ns_has.need(P)); CU(e->ns_rank.need(P));
+    CU(e->ns_order.need(P)); CU(e->ns_offsets.need((size_t)P + 2)); CU(e->ns_after.need(P));
+    CU(e->ns_crowd.need(P));
+    CU(cudaMemcpyAsync(e->ns_fit.p, fitness, PM * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (has_norm) {
+        CU(cudaMemcpyAsync(e->ns_has.p, has_norm, (size_t)P, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(e->ns_norm.p, norm_io, PM * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    int nf = 0;
+    TRY(nsga2_device(e, P, M, e->ns_fit.p, has_norm ? e->ns_has.p : nullptr, e->ns_norm.p, e->ns_rank.p,
+                     e->ns_order.p, e->ns_offsets.p, &nf, e->ns_after.p, e->ns_crowd.p));
+    *n_fronts = nf;
+    if (norm_io) CU(cudaMemcpyAsync(norm_io, e->ns_norm.p, PM * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dom_rank) CU(cudaMemcpyAsync(dom_rank, e->ns_rank.p, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (front_order) CU(cudaMemcpyAsync(front_order, e->ns_order.p, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (front_offsets) CU(cudaMemcpyAsync(front_offsets, e->ns_offsets.p, ((size_t)nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (order_after) CU(cudaMemcpyAsync(order_after, e->ns_after.p, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (crowd_dist) CU(cudaMemcpyAsync(crowd_dist, e->ns_crowd.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return ONA_OK;
 }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "ona_set_island_offset", "ona_set_objectives", "ona_pop_resize", "ona_pop_upload", "ona_pop_download",
     "ona_pop_set_counters", "ona_pop_get_counters", "ona_full_fitness", "ona_full_fitness_dev",
     "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_steepest_step", "ona_rng_proposals", "ona_hill_climb", "ona_hill_climb_batched",
-    "ona_apply_swaps", "ona_export_fitness_dev",
+    "ona_apply_swaps", "ona_export_fitness_dev", "ona_nsga2_rank", "ona_nsga2_rank_dev",
 ]
 
 
@@ -95,6 +95,8 @@ def load_library(build_if_missing=True):
     L.ona_hill_climb_batched.argtypes = [vp, ci, ci, ll, vp, C.c_ulonglong, vp, vp]
     L.ona_apply_swaps.argtypes = [vp, ci, ci, ci, vp]
     L.ona_export_fitness_dev.argtypes = [vp, ci, ci, vp]
+    L.ona_nsga2_rank.argtypes = [vp, ci, ci] + [vp] * 9
+    L.ona_nsga2_rank_dev.argtypes = [vp, ci, ci] + [vp] * 9
     _LIB = L
     return L
 
@@ -336,6 +338,31 @@ class Engine:
     def export_fitness_dev(self, dst_ptr, first=0, count=None):
         count = self.P - first if count is None else count
         self._check(self.L.ona_export_fitness_dev(self.h, first, count, C.c_void_p(dst_ptr)))
+
+    def nsga2_rank(self, fitness, has_norm=None, norm=None):
+        """nonDominatedSort + normalizeFitnesses + setCrowdingDists on every front
+        (nsga-ii.cpp:14-118, in nsgaiimain.cpp:157-175's order) of a host [P, M] matrix."""
+        f = np.ascontiguousarray(fitness, dtype=np.float64)
+        P, M = f.shape
+        hn = None if has_norm is None else np.ascontiguousarray(has_norm, dtype=np.uint8)
+        nio = np.zeros((P, M), np.float64) if norm is None else np.array(norm, dtype=np.float64, order="C")
+        rank, order, after = (np.full(P, -1, np.int32) for _ in range(3))
+        offs, nf, crowd = np.zeros(P + 1, np.int32), C.c_int(0), np.zeros(P, np.float64)
+        self._check(self.L.ona_nsga2_rank(self.h, P, M, _ptr(f), _ptr(hn) if hn is not None else None,
+                                          _ptr(nio), _ptr(rank), _ptr(order), _ptr(offs),
+                                          C.addressof(nf), _ptr(after), _ptr(crowd)))
+        return {"dom_rank": rank, "front_order": order, "front_offsets": offs[:nf.value + 1].copy(),
+                "order_after": after, "crowd_dist": crowd, "norm": nio}
+
+    def nsga2_rank_dev(self, P, M, fitness_ptr, has_norm_ptr=None, norm_ptr=None, dom_rank_ptr=None,
+                       front_order_ptr=None, front_offsets_ptr=None, order_after_ptr=None,
+                       crowd_dist_ptr=None):
+        """the same on device buffers (data_ptr()s); returns the number of fronts."""
+        nf = C.c_int(0)
+        self._check(self.L.ona_nsga2_rank_dev(self.h, P, M, *[C.c_void_p(p) if p else None for p in (
+            fitness_ptr, has_norm_ptr, norm_ptr, dom_rank_ptr, front_order_ptr, front_offsets_ptr)],
+            C.addressof(nf), *[C.c_void_p(p) if p else None for p in (order_after_ptr, crowd_dist_ptr)]))
+        return nf.value
 
 
 def rng_proposals_host(seed, n1, n2, first_global, count, K, start=0):

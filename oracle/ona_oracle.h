@@ -77,6 +77,16 @@ double orc_time_hill_climb(OrcAln** alns, int nalns, const int* xy, long iters, 
 double orc_time_full_fitness(OrcAln** alns, int nalns, const int* names, int M, long reps,
                              int nthreads, double* sink);
 
+/* NSGA-II ranking of the objective rows (ona_oracle_nsga2.c; nsga-ii.cpp:14-134).
+ * fitness [P][M]; has_norm [P] or NULL; norm_io [P][M] in/out; dom_rank, front_order,
+ * order_after, crowd_dist [P]; front_offsets [P+1].  See oracle/ref_shim.cpp:ref_nsga2. */
+int orc_dominates(const double* f1, const double* f2, int M);                 /* :121-134 */
+void orc_gnu_sort_by_key(int n, const double* keys, int* idx);                /* std::sort, libstdc++ */
+void orc_gnu_heap_sort_by_key(int n, const double* keys, int* idx);           /* its depth-limit fallback */
+int orc_nsga2(int P, int M, const double* fitness, const unsigned char* has_norm, double* norm_io,
+              int* dom_rank, int* front_order, int* front_offsets, int* n_fronts,
+              int* order_after, double* crowd_dist);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,12 @@ def lib():
     L.orc_time_hill_climb.argtypes = [vp, C.c_int, I32P, C.c_long, I32P, C.c_int, C.c_int, C.c_int]
     L.orc_time_full_fitness.restype = C.c_double
     L.orc_time_full_fitness.argtypes = [vp, C.c_int, I32P, C.c_int, C.c_long, C.c_int, vp]
+    L.orc_nsga2.restype = C.c_int
+    L.orc_nsga2.argtypes = [C.c_int, C.c_int] + [vp] * 9
+    L.orc_dominates.restype = C.c_int
+    L.orc_dominates.argtypes = [vp, vp, C.c_int]
+    L.orc_gnu_sort_by_key.argtypes = [C.c_int, vp, vp]
+    L.orc_gnu_heap_sort_by_key.argtypes = [C.c_int, vp, vp]
     _LIB = L
     return L
 
@@ -208,3 +214,24 @@ def time_full_fitness(alns, names, reps, nthreads):
     t = lib().orc_time_full_fitness(_handles(alns), len(alns), names, len(names), reps, nthreads,
                                     C.addressof(sink))
     return t, sink.value
+
+
+def nsga2(fitness, has_norm=None, norm=None):
+    """orc_nsga2 (ona_oracle_nsga2.c); same result dictionary as oracle.ref.nsga2."""
+    from .ref import _nsga2_call
+    r = _nsga2_call(lib().orc_nsga2, fitness, has_norm, norm)
+    if r.pop("seconds") != 0:
+        raise ValueError("orc_nsga2: bad arguments")
+    return r
+
+
+def dominates(f1, f2):
+    a, b = (np.ascontiguousarray(v, dtype=np.float64) for v in (f1, f2))
+    return bool(lib().orc_dominates(a.ctypes.data, b.ctypes.data, len(a)))
+
+
+def gnu_sort_by_key(keys, idx, heap=False):
+    k, i = np.ascontiguousarray(keys, dtype=np.float64), np.array(idx, dtype=np.int32)
+    (lib().orc_gnu_heap_sort_by_key if heap else lib().orc_gnu_sort_by_key)(len(i), k.ctypes.data,
+                                                                            i.ctypes.data)
+    return i

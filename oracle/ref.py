@@ -103,6 +103,12 @@ def lib():
     L.ref_time_full_fitness.restype = C.c_double
     L.ref_time_full_fitness.argtypes = [vp, C.c_int, I32P, C.c_int, C.c_long, C.c_int, C.c_int, vp]
     L.ref_hardware_threads.restype = C.c_int
+    L.ref_nsga2.restype = C.c_double
+    L.ref_nsga2.argtypes = [C.c_int, C.c_int] + [vp] * 9
+    L.ref_dominates.restype = C.c_int
+    L.ref_dominates.argtypes = [vp, vp, C.c_int]
+    L.ref_std_sort_by_key.argtypes = [C.c_int, vp, vp]
+    L.ref_std_partial_sort_by_key.argtypes = [C.c_int, vp, vp]
     _LIB = L
     return L
 
@@ -327,3 +333,39 @@ def time_full_fitness(alns, names, reps, nthreads, with_ics=True):
 
 def hardware_threads():
     return lib().ref_hardware_threads()
+
+
+def _nsga2_call(fn, fitness, has_norm, norm):
+    """shared argument marshalling of ref_nsga2 / orc_nsga2 (oracle/port.py imports it)."""
+    f = np.ascontiguousarray(fitness, dtype=np.float64)
+    P, M = f.shape
+    hn = None if has_norm is None else np.ascontiguousarray(has_norm, dtype=np.uint8)
+    nio = np.zeros((P, M), np.float64) if norm is None else np.array(norm, dtype=np.float64, order="C")
+    rank, order, after = (np.full(P, -1, np.int32) for _ in range(3))
+    offs, nf, crowd = np.zeros(P + 1, np.int32), C.c_int(0), np.zeros(P, np.float64)
+    t = fn(P, M, f.ctypes.data, hn.ctypes.data if hn is not None else None, nio.ctypes.data,
+           rank.ctypes.data, order.ctypes.data, offs.ctypes.data, C.addressof(nf), after.ctypes.data,
+           crowd.ctypes.data)
+    return {"dom_rank": rank, "front_order": order, "front_offsets": offs[:nf.value + 1].copy(),
+            "order_after": after, "crowd_dist": crowd, "norm": nio, "seconds": t}
+
+
+def nsga2(fitness, has_norm=None, norm=None):
+    """nonDominatedSort + normalizeFitnesses + setCrowdingDists on every front (nsga-ii.cpp:14-118)."""
+    r = _nsga2_call(lib().ref_nsga2, fitness, has_norm, norm)
+    if r["seconds"] < 0:
+        raise RuntimeError("ref_nsga2: " + lib().ref_last_error().decode())
+    return r
+
+
+def dominates(f1, f2):
+    a, b = (np.ascontiguousarray(v, dtype=np.float64) for v in (f1, f2))
+    return bool(lib().ref_dominates(a.ctypes.data, b.ctypes.data, len(a)))
+
+
+def std_sort_by_key(keys, idx, heap=False):
+    """std::sort (or, heap=True, std::partial_sort over the whole range: introsort's fallback)."""
+    k, i = np.ascontiguousarray(keys, dtype=np.float64), np.array(idx, dtype=np.int32)
+    (lib().ref_std_partial_sort_by_key if heap else lib().ref_std_sort_by_key)(len(i), k.ctypes.data,
+                                                                               i.ctypes.data)
+    return i

@@ -24,6 +24,7 @@
 //                               caller-provided permutation/mask.
 // All three operate through the reference's doSwap/computeFitness/ics/... so the
 // arithmetic is still the reference's.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdint>
@@ -39,6 +40,7 @@
 #include "blastinfo.h"
 #include "goc.h"
 #include "localSearch.h"
+#include "nsga-ii.h"
 
 static thread_local std::string g_err;
 
@@ -436,6 +438,68 @@ double ref_time_full_fitness(void** alns, int nalns, const int* names, int M, lo
     for (double v : sums) s += v;
     if (sink) *sink = s;
     return t1 - t0;
+}
+
+// nsga-ii.cpp:14-118 through real Alignment objects, in the order nsgaiimain.cpp:157-175 calls them:
+// nonDominatedSort(all) -> normalizeFitnesses(all) -> setCrowdingDists(front) for every front.
+//   has_norm[i] != 0: individual i already carries M normalised values (norm_io row i) from an
+//   earlier generation; normalizeFitnesses only APPENDS (:79), so setCrowdingDists keeps reading
+//   those stale leading entries.  norm_io returns the leading M entries of every individual.
+//   front_order: the fronts as nonDominatedSort returned them; order_after: the same fronts after
+//   setCrowdingDists' in-place sorts.  Returns the time spent inside the three reference calls.
+double ref_nsga2(int P, int M, const double* fitness, const unsigned char* has_norm, double* norm_io,
+                 int* dom_rank, int* front_order, int* front_offsets, int* n_fronts, int* order_after,
+                 double* crowd_dist) {
+    REF_TRY
+    std::vector<Alignment> objs(P);
+    std::vector<Alignment*> all(P);
+    for (int i = 0; i < P; ++i) {
+        objs[i].fitness.assign(fitness + (size_t)i * M, fitness + (size_t)(i + 1) * M);
+        objs[i].domRank = -1;
+        objs[i].crowdDist = -1.0;
+        if (has_norm && has_norm[i])
+            objs[i].fitnessNormalized.assign(norm_io + (size_t)i * M, norm_io + (size_t)(i + 1) * M);
+        all[i] = &objs[i];
+    }
+    double t0 = now_s();
+    std::vector<std::vector<Alignment*> > fronts = nonDominatedSort(all);
+    normalizeFitnesses(all);
+    double t1 = now_s();
+    int off = 0;
+    *n_fronts = (int)fronts.size();
+    for (size_t f = 0; f < fronts.size(); ++f) {
+        front_offsets[f] = off;
+        for (Alignment* a : fronts[f]) front_order[off++] = (int)(a - &objs[0]);
+    }
+    front_offsets[fronts.size()] = off;
+    double t2 = now_s();
+    for (auto& fr : fronts)
+        if (!fr.empty()) setCrowdingDists(fr);
+    double t3 = now_s();
+    off = 0;
+    for (auto& fr : fronts)
+        for (Alignment* a : fr) order_after[off++] = (int)(a - &objs[0]);
+    for (int i = 0; i < P; ++i) {
+        dom_rank[i] = objs[i].domRank;
+        crowd_dist[i] = objs[i].crowdDist;
+        for (int m = 0; m < M; ++m) norm_io[(size_t)i * M + m] = objs[i].fitnessNormalized[m];
+    }
+    return (t1 - t0) + (t3 - t2);
+    REF_CATCH(-1.0)
+}
+
+// dominates (nsga-ii.cpp:121-134)
+int ref_dominates(const double* f1, const double* f2, int M) {
+    return dominates(std::vector<double>(f1, f1 + M), std::vector<double>(f2, f2 + M)) ? 1 : 0;
+}
+
+// std::sort of this toolchain's libstdc++ on an index array keyed by `keys` (the comparator shape of
+// nsga-ii.cpp:98-101), used to pin the oracle's restatement of GNU introsort on tie-heavy inputs.
+void ref_std_sort_by_key(int n, const double* keys, int* idx) {
+    std::sort(idx, idx + n, [keys](int a, int b) { return keys[a] < keys[b]; });
+}
+void ref_std_partial_sort_by_key(int n, const double* keys, int* idx) {
+    std::partial_sort(idx, idx + n, idx + n, [keys](int a, int b) { return keys[a] < keys[b]; });
 }
 
 int ref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }

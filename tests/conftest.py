@@ -25,6 +25,11 @@ def small_golden():
     return dict(np.load(os.path.join(GOLDEN, "small_pair.npz")))
 
 
+@pytest.fixture(scope="session")
+def nsga_golden():
+    return dict(np.load(os.path.join(GOLDEN, "nsga2.npz")))
+
+
 def dense_from_coo(n1, n2, r, c, v):
     S = np.zeros((n1, n2), np.float64)
     S[r, c] = v

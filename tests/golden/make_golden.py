@@ -13,6 +13,10 @@ Outputs
                      trajectory (proposals from mt19937(7), localSearch.cpp:21-28).
   small_pair.npz     a 120/150-node synthetic pair with bit scores AND GO annotations, with
                      partial (masked) individuals and every objective name.
+  nsga2.npz          nonDominatedSort / normalizeFitnesses / setCrowdingDists (nsga-ii.cpp:14-118)
+                     results of the compiled reference on the seeded matrices of
+                     tests/nsga_cases.py:GOLDEN_CASES, plus the two known-answer cases of the
+                     reference's own suite (tests.cpp:355-437).
 Nothing here is read at test time except the .npz files.
 """
 import os
@@ -159,7 +163,31 @@ def small_pair():
     print("small_pair.npz written", ctr)
 
 
+def nsga2():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import nsga_cases
+    out = {}
+    for i, (kind, P, M, seed, stale) in enumerate(nsga_cases.GOLDEN_CASES):
+        f = nsga_cases.make_case(kind, P, M, seed)
+        hn, nm = nsga_cases.stale_norm(P, M, seed) if stale else (None, None)
+        r = ref.nsga2(f, hn, nm)
+        for k in ("dom_rank", "front_order", "front_offsets", "order_after", "crowd_dist", "norm"):
+            out["c%d_%s" % (i, k)] = r[k]
+    # tests.cpp:355-408 (non_dominated_sort) and :410-437 (crowding_dist_assignment)
+    ka1 = np.array([[0.8, 0.7], [0.75, 0.75], [0.4, 0.6], [0.7, 0.8], [0.6, 0.4], [0.5, 0.5]])
+    ka2 = np.array([[0.6, 0.9], [0.7, 0.8], [0.75, 0.75], [0.8, 0.7], [0.9, 0.6]])
+    for name, f in (("ka1", ka1), ("ka2", ka2)):
+        r = ref.nsga2(f)
+        out[name + "_fitness"] = f
+        for k in ("dom_rank", "front_order", "front_offsets", "order_after", "crowd_dist", "norm"):
+            out["%s_%s" % (name, k)] = r[k]
+    np.savez_compressed(os.path.join(OUT, "nsga2.npz"), **out)
+    print("nsga2.npz written;", len(nsga_cases.GOLDEN_CASES), "cases; ka1 fronts", out["ka1_front_offsets"],
+          "ka2 crowd", out["ka2_crowd_dist"])
+
+
 if __name__ == "__main__":
     assert ref.available(), "build oracle/_ref first (make -C oracle)"
+    nsga2()
     small_pair()
     example_pair()

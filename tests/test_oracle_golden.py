@@ -97,3 +97,33 @@ def test_refseed_truncation_hazard():
     assert port.lib().orc_refseed_conserved(104, 11500) == 103
     assert port.lib().orc_refseed_conserved(140, 12177) == 140
     assert port.lib().orc_refseed_conserved(5, 0) == 0
+
+
+# ------------------------------------------------------------------ NSGA-II ranking (nsga-ii.cpp:14-118)
+NSGA_KEYS = ("dom_rank", "front_order", "front_offsets", "order_after", "crowd_dist", "norm")
+
+
+def test_nsga2_golden_cases(nsga_golden):
+    import nsga_cases
+    for i, (kind, P, M, seed, stale) in enumerate(nsga_cases.GOLDEN_CASES):
+        f = nsga_cases.make_case(kind, P, M, seed)
+        hn, nm = nsga_cases.stale_norm(P, M, seed) if stale else (None, None)
+        got = port.nsga2(f, hn, nm)
+        want = {k: nsga_golden["c%d_%s" % (i, k)] for k in NSGA_KEYS}
+        nsga_cases.assert_same(got, want, (i, kind))
+
+
+def test_nsga2_reference_suite_known_answers(nsga_golden):
+    """tests.cpp:355-408 (two fronts of three) and :410-437 (crowding 1.0, 2/3, 1.0)."""
+    import nsga_cases
+    g = nsga_golden
+    r = port.nsga2(g["ka1_fitness"])
+    assert list(r["front_offsets"]) == [0, 3, 6]
+    assert (g["ka1_fitness"][r["front_order"][:3]] > 0.6).all()
+    assert (g["ka1_fitness"][r["front_order"][3:]] < 0.7).all()
+    nsga_cases.assert_same(r, {k: g["ka1_" + k] for k in NSGA_KEYS}, "ka1")
+    r = port.nsga2(g["ka2_fitness"])
+    assert list(r["front_offsets"]) == [0, 5]
+    assert np.allclose(r["crowd_dist"][1:4], [1.0, 2.0 / 3.0, 1.0], rtol=1e-12)
+    assert r["crowd_dist"][0] == r["crowd_dist"][4] == np.finfo(np.float64).max
+    nsga_cases.assert_same(r, {k: g["ka2_" + k] for k in NSGA_KEYS}, "ka2")

@@ -122,3 +122,42 @@ def test_refseed_formula_matches_compiled_reference(world):
         assert a.counters()[0] == port.lib().orc_refseed_conserved(C, I)
         hits += int(a.counters()[0] != C)
     assert hits >= 0
+
+
+# ------------------------------------------------------------------ NSGA-II ranking
+def test_gnu_sort_restatement_matches_std_sort():
+    """orc_gnu_sort_by_key places tied keys exactly where this toolchain's std::sort does
+    (setCrowdingDists sorts fronts with it, nsga-ii.cpp:98-101); the heap-sort fallback of the
+    depth limit is pinned separately against std::partial_sort."""
+    rng = np.random.default_rng(5)
+    for t in range(600):
+        n = int(rng.integers(1, 400)) if t % 10 else int(rng.integers(1000, 5000))
+        kind = t % 5
+        if kind == 0:
+            k = rng.random(n)
+        elif kind == 1:
+            k = rng.integers(0, 5, n).astype(np.float64)
+        elif kind == 2:
+            k = rng.integers(0, max(2, n // 4), n).astype(np.float64)
+        elif kind == 3:
+            k = np.sort(rng.integers(0, 50, n)).astype(np.float64)
+        else:
+            k = np.sort(rng.integers(0, 50, n))[::-1].astype(np.float64)
+        idx = rng.permutation(n) if t % 2 else np.arange(n)
+        assert np.array_equal(ref.std_sort_by_key(k, idx), port.gnu_sort_by_key(k, idx)), t
+        if n <= 400:
+            assert np.array_equal(ref.std_sort_by_key(k, idx, heap=True),
+                                  port.gnu_sort_by_key(k, idx, heap=True)), t
+
+
+def test_nsga2_matches_reference_live():
+    import nsga_cases
+    rng = np.random.default_rng(6)
+    for t in range(120):
+        kind = nsga_cases.KINDS[t % len(nsga_cases.KINDS)]
+        P, M = int(rng.integers(1, 420)), int(rng.integers(1, 5))
+        f = nsga_cases.make_case(kind, P, M, 500 + t)
+        hn, nm = nsga_cases.stale_norm(P, M, t) if t % 3 == 0 else (None, None)
+        nsga_cases.assert_same(port.nsga2(f, hn, nm), ref.nsga2(f, hn, nm), (t, kind, P, M))
+        a, b = f[int(rng.integers(0, P))], f[int(rng.integers(0, P))]
+        assert port.dominates(a, b) == ref.dominates(a, b)
