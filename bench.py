@@ -180,6 +180,14 @@ class CpuArm:
             t = self.mod.time_hill_climb(copies, OBJECTIVES, xy, iters, -1, self.threads)
         return n * iters / t
 
+    def nsga2(self, rows):
+        """single-threaded like the reference's (nsgaiimain.cpp:157-175 runs it on the main thread)"""
+        if self.kind == "reference":
+            return self.mod.nsga2(rows)["seconds"]
+        t0 = time.perf_counter()
+        self.mod.nsga2(rows)
+        return time.perf_counter() - t0
+
     def full_fitness(self, reps):
         if self.kind == "reference":
             t_ics, _ = self.mod.time_full_fitness(self.alns, OBJECTIVES, reps, self.threads, True)
@@ -379,6 +387,28 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(hb_ms, op=dist.ReduceOp.MAX)
     hb_ms = float(hb_ms.item())
+    # ---- NSGA-II ranking of one generation's objective rows (rank 0; every island would run the
+    # same call on the all-gathered matrix).  R_t = parents + children = 2 x popsize rows of the
+    # bench objectives, and a C5-sized 16 384 x 3 matrix.
+    nsga = {}
+    if rank == 0:
+        rng = np.random.default_rng(5)
+        c_ = rng.integers(0, 60, 2 * world * P).astype(np.float64)
+        gen_rows = np.stack([c_ / (pair.E1 + rng.integers(60, 90, c_.size) - c_),
+                             np.round(rng.random(c_.size) * 40.0, 1)], axis=1)
+        for tag, rows in (("generation", gen_rows), ("c5", rng.random((16384, 3)))):
+            ft = torch.from_numpy(np.ascontiguousarray(rows)).to(dev)
+            with torch.cuda.stream(stream):
+                nf = e.nsga2_rank_dev(rows.shape[0], rows.shape[1], ft.data_ptr())   # warm-up
+                l0 = e.kernel_launches()
+                hc_ev[0].record(stream)
+                for _ in range(5):
+                    nf = e.nsga2_rank_dev(rows.shape[0], rows.shape[1], ft.data_ptr())
+                hc_ev[1].record(stream)
+                e.synchronize()
+            nsga[tag] = {"rows": int(rows.shape[0]), "objectives": int(rows.shape[1]), "fronts": int(nf),
+                         "ms": hc_ev[0].elapsed_time(hc_ev[1]) / 5,
+                         "launches": int((e.kernel_launches() - l0) // 5), "_rows": rows}
     clocks = sampler.stop()
 
     if rank == 0:
@@ -427,6 +457,9 @@ def run_ours(args):
                                                 "subset applied in-kernel (ona_hill_climb_batched)"},
             "wall_s_timed_region": t_wall,
         }
+        line["nsga2_rank"] = {k: {kk: vv for kk, vv in v.items() if kk != "_rows"} for k, v in nsga.items()}
+        line["nsga2_rank"]["call"] = ("ona_nsga2_rank_dev: nonDominatedSort + normalizeFitnesses + "
+                                      "setCrowdingDists on every front (nsga-ii.cpp:14-118), device-resident rows")
         if world == 1 and not args.no_cpu_baseline:
             arm = CpuArm(pair)
             n = 150000 * arm.threads
@@ -440,7 +473,8 @@ def run_ours(args):
                               n, arm.threads, len(arm.alns)),
                 "full_fitness_evals_per_sec_with_ics": ff_ics,
                 "full_fitness_evals_per_sec_adjacency_recount": ff_adj,
-                "hill_climb_iters_per_sec": arm.hill_climb(20000)}
+                "hill_climb_iters_per_sec": arm.hill_climb(20000),
+                "nsga2_rank_ms_1_thread": {k: 1e3 * arm.nsga2(v["_rows"]) for k, v in nsga.items()}}
         line["config"]["numa_node"] = numa
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:

@@ -8,6 +8,10 @@
 // Per thread t: Alignment(net1,net2,bit,goc); shuf(mt19937(seed+t)); computeFitness;
 // correctHillClimb(mt19937(seed+1000+t), iters, obj=-1); then mutate + a crossover with thread
 // 0's result; prints counters/objectives and writes <out_prefix>_<t>.aln via Alignment::save.
+// Last, one NSGA-II generation's ranking (nsgaiimain.cpp:157-175) of a small population of
+// mutated children, once by the reference's own nsga-ii.cpp (linked unchanged) and once by
+// ona_host::rankGeneration on copies; prints whether the two agree member by member.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -18,6 +22,8 @@
 #include "blastinfo.h"
 #include "goc.h"
 #include "localSearch.h"
+#include "nsga-ii.h"
+#include "ona_host.hpp"
 
 using namespace std;
 
@@ -71,6 +77,44 @@ int main(int argc, char** argv) {
                    child.currInducedCount, bit ? child.currBitscore : 0.0, goc ? child.currGOC : 0.0, child.ics());
             for (double f : child.fitness) printf(" %.17g", f);
             printf("\n");
+        }
+        {
+            vector<Alignment*> refPop, gpuPop;
+            RandGenT g(seed + 4000);
+            for (int i = 0; i < 48; i++) {
+                Alignment* a = new Alignment(*alns[i % nthreads]);
+                if (i >= nthreads) a->mutate(g, 0.002f * (1 + i % 5), true);
+                a->computeFitness(names);
+                refPop.push_back(a);
+                gpuPop.push_back(new Alignment(*a));
+            }
+            bool same = true;
+            size_t nfronts = 0;
+            for (int gen = 0; gen < 2; gen++) {  // second pass: stale fitnessNormalized entries (:79)
+                vector<vector<Alignment*> > fr = nonDominatedSort(refPop);
+                normalizeFitnesses(refPop);
+                for (auto& f : fr) setCrowdingDists(f);
+                vector<vector<Alignment*> > fg = ona_host::rankGeneration(gpuPop);
+                same = same && fr.size() == fg.size();
+                nfronts = fg.size();
+                for (size_t f = 0; same && f < fr.size(); f++) {
+                    same = fr[f].size() == fg[f].size();
+                    for (size_t k = 0; same && k < fr[f].size(); k++) {
+                        const size_t ir = find(refPop.begin(), refPop.end(), fr[f][k]) - refPop.begin();
+                        const size_t ig = find(gpuPop.begin(), gpuPop.end(), fg[f][k]) - gpuPop.begin();
+                        same = ir == ig && fr[f][k]->domRank == fg[f][k]->domRank &&
+                               fr[f][k]->crowdDist == fg[f][k]->crowdDist &&
+                               fr[f][k]->fitnessNormalized == fg[f][k]->fitnessNormalized;
+                    }
+                }
+                for (int i = 0; i < 10; i++) {  // next generation: replace a few members
+                    refPop[i]->mutate(g, 0.004f, true);
+                    refPop[i]->computeFitness(names);
+                    refPop[i]->fitnessNormalized.clear();  // a new child has none yet
+                    *gpuPop[i] = *refPop[i];
+                }
+            }
+            printf("nsga2 fronts %zu %s\n", nfronts, same ? "identical" : "DIFFERENT");
         }
         Alignment probe(*alns[0]);
         printf("snd %.17g\n", swapNormalizedDelta(probe, names, 3, 7));

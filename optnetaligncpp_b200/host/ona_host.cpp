@@ -160,4 +160,49 @@ void apply_swaps(Alignment& a, const std::vector<int>& xy) {
     c.download(one);
 }
 
+std::vector<std::vector<Alignment*> > rankGeneration(const std::vector<Alignment*>& in, bool crowding) {
+    std::vector<std::vector<Alignment*> > fronts(1);  // nsga-ii.cpp:16: there is always a front 0
+    if (in.empty()) return fronts;
+    const int P = (int)in.size(), M = (int)in[0]->fitness.size();
+    std::vector<double> fit((size_t)P * M), norm((size_t)P * M, 0.0), crowd(P);
+    std::vector<unsigned char> has(P, 0);
+    for (int i = 0; i < P; i++) {
+        std::copy(in[i]->fitness.begin(), in[i]->fitness.end(), fit.begin() + (size_t)i * M);
+        // normalizeFitnesses only appends (:79): whoever was normalised in an earlier generation
+        // keeps being read through its first M entries
+        if ((int)in[i]->fitnessNormalized.size() >= M) {
+            has[i] = 1;
+            std::copy(in[i]->fitnessNormalized.begin(), in[i]->fitnessNormalized.begin() + M,
+                      norm.begin() + (size_t)i * M);
+        }
+    }
+    std::vector<int> rank(P), order(P), after(P), offs(P + 1);
+    int nf = 0;
+    Context& c = context_for(*in[0]);
+    {
+        std::lock_guard<std::mutex> lk(c.lock());
+        check(ona_nsga2_rank(c.engine(), P, M, fit.data(), has.data(), norm.data(), rank.data(), order.data(),
+                             offs.data(), &nf, after.data(), crowd.data()));
+    }
+    for (int i = 0; i < P; i++) {
+        in[i]->domRank = rank[i];
+        in[i]->numThatDominate = 0;
+        in[i]->dominated.clear();
+    }
+    if (crowding) {
+        for (int m = 0; m < M; m++) {  // :68-84, the append itself
+            double mx = 0.0;
+            for (int i = 0; i < P; i++)
+                if (fit[(size_t)i * M + m] > mx) mx = fit[(size_t)i * M + m];
+            for (int i = 0; i < P; i++) in[i]->fitnessNormalized.push_back(fit[(size_t)i * M + m] / mx);
+        }
+        for (int i = 0; i < P; i++) in[i]->crowdDist = crowd[i];
+    }
+    fronts.assign(nf, std::vector<Alignment*>());
+    const std::vector<int>& src = crowding ? after : order;
+    for (int f = 0; f < nf; f++)
+        for (int k = offs[f]; k < offs[f + 1]; k++) fronts[f].push_back(in[src[k]]);
+    return fronts;
+}
+
 }  // namespace ona_host

@@ -72,4 +72,14 @@ void seed_counters(Alignment& a);
 // apply an ordered list of doSwap(x,y) to `a` on the GPU (incremental counter updates)
 void apply_swaps(Alignment& a, const std::vector<int>& xy);
 
+
+// nsgaiimain.cpp:157-175 as ONE engine call (ona_nsga2_rank): nonDominatedSort(in)
+// (nsga-ii.cpp:14-66), normalizeFitnesses(in) (:68-84) and setCrowdingDists on every front
+// (:89-118).  Sets domRank, numThatDominate (0, as the peeling leaves it), crowdDist and appends
+// the normalised objectives exactly like the reference; returns the fronts in the order
+// setCrowdingDists leaves them (pass crowding = false for nonDominatedSort's own order and
+// nothing but domRank set).  The `dominated` lists -- scratch of the reference's sort, read by
+// nobody else -- are left empty.
+std::vector<std::vector<Alignment*> > rankGeneration(const std::vector<Alignment*>& in, bool crowding = true);
+
 }  // namespace ona_host

@@ -69,6 +69,10 @@ def test_dropin_matches_reference(with_goc):
         assert float(got[7]) == c[2] and float(got[9]) == c[3]
         assert float(got[11]) == child.ics()
         assert [float(v) for v in got[12:]] == list(child.compute_fitness(names))
+    # one generation's NSGA-II ranking, checked inside the demo against the reference's own
+    # nsga-ii.cpp (linked unchanged): fronts, member order, domRank, crowdDist, fitnessNormalized
+    got = lines[2 * nthreads]
+    assert got[0] == "nsga2" and int(got[2]) >= 1 and got[3] == "identical", got
     snd = climbed[0].swap_normalized_delta(names, 3, 7)
-    got = float(lines[2 * nthreads][1])
+    got = float(lines[2 * nthreads + 1][1])
     assert got == snd or (np.isnan(got) and np.isnan(snd))
