@@ -1132,6 +1132,22 @@ int nsga2_device(ona_engine* e, int P, int M, const double* d_fit, const unsigne
     if (!d_after) { CU(e->ns_after.need(P)); d_after = e->ns_after.p; }
     if (!d_crowd) { CU(e->ns_crowd.need(P)); d_crowd = e->ns_crowd.p; }
     cudaStream_t st = e->stream;
+    if (P <= kSmallP && !getenv("ONA_NSGA_MULTI")) {
+        // one CTA ranks the whole population; the crowding grid covers every possible front
+        // (CTAs of empty fronts exit at once), so nothing waits for the host
+        const size_t sm = nsga_small_smem(P);
+        CU(cudaFuncSetAttribute(k_nsga_rank_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsga_small_smem(kSmallP)));
+        CU(e->ns_cnt.need(2));
+        k_nsga_rank_small<<<1, 1024, sm, st>>>(d_fit, d_has, d_norm, P, M, d_rank, d_order, d_offsets, e->ns_cnt.p);
+        CU(cudaMemcpyAsync(d_after, d_order, (size_t)P * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        NsgaCrowd c{d_norm, d_offsets, d_after, d_crowd, e->ns_key.p, e->ns_slot.p, e->ns_old.p, M, P};
+        k_nsga_crowd<<<P, kCrowdThreads, (size_t)P * 16, st>>>(c);
+        e->launches += 2;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(n_fronts, e->ns_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return ONA_OK;
+    }
     CU(cudaMemsetAsync(e->ns_count.p, 0, (size_t)P * sizeof(int), st));
     CU(cudaMemsetAsync(e->ns_front.p, 0, 2 * (size_t)W * sizeof(uint32_t), st));
     CU(cudaMemsetAsync(e->ns_cnt.p, 0, 2 * sizeof(int), st));

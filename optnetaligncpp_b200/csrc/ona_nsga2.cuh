@@ -175,6 +175,130 @@ __global__ void k_nsga_peel(NsgaPeel s, int t) {
     }
 }
 
+// ------------------------------------------------------------------ small populations, one CTA
+// P <= 1024 rows (the reference's usual 2 x popsize): dominator matrix, counts and the whole peel
+// loop stay in one CTA's shared memory, so ranking a generation is two launches (this + the
+// crowding kernel) and no host round trip.  Same keys, same order as the multi-kernel path.
+constexpr int kSmallP = 1024;
+__host__ __device__ inline size_t nsga_small_smem(int P) {
+    const int W = (P + 31) / 32;
+    return (size_t)P * 8 + ((size_t)P * W + 2 * (size_t)P + W) * 4;
+}
+__global__ void __launch_bounds__(1024)
+k_nsga_rank_small(const double* __restrict__ fit, const unsigned char* __restrict__ has_norm,
+                  double* __restrict__ norm, int P, int M, int* __restrict__ rank,
+                  int* __restrict__ order, int* __restrict__ offsets, int* __restrict__ n_fronts) {
+    extern __shared__ double nsga_sm[];
+    const int W = (P + 31) / 32;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(nsga_sm);  // [P]
+    uint32_t* dom = reinterpret_cast<uint32_t*>(keys + P);                      // [P][W]
+    int* count = reinterpret_cast<int*>(dom + (size_t)P * W);                   // [P]; -1 = ranked
+    int* pos = count + P;                                                       // [P]
+    uint32_t* front = reinterpret_cast<uint32_t*>(pos + P);                     // [W]
+    __shared__ int s_n;
+    __shared__ double s_max[kNsgaMaxM];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp < M) {  // :71-76
+        double mx = 0.0;
+        for (int i = lane; i < P; i += 32) {
+            const double v = fit[(size_t)i * M + warp];
+            if (v > mx) mx = v;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double v = __shfl_xor_sync(0xffffffffu, mx, o);
+            if (v > mx) mx = v;
+        }
+        if (lane == 0) s_max[warp] = mx;
+    }
+    for (int q = warp; q < P; q += 32) {  // :17-30, one warp per row, one ballot per word
+        int cnt = 0;
+        for (int w = 0; w < W; ++w) {
+            const int a = 32 * w + lane;
+            bool ge = a < P, gt = false;
+            if (ge)
+                for (int m = 0; m < M; ++m) {
+                    const double x = fit[(size_t)a * M + m], y = fit[(size_t)q * M + m];
+                    ge &= !(x < y);
+                    gt |= x > y;
+                }
+            const unsigned b = __ballot_sync(0xffffffffu, ge & gt);
+            if (lane == 0) dom[(size_t)q * W + w] = b;
+            cnt += __popc(b);
+        }
+        if (lane == 0) count[q] = cnt;
+    }
+    if (tid == 0) {
+        s_n = 0;
+        offsets[0] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < P * M; i += 1024)  // :78-81
+        if (!(has_norm && has_norm[i / M])) norm[i] = fit[i] / s_max[i % M];
+    for (int q = tid; q < P; q += 1024) {    // :31-35
+        const bool first = count[q] == 0;
+        rank[q] = first ? 0 : -1;
+        if (first) {
+            count[q] = -1;
+            keys[atomicAdd(&s_n, 1)] = (unsigned long long)q;
+        }
+    }
+    __syncthreads();
+    int t = 0, base = 0;
+    for (;;) {
+        const int n = s_n;
+        if (n == 0) break;
+        __syncthreads();
+        if (tid < W) front[tid] = 0u;
+        if (tid == 0) {
+            s_n = 0;
+            offsets[t + 1] = base + n;
+        }
+        unsigned long long key = 0ull;
+        int p = 0;
+        if (tid < n) {  // n <= P <= 1024
+            key = keys[tid];
+            for (int j = 0; j < n; ++j) p += keys[j] < key ? 1 : 0;
+        }
+        __syncthreads();
+        if (tid < n) {
+            const int q = (int)(key & 0xffffffffull);
+            order[base + p] = q;
+            pos[q] = p;
+            atomicOr(front + (q >> 5), 1u << (q & 31));
+        }
+        __syncthreads();
+        for (int q = warp; q < P; q += 32) {  // :41-49
+            if (count[q] <= 0) continue;
+            uint32_t d = lane < W ? (dom[(size_t)q * W + lane] & front[lane]) : 0u;
+            int hit = __popc(d), mp = -1;
+            while (d) {
+                const int b = __ffs(d) - 1;
+                d &= d - 1;
+                mp = max(mp, pos[32 * lane + b]);
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                hit += __shfl_xor_sync(0xffffffffu, hit, o);
+                mp = max(mp, __shfl_xor_sync(0xffffffffu, mp, o));
+            }
+            if (lane == 0 && hit) {
+                const int c = count[q] - hit;
+                count[q] = c == 0 ? -1 : c;
+                if (c == 0) {
+                    rank[q] = t + 1;
+                    keys[atomicAdd(&s_n, 1)] = ((unsigned long long)(unsigned)mp << 32) | (unsigned)q;
+                }
+            }
+        }
+        __syncthreads();
+        base += n;
+        ++t;
+    }
+    // fronts(1): there is always a front 0; the unused tail of `offsets` describes empty fronts
+    if (tid == 0) *n_fronts = max(t, 1);
+    for (int f = t + 1 + tid; f <= P; f += 1024) offsets[f] = base;
+}
+
 // ------------------------------------------------------------------ std::sort of libstdc++, on pairs
 // (key[i], slot[i]) is one element; comp(i, j) = key[i] < key[j] (nsga-ii.cpp:98-101).
 // The range guards [lo, hi) never trigger on NaN-free keys (the library's loops are unguarded

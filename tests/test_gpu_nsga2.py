@@ -20,7 +20,16 @@ def eng():
     return engine.Engine.from_pair(pair, [1, 6])
 
 
-def test_golden_cases(eng, nsga_golden):
+@pytest.fixture(params=["one_cta", "multi_kernel"])
+def small_path(request, monkeypatch):
+    """populations of <= 1024 rows are ranked by one CTA; ONA_NSGA_MULTI forces the per-front
+    kernel pairs that larger populations use, so both paths see every small case"""
+    if request.param == "multi_kernel":
+        monkeypatch.setenv("ONA_NSGA_MULTI", "1")
+    return request.param
+
+
+def test_golden_cases(eng, nsga_golden, small_path):
     for i, (kind, P, M, seed, stale) in enumerate(nsga_cases.GOLDEN_CASES):
         f = nsga_cases.make_case(kind, P, M, seed)
         hn, nm = nsga_cases.stale_norm(P, M, seed) if stale else (None, None)
@@ -28,7 +37,7 @@ def test_golden_cases(eng, nsga_golden):
         nsga_cases.assert_same(got, {k: nsga_golden["c%d_%s" % (i, k)] for k in KEYS}, (i, kind))
 
 
-def test_reference_suite_known_answers(eng, nsga_golden):
+def test_reference_suite_known_answers(eng, nsga_golden, small_path):
     g = nsga_golden
     for name in ("ka1", "ka2"):  # tests.cpp:355-408, :410-437
         r = eng.nsga2_rank(g[name + "_fitness"])
@@ -37,10 +46,10 @@ def test_reference_suite_known_answers(eng, nsga_golden):
 
 
 @pytest.mark.parametrize("kind", nsga_cases.KINDS)
-def test_random_cases_against_oracle(eng, kind):
+def test_random_cases_against_oracle(eng, kind, small_path):
     rng = np.random.default_rng(nsga_cases.KINDS.index(kind))
     for t in range(12):
-        P, M = int(rng.integers(1, 700)), int(rng.integers(1, 6))
+        P, M = int(rng.integers(1, 1025 if t % 4 == 0 else 700)), int(rng.integers(1, 6))
         f = nsga_cases.make_case(kind, P, M, 900 + t)
         hn, nm = nsga_cases.stale_norm(P, M, t) if t % 3 == 0 else (None, None)
         nsga_cases.assert_same(eng.nsga2_rank(f, hn, nm), port.nsga2(f, hn, nm), (kind, t, P, M))
