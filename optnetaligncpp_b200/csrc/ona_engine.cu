@@ -1121,7 +1121,7 @@ namespace {
 int nsga2_device(ona_engine* e, int P, int M, const double* d_fit, const unsigned char* d_has,
                  double* d_norm, int* d_rank, int* d_order, int* d_offsets, int* n_fronts, int* d_after,
                  double* d_crowd) {
-    const int W = (P + 31) / 32;
+    const int W = ((P + kDomCand - 1) / kDomCand) * (kDomCand / 32);  // row stride: words, multiple of 8
     CU(e->ns_dom.need((size_t)P * W)); CU(e->ns_front.need(2 * (size_t)W));
     CU(e->ns_count.need(P)); CU(e->ns_pos.need(P)); CU(e->ns_cnt.need(2)); CU(e->ns_keys.need(P));
     CU(e->ns_colmax.need(M)); CU(e->ns_key.need(P)); CU(e->ns_slot.need(P)); CU(e->ns_old.need(P));
@@ -1148,19 +1148,24 @@ int nsga2_device(ona_engine* e, int P, int M, const double* d_fit, const unsigne
         CU(cudaStreamSynchronize(st));
         return ONA_OK;
     }
-    CU(cudaMemsetAsync(e->ns_count.p, 0, (size_t)P * sizeof(int), st));
     CU(cudaMemsetAsync(e->ns_front.p, 0, 2 * (size_t)W * sizeof(uint32_t), st));
     CU(cudaMemsetAsync(e->ns_cnt.p, 0, 2 * sizeof(int), st));
     CU(cudaMemsetAsync(d_offsets, 0, ((size_t)P + 1) * sizeof(int), st));
 
     const dim3 dgrid((P + kDomCand - 1) / kDomCand, (P + kDomRows - 1) / kDomRows);
-    k_nsga_dominators<<<dgrid, kDomCand, (size_t)M * (kDomCand + kDomRows) * sizeof(double), st>>>(
-        d_fit, P, M, W, e->ns_dom.p, e->ns_count.p);
+    const size_t dsm = (size_t)M * (kDomCand + kDomRows) * sizeof(double);
+    switch (M) {
+        case 1: k_nsga_dominators<1><<<dgrid, kDomCand, dsm, st>>>(d_fit, P, M, W, e->ns_dom.p); break;
+        case 2: k_nsga_dominators<2><<<dgrid, kDomCand, dsm, st>>>(d_fit, P, M, W, e->ns_dom.p); break;
+        case 3: k_nsga_dominators<3><<<dgrid, kDomCand, dsm, st>>>(d_fit, P, M, W, e->ns_dom.p); break;
+        case 4: k_nsga_dominators<4><<<dgrid, kDomCand, dsm, st>>>(d_fit, P, M, W, e->ns_dom.p); break;
+        default: k_nsga_dominators<0><<<dgrid, kDomCand, dsm, st>>>(d_fit, P, M, W, e->ns_dom.p); break;
+    }
     k_nsga_colmax<<<M, 256, 0, st>>>(d_fit, P, M, e->ns_colmax.p);
     k_nsga_normalize<<<(P * M + 255) / 256, 256, 0, st>>>(d_fit, d_has, e->ns_colmax.p, P, M, d_norm);
     NsgaPeel s{e->ns_dom.p, e->ns_count.p, d_rank, e->ns_front.p, e->ns_pos.p, e->ns_keys.p,
                e->ns_cnt.p, d_offsets, d_order, P, W};
-    k_nsga_seed<<<(P + 255) / 256, 256, 0, st>>>(s);
+    k_nsga_seed<<<(P + 7) / 8, 256, 0, st>>>(s);
     e->launches += 4;
     CU(cudaGetLastError());
 

@@ -32,14 +32,19 @@ constexpr int kCrowdThreads = 1024;
 constexpr int kCrowdSmemItems = 14336;  // 16 B per front member; larger fronts use HBM scratch
 
 // ------------------------------------------------------------------ dominance bit matrix
-// dom[q*W + w] bit b  <=>  individual 32w+b dominates individual q;  count[q] += popcount.
-// Lane = candidate dominator, so one ballot is one word of the matrix.
+// dom[q*W + w] bit b  <=>  individual 32w+b dominates individual q.  W is the row stride in words,
+// a multiple of 8 (pad words stay zero).  Lane = candidate dominator, so one ballot is one word;
+// a CTA's 64 x 8 words are staged in shared memory and leave as full 32-byte sectors.
+// MT > 0: the number of objectives is a compile-time constant and the lane's own row lives in registers.
+template <int MT>
 __global__ void __launch_bounds__(kDomCand)
-k_nsga_dominators(const double* __restrict__ fit, int P, int M, int W, uint32_t* __restrict__ dom,
-                  int* __restrict__ count) {
+k_nsga_dominators(const double* __restrict__ fit, int P, int Mrt, int W, uint32_t* __restrict__ dom) {
+    const int M = MT > 0 ? MT : Mrt;
     extern __shared__ double nsga_sm[];
     double* sa = nsga_sm;                  // [M][kDomCand] candidates, objective-major
     double* sq = nsga_sm + M * kDomCand;   // [kDomRows][M]
+    __shared__ uint4 tile4[kDomRows * (kDomCand / 32) / 4];
+    uint32_t* tile = reinterpret_cast<uint32_t*>(tile4);
     const int tid = threadIdx.x, a0 = blockIdx.x * kDomCand, q0 = blockIdx.y * kDomRows;
     for (int i = tid; i < kDomCand * M; i += kDomCand) {
         const int a = i / M, m = i - a * M;
@@ -50,21 +55,34 @@ k_nsga_dominators(const double* __restrict__ fit, int P, int M, int W, uint32_t*
         sq[i] = q < P ? fit[(size_t)q * M + (i % M)] : 0.0;
     }
     __syncthreads();
-    const int a = a0 + tid, word = blockIdx.x * (kDomCand / 32) + (tid >> 5);
+    const int a = a0 + tid;
     const int rows = min(kDomRows, P - q0);
+    double xr[MT > 0 ? MT : 1];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) xr[m] = sa[m * kDomCand + tid];
     for (int r = 0; r < rows; ++r) {
         bool ge = a < P, gt = false;       // dominates(), :121-134, without the early exit
-        for (int m = 0; m < M; ++m) {
-            const double x = sa[m * kDomCand + tid], y = sq[r * M + m];
-            ge &= !(x < y);
-            gt |= x > y;
+        if (MT > 0) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const double y = sq[r * MT + m];
+                ge &= !(xr[m] < y);
+                gt |= xr[m] > y;
+            }
+        } else {
+            for (int m = 0; m < M; ++m) {
+                const double x = sa[m * kDomCand + tid], y = sq[r * M + m];
+                ge &= !(x < y);
+                gt |= x > y;
+            }
         }
         const unsigned b = __ballot_sync(0xffffffffu, ge & gt);
-        if ((tid & 31) == 0 && word < W) {
-            dom[(size_t)(q0 + r) * W + word] = b;
-            if (b) atomicAdd(count + q0 + r, __popc(b));
-        }
+        if ((tid & 31) == 0) tile[r * (kDomCand / 32) + (tid >> 5)] = b;
     }
+    __syncthreads();
+    if (tid < 2 * rows)   // two 16-byte halves per row
+        *reinterpret_cast<uint4*>(dom + (size_t)(q0 + (tid >> 1)) * W + blockIdx.x * (kDomCand / 32) +
+                                  (tid & 1) * 4) = tile4[tid];
 }
 
 // normalizeFitnesses :68-84: max starts at 0.0 and only a strictly greater value replaces it
@@ -112,13 +130,17 @@ struct NsgaPeel {
     int P, W;
 };
 
-// :26-35  front 0 = nobody dominates, in index order
+// :17-35  dominator counts (row popcounts); front 0 = nobody dominates, in index order
 __global__ void k_nsga_seed(NsgaPeel s) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (q >= s.P) return;
-    const bool first = s.count[q] == 0;
-    s.rank[q] = first ? 0 : -1;
-    if (first) s.keys[atomicAdd(s.cnt, 1)] = (unsigned long long)q;
+    int c = 0;
+    for (int w = lane; w < s.W; w += 32) c += __popc(__ldg(s.dom + (size_t)q * s.W + w));
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane) return;
+    s.count[q] = c;
+    s.rank[q] = c == 0 ? 0 : -1;
+    if (c == 0) s.keys[atomicAdd(s.cnt, 1)] = (unsigned long long)q;
 }
 
 // front t: rank the keys gathered by seed / peel(t-1)
@@ -139,8 +161,10 @@ __global__ void k_nsga_order(NsgaPeel s, int t) {
     atomicOr(s.front + (size_t)(t & 1) * s.W + (q >> 5), 1u << (q & 31));
 }
 
-// :41-49  one warp per unranked q
-__global__ void k_nsga_peel(NsgaPeel s, int t) {
+// :41-49  One warp per unranked row q: the row is ANDed with front t's membership mask 256 words at
+// a time (the loads of a chunk are issued together), popcount = dominators that just left.
+constexpr int kPeelRegs = 8;
+__global__ void __launch_bounds__(256) k_nsga_peel(NsgaPeel s, int t) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t* next = s.front + (size_t)((t + 1) & 1) * s.W;
     for (int w = gt; w < s.W; w += gridDim.x * blockDim.x) next[w] = 0u;
@@ -150,15 +174,22 @@ __global__ void k_nsga_peel(NsgaPeel s, int t) {
     const uint32_t* fr = s.front + (size_t)(t & 1) * s.W;
     const uint32_t* row = s.dom + (size_t)q * s.W;
     int hit = 0, mp = -1;
-    for (int w = lane; w < s.W; w += 32) {
-        const uint32_t f = __ldg(fr + w);
-        if (!f) continue;
-        uint32_t d = __ldg(row + w) & f;
-        hit += __popc(d);
-        while (d) {
-            const int b = __ffs(d) - 1;
-            d &= d - 1;
-            mp = max(mp, __ldg(s.pos + 32 * w + b));
+    for (int c0 = lane; c0 < s.W; c0 += 32 * kPeelRegs) {
+        uint32_t d[kPeelRegs];
+#pragma unroll
+        for (int k = 0; k < kPeelRegs; ++k) d[k] = c0 + 32 * k < s.W ? __ldg(fr + c0 + 32 * k) : 0u;
+#pragma unroll
+        for (int k = 0; k < kPeelRegs; ++k)
+            if (d[k]) d[k] &= __ldg(row + c0 + 32 * k);
+#pragma unroll
+        for (int k = 0; k < kPeelRegs; ++k) {
+            uint32_t v = d[k];
+            hit += __popc(v);
+            while (v) {
+                const int b = __ffs(v) - 1;
+                v &= v - 1;
+                mp = max(mp, __ldg(s.pos + 32 * (c0 + 32 * k) + b));
+            }
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
