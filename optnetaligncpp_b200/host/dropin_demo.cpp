@@ -118,6 +118,35 @@ int main(int argc, char** argv) {
         }
         Alignment probe(*alns[0]);
         printf("snd %.17g\n", swapNormalizedDelta(probe, names, 3, 7));
+        // partial alignments (no --total): random mask (shuf), mask flips (mutate), mask AND/OR
+        // (UPMX), onBit, and a climb over the masked state
+        auto report = [&](const char* tag, Alignment& a) {
+            a.computeFitness(names);
+            printf("%s cons %d ind %d bits %.17g goc %.17g size %.17g", tag, a.currConservedCount,
+                   a.currInducedCount, bit ? a.currBitscore : 0.0, goc ? a.currGOC : 0.0, a.alnSize());
+            for (double f : a.fitness) printf(" %.17g", f);
+            printf("\n");
+        };
+        vector<Alignment*> parts;
+        for (int t = 0; t < 2; t++) {
+            RandGenT g(seed + 5000 + t), m(seed + 6000 + t);
+            Alignment* a = new Alignment(net1, net2, bit, goc);
+            a->shuf(g, false, false, false);
+            report("pshuf", *a);
+            a->mutate(m, 0.01f, false);
+            report("pmut", *a);
+            parts.push_back(a);
+        }
+        RandGenT c(seed + 7000), h(seed + 8000);
+        Alignment child(c, 0.2f, *parts[0], *parts[1], false);
+        report("pcx", child);
+        int off = 0;
+        while (off < child.actualSize && child.alnMask[off]) off++;
+        child.onBit(off);
+        printf("pbit %d ", off);
+        report("pon", child);
+        correctHillClimb(h, &child, false, iters, names);
+        report("pclimb", child);
     } catch (exception& e) {
         cerr << "error: " << e.what() << endl;
         return 1;

@@ -87,6 +87,7 @@ def lib():
     L.ref_aln_conserved_count.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ref_aln_induced_count.argtypes = [vp, C.c_int, C.c_int]
     L.ref_aln_mutate.argtypes = [vp, C.c_uint32, C.c_float, C.c_int]
+    L.ref_aln_on_bit.argtypes = [vp, C.c_int]
     L.ref_aln_crossover.restype = vp
     L.ref_aln_crossover.argtypes = [C.c_uint32, C.c_float, vp, vp, C.c_int]
     L.ref_correct_hill_climb.argtypes = [vp, C.c_uint32, C.c_int, I32P, C.c_int, C.c_int]
@@ -261,6 +262,9 @@ class Aln:
 
     def induced_count(self, n2, ignore):
         return lib().ref_aln_induced_count(self.h, n2, ignore)
+
+    def on_bit(self, x):
+        lib().ref_aln_on_bit(self.h, int(x))
 
     def mutate(self, seed, mutswappb, total=True):
         lib().ref_aln_mutate(self.h, seed, mutswappb, int(total))

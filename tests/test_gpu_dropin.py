@@ -76,3 +76,33 @@ def test_dropin_matches_reference(with_goc):
     snd = climbed[0].swap_normalized_delta(names, 3, 7)
     got = float(lines[2 * nthreads + 1][1])
     assert got == snd or (np.isnan(got) and np.isnan(snd))
+
+    # partial alignments: integer counters exact; the fp64 accumulators of the mask-editing
+    # operators are re-based from two from-scratch evaluations: 1e-9 relative
+    rest = lines[2 * nthreads + 2:]
+
+    def check(row, tag, a):
+        assert row[0] == tag, row
+        c = a.counters()
+        assert (int(row[2]), int(row[4])) == (c[0], c[1]), (tag, row, c)
+        assert np.isclose(float(row[6]), c[2], rtol=1e-9, atol=0) and np.isclose(float(row[8]), c[3], rtol=1e-9, atol=0)
+        assert float(row[10]) == a.aln_size()
+        assert np.allclose([float(v) for v in row[11:]], a.compute_fitness(names), rtol=1e-9, atol=0)
+
+    parts = []
+    for t in range(2):
+        a = ref.Aln(n1, n2, B, G)
+        a.shuf(seed + 5000 + t, total=False)
+        check(rest[2 * t], "pshuf", a)
+        a.mutate(seed + 6000 + t, 0.01, False)
+        check(rest[2 * t + 1], "pmut", a)
+        parts.append(a)
+    child = ref.Aln.crossover(seed + 7000, 0.2, parts[0], parts[1], False)
+    check(rest[4], "pcx", child)
+    mask = child.state()[2]
+    off = int(np.argmin(mask[:pair.n1])) if not mask[:pair.n1].all() else pair.n1
+    assert rest[5][0] == "pbit" and int(rest[5][1]) == off
+    child.on_bit(off)
+    check(rest[5][2:], "pon", child)
+    child.correct_hill_climb(seed + 8000, iters, names)
+    check(rest[6], "pclimb", child)
