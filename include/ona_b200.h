@@ -220,6 +220,24 @@ int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters,
  * skipped (ragged lists).  Counters/accumulators are updated incrementally like doSwap. */
 int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* xy);
 
+/* Replaces: the variation operators' edits of PARTIAL alignments (no --total), which are not pure
+ * doSwap runs -- Alignment::mutate's mask flip (Alignment.cpp:468-480), Alignment::onBit
+ * (:522-533) and the UPMX step with its mask AND/OR (:197-252) -- replayed in order with the
+ * reference's own conservedCount / inducedCount / updateBitscore / updateGOC call pattern, so
+ * counters and fp64 accumulators match the reference bit for bit.
+ * ops is [count][nops][4] = {kind, a, b, c}; kind < 0: skipped (ragged lists).
+ *   ONA_EDIT_SWAP  (a = x, b = y)          doSwap(x, y), :491-520
+ *   ONA_EDIT_FLIP  (a = i)                 alnMask[i] = !alnMask[i] with mutate's updates
+ *   ONA_EDIT_ONBIT (a = x)                 onBit(x)
+ *   ONA_EDIT_CROSS (a = i, b = par2.aln[i], c = par2.alnMask[i] | coinFlip << 1 | total << 2)
+ *                                          position i takes parent 2's image, the displaced image
+ *                                          moves to where that image was (:197-252) */
+#define ONA_EDIT_SWAP 0
+#define ONA_EDIT_FLIP 1
+#define ONA_EDIT_ONBIT 2
+#define ONA_EDIT_CROSS 3
+int ona_apply_edits(ona_engine* e, int first, int count, int nops, const int* ops);
+
 /* -------------------------------------------------------------- device access */
 /* copy the [count][M] objective rows of slots first..first+count into a device buffer
  * (e.g. a torch tensor's data_ptr) on the engine's stream -- the send buffer of the

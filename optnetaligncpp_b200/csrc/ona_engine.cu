@@ -1101,6 +1101,24 @@ int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* 
     return finish_checked(e, "swap outside [0,n2)");
 }
 
+int ona_apply_edits(ona_engine* e, int first, int count, int nops, const int* ops) {
+    TRY(check_range(e, first, count));
+    if (!ops || nops < 0) return fail(ONA_ERR_INVALID, "null edit list");
+    if (count == 0 || nops == 0) return ONA_OK;
+    const size_t n = (size_t)count * nops;
+    LOCK(e);
+    CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
+    CU(e->t_xy.need(4 * n));
+    TRY(h2d(e, e->t_xy.p, ops, 4 * n));
+    k_apply_edits<<<count, 32, 0, e->stream>>>(e->g, e->S, e->G, e->pop, first, nops,
+                                               reinterpret_cast<const int4*>(e->t_xy.p), e->d_flag);
+    k_recount_size<<<count, 256, 0, e->stream>>>(e->g, e->pop, first, count);
+    k_refresh_fitness<<<(count + 127) / 128, 128, 0, e->stream>>>(e->g, e->ob, e->pop, first, count);
+    e->launches += 3;
+    CU(cudaGetLastError());
+    return finish_checked(e, "edit outside [0,n2) or unknown edit kind");
+}
+
 int ona_export_fitness_dev(ona_engine* e, int first, int count, double* dst_dev) {
     TRY(check_range(e, first, count));
     if (!dst_dev) return fail(ONA_ERR_INVALID, "null destination");

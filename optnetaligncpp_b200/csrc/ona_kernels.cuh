@@ -280,6 +280,147 @@ __global__ void k_recount_size(DevGraph g, DevPop pop, int first, int count) {
     (void)count;
 }
 
+// --------------------------------------------------------------------------------
+// Ordered edit lists of the variation operators that run right before the hot loop for every
+// child: doSwap (Alignment.cpp:491-520), the mask flip of mutate (:468-480),
+// onBit (:522-533) and one UPMX step with its mask AND/OR (:197-252).  One warp per individual
+// replays the list in order on the packed state in HBM, with the reference's own
+// conservedCount (:791-808) / inducedCount (:812-826) / updateBitscore / updateGOC (:745-786)
+// call pattern, so counters AND fp64 accumulators come out bit for bit.  A few dozen edits
+// per child: latency is irrelevant here, exactness is the point.
+constexpr int kEditSwap = 0, kEditFlip = 1, kEditOnBit = 2, kEditCross = 3;
+
+struct EditState {
+    uint32_t* aln;
+    uint32_t* inv;
+    int lane;
+    __device__ __forceinline__ bool mask(int u) const { return !(aln[u] & kGFlag); }
+    __device__ __forceinline__ int img(int u) const { return (int)(aln[u] & kGMask); }
+    __device__ __forceinline__ void set(int u, int v, bool m) const {  // lane 0 only
+        const uint32_t f = m ? 0u : kGFlag;
+        aln[u] = (uint32_t)v | f;
+        inv[v] = (uint32_t)u | f;
+    }
+};
+// :791-808, all lanes; result in every lane
+__device__ inline int edit_cons(const DevGraph& g, const EditState& st, int n1node, int n2node, bool mask,
+                                int ignore) {
+    if (!mask || n1node >= g.n1 || n1node == ignore) return 0;
+    int c = 0;
+    for (int k = __ldg(g.rp1 + n1node) + st.lane; k < __ldg(g.rp1 + n1node + 1); k += 32) {
+        const int i = __ldg(g.col1 + k);
+        const uint32_t r = st.aln[i];
+        if (i != ignore && !(r & kGFlag) && probe(g, n2node, (int)(r & kGMask))) ++c;
+    }
+    return warp_sum(c);
+}
+// :812-826
+__device__ inline int edit_ind(const DevGraph& g, const EditState& st, int n2node, int ignore) {
+    if (!(st.inv[n2node] < (uint32_t)g.n1)) return 0;  // dummy pre-image or mask bit off
+    int c = 0;
+    for (int k = __ldg(g.rp2 + n2node) + st.lane; k < __ldg(g.rp2 + n2node + 1); k += 32) {
+        const int x = __ldg(g.col2 + k);
+        if (st.inv[x] < (uint32_t)g.n1 && x != ignore) ++c;
+    }
+    return warp_sum(c);
+}
+// :745-786 (one table)
+__device__ __forceinline__ double edit_score(const DevGraph& g, const DevTable& t, int n1node, int n2old,
+                                             int n2new, bool oldMask, bool newMask) {
+    if (!t.kind || n1node >= g.n1) return 0.0;
+    const double o = oldMask ? table_lookup(t, n1node, n2old) : 0.0;
+    const double n = newMask ? table_lookup(t, n1node, n2new) : 0.0;
+    return n - o;
+}
+
+__global__ void __launch_bounds__(32)
+k_apply_edits(DevGraph g, DevTable S, DevTable Gt, DevPop pop, int first, int nops,
+              const int4* __restrict__ ops, int* __restrict__ err_flag) {
+    const int pl = blockIdx.x, p = first + pl, lane = threadIdx.x;
+    const EditState st{pop.aln + (size_t)p * pop.n2p, pop.inv + (size_t)p * pop.n2p, lane};
+    int C = pop.cons[p], I = pop.ind[p];
+    double bits = pop.bits[p], goc = pop.goc[p];
+    for (int o = 0; o < nops; ++o) {
+        const int4 op = __ldg(ops + (size_t)pl * nops + o);
+        if (op.x < 0) continue;  // ragged lists
+        const int kind = op.x;
+        if (kind > kEditCross || (unsigned)op.y >= (unsigned)g.n2 ||
+            ((kind == kEditSwap || kind == kEditCross) && (unsigned)op.z >= (unsigned)g.n2)) {
+            if (lane == 0) atomicOr(err_flag, 1);
+            continue;
+        }
+        if (kind == kEditSwap) {  // doSwap(x, y), :491-520
+            const int x = op.y, y = op.z;
+            const int ax = st.img(x), ay = st.img(y);
+            const bool mx = st.mask(x), my = st.mask(y);
+            const int oCx = edit_cons(g, st, x, ax, mx, -1), oCy = edit_cons(g, st, y, ay, my, x);
+            const int oIx = edit_ind(g, st, ax, -1), oIy = edit_ind(g, st, ay, ax);
+            __syncwarp();
+            if (lane == 0) {
+                st.set(x, ay, my);
+                st.set(y, ax, mx);
+            }
+            __syncwarp();
+            const int nCx = edit_cons(g, st, x, ay, my, -1), nCy = edit_cons(g, st, y, ax, mx, x);
+            const int nIx = edit_ind(g, st, ax, -1), nIy = edit_ind(g, st, ay, ax);
+            bits += edit_score(g, S, x, ax, ay, mx, my);
+            goc += edit_score(g, Gt, x, ax, ay, mx, my);
+            bits += edit_score(g, S, y, ay, ax, my, mx);
+            goc += edit_score(g, Gt, y, ay, ax, my, mx);
+            C += (nCx - oCx) + (nCy - oCy);
+            I += (nIx - oIx) + (nIy - oIy);
+        } else if (kind == kEditFlip || kind == kEditOnBit) {  // :468-480 / :522-533
+            const int i = op.y, ai = st.img(i);
+            const bool old = st.mask(i), nw = kind == kEditOnBit ? true : !old;
+            const int oC = edit_cons(g, st, i, ai, old, -1), oI = edit_ind(g, st, ai, -1);
+            __syncwarp();
+            if (lane == 0) st.set(i, ai, nw);
+            __syncwarp();
+            const int nC = edit_cons(g, st, i, ai, nw, -1), nI = edit_ind(g, st, ai, -1);
+            bits += edit_score(g, S, i, ai, ai, old, nw);
+            goc += edit_score(g, Gt, i, ai, ai, old, nw);
+            C += nC - oC;
+            I += nI - oI;
+        } else {  // one UPMX step, :197-252: position i takes image `want`, the displaced image
+                  // moves to where `want` was; op.w bit 0 = parent 2's mask bit, bit 1 = the coin,
+                  // bit 2 = --total (mask bits stay where they are)
+            const int i = op.y, temp2 = op.z, temp1 = st.img(i);
+            const int j = (int)(st.inv[temp2] & kGMask);
+            const bool temp1Mask = st.mask(i), par1bool = st.mask(j);
+            const bool par2bool = (op.w & 1) != 0, coin = (op.w & 2) != 0, total = (op.w & 4) != 0;
+            const int oCi = edit_cons(g, st, i, temp1, temp1Mask, -1), oCj = edit_cons(g, st, j, temp2, par1bool, i);
+            const int oIi = edit_ind(g, st, temp1, -1), oIj = edit_ind(g, st, temp2, temp1);
+            bool maskI = temp1Mask, maskJ = par1bool;
+            if (!total) {
+                maskJ = temp1Mask;
+                maskI = coin ? (par1bool && par2bool) : (par1bool || par2bool);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (i == j) {
+                    st.set(i, temp1, maskI);   // :223-228 write alnMask[j] first, then alnMask[i]
+                } else {
+                    st.set(i, temp2, maskI);
+                    st.set(j, temp1, maskJ);
+                }
+            }
+            __syncwarp();
+            const int nCi = edit_cons(g, st, i, st.img(i), st.mask(i), -1);
+            const int nCj = edit_cons(g, st, j, st.img(j), st.mask(j), i);
+            const int nIi = edit_ind(g, st, st.img(j), -1), nIj = edit_ind(g, st, st.img(i), st.img(j));
+            bits += edit_score(g, S, i, temp1, temp2, temp1Mask, st.mask(i));
+            goc += edit_score(g, Gt, i, temp1, temp2, temp1Mask, st.mask(i));
+            bits += edit_score(g, S, j, temp2, temp1, par1bool, st.mask(j));
+            goc += edit_score(g, Gt, j, temp2, temp1, par1bool, st.mask(j));
+            C += (nCi - oCi) + (nCj - oCj);
+            I += (nIi - oIi) + (nIj - oIj);
+        }
+    }
+    if (lane == 0) {
+        pop.cons[p] = C; pop.ind[p] = I; pop.bits[p] = bits; pop.goc[p] = goc;
+    }
+}
+
 // per-individual summaries of the swap-delta kernel (null = not wanted)
 struct DeltaSummary {
     int* num_improved;    // [count] (atomic)

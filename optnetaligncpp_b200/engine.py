@@ -24,8 +24,11 @@ EXPORTS = [
     "ona_set_island_offset", "ona_set_objectives", "ona_pop_resize", "ona_pop_upload", "ona_pop_download",
     "ona_pop_set_counters", "ona_pop_get_counters", "ona_full_fitness", "ona_full_fitness_dev",
     "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_steepest_step", "ona_rng_proposals", "ona_hill_climb", "ona_hill_climb_batched",
-    "ona_apply_swaps", "ona_export_fitness_dev", "ona_nsga2_rank", "ona_nsga2_rank_dev",
+    "ona_apply_swaps", "ona_apply_edits", "ona_export_fitness_dev", "ona_nsga2_rank", "ona_nsga2_rank_dev",
 ]
+
+
+EDIT_SWAP, EDIT_FLIP, EDIT_ONBIT, EDIT_CROSS = 0, 1, 2, 3
 
 
 class OnaError(RuntimeError):
@@ -95,6 +98,7 @@ def load_library(build_if_missing=True):
     L.ona_hill_climb_batched.argtypes = [vp, ci, ci, ll, vp, C.c_ulonglong, vp, vp]
     L.ona_apply_swaps.argtypes = [vp, ci, ci, ci, vp]
     L.ona_export_fitness_dev.argtypes = [vp, ci, ci, vp]
+    L.ona_apply_edits.argtypes = [vp, ci, ci, ci, vp]
     L.ona_nsga2_rank.argtypes = [vp, ci, ci] + [vp] * 9
     L.ona_nsga2_rank_dev.argtypes = [vp, ci, ci] + [vp] * 9
     _LIB = L
@@ -334,6 +338,12 @@ class Engine:
     def apply_swaps(self, xy, first=0):
         xy = _i32(xy)
         self._check(self.L.ona_apply_swaps(self.h, first, xy.shape[0], xy.shape[1], _ptr(xy)))
+
+    def apply_edits(self, ops, first=0):
+        """ops [count, nops, 4] int32 = (kind, a, b, c): EDIT_SWAP / EDIT_FLIP / EDIT_ONBIT /
+        EDIT_CROSS, see include/ona_b200.h (Alignment.cpp:197-252, :468-480, :491-533)."""
+        ops = _i32(ops)
+        self._check(self.L.ona_apply_edits(self.h, first, ops.shape[0], ops.shape[1], _ptr(ops)))
 
     def export_fitness_dev(self, dst_ptr, first=0, count=None):
         count = self.P - first if count is None else count

@@ -26,27 +26,6 @@ void init_bookkeeping(Alignment& a) {
     a.crowdDist = -1.0;
 }
 
-// counters of a state reached by host-side edits of permutation/mask (non --total operators):
-// the reference updates its counters incrementally, i.e. new = old + (exact change).  The
-// exact change is the difference of two from-scratch GPU evaluations, which keeps any
-// inherited seed offset; fp64 accumulators agree to <= 1e-9 relative.
-struct Before {
-    ona_host::Scratch s;
-    int cons, ind;
-    double bits, goc;
-};
-Before snapshot(const Alignment& a) {
-    Before b{ona_host::score_from_scratch(a), a.currConservedCount, a.currInducedCount, a.currBitscore, a.currGOC};
-    return b;
-}
-void rebase(Alignment& a, const Before& b) {
-    const ona_host::Scratch s = ona_host::score_from_scratch(a);
-    a.currConservedCount = b.cons + (s.cons_true - b.s.cons_true);
-    a.currInducedCount = b.ind + (s.induced - b.s.induced);
-    if (a.bitscores) a.currBitscore = b.bits + (s.bits - b.s.bits);
-    if (a.gocs) a.currGOC = b.goc + (s.goc - b.s.goc);
-}
-
 // assign every still-unaligned position an arbitrary unaligned V2 node and mask it off
 // (Alignment.cpp:116-127 / 321-330); iteration order of the unordered_set is the reference's
 void fill_unaligned(Alignment& a, unordered_set<node>& v2Unaligned) {
@@ -145,18 +124,18 @@ Alignment::Alignment(RandGenT& prng, float cxswappb, const Alignment& p1, const 
         ona_host::apply_swaps(*this, swaps);
     } else {
         // partial alignments: the mask of the swapped-in position becomes parent1 AND/OR parent2
-        // (:219-227), which is not a pure doSwap; edit on the host, re-base the counters
-        const Before b = snapshot(*this);
+        // (:219-227), which is not a pure doSwap.  The PRNG draws do not depend on the running
+        // state, so the ordered step list is drawn here and replayed on the GPU (ONA_EDIT_CROSS).
+        vector<int> ops;
         for (int i = 0; i < size; i++) {
             if (!(fltgen(prng) < cxswappb)) continue;
-            const node want = par2->aln[i], j = alnInv[want], have = aln[i];
-            const bool maskI = alnMask[i], maskJ = alnMask[j], mask2 = par2->alnMask[i];
-            aln[i] = want; alnInv[want] = i;
-            aln[j] = have; alnInv[have] = j;
-            alnMask[j] = maskI;
-            alnMask[i] = coinFlip(prng) ? (maskJ && mask2) : (maskJ || mask2);
+            const int coin = coinFlip(prng);
+            ops.push_back(ONA_EDIT_CROSS);
+            ops.push_back(i);
+            ops.push_back(par2->aln[i]);
+            ops.push_back((par2->alnMask[i] ? 1 : 0) | (coin ? 2 : 0));
         }
-        rebase(*this, b);
+        ona_host::apply_edits(*this, ops);
     }
     fitnessValid = false;
 }
@@ -248,21 +227,16 @@ void Alignment::mutate(RandGenT& prng, float mutswappb, bool total) {
         }
         ona_host::apply_swaps(*this, swaps);
     } else {
-        const Before b = snapshot(*this);
+        vector<int> ops;
         for (int i = 0; i < size; i++) {
             if (fltgen(prng) < mutswappb) {
                 int other = intgen(prng);
                 if (other >= i) other++;
-                const node ai = aln[i], ao = aln[other];
-                aln[i] = ao; alnInv[ao] = i;
-                aln[other] = ai; alnInv[ai] = other;
-                const bool t = alnMask[i];
-                alnMask[i] = alnMask[other];
-                alnMask[other] = t;
+                ops.insert(ops.end(), {ONA_EDIT_SWAP, i, other, 0});
             }
-            if (fltgen(prng) < mutswappb) alnMask[i] = !alnMask[i];
+            if (fltgen(prng) < mutswappb) ops.insert(ops.end(), {ONA_EDIT_FLIP, i, 0, 0});
         }
-        rebase(*this, b);
+        ona_host::apply_edits(*this, ops);
     }
     fitnessValid = false;
 }
@@ -271,12 +245,7 @@ void Alignment::mutate(RandGenT& prng, float mutswappb, bool total) {
 void Alignment::doSwap(node x, node y) { ona_host::apply_swaps(*this, vector<int>{x, y}); }
 
 // Alignment.cpp:522-533
-void Alignment::onBit(node x) {
-    if (alnMask[x]) return;  // the reference recomputes and adds zero
-    const Before b = snapshot(*this);
-    alnMask[x] = true;
-    rebase(*this, b);
-}
+void Alignment::onBit(node x) { ona_host::apply_edits(*this, vector<int>{ONA_EDIT_ONBIT, x, 0, 0}); }
 
 // Alignment.cpp:535-556, 693-699 -- objectives from the cached counters
 double Alignment::fastEC() const { return double(currConservedCount) / double(net1->edges.size()); }

@@ -160,6 +160,16 @@ void apply_swaps(Alignment& a, const std::vector<int>& xy) {
     c.download(one);
 }
 
+void apply_edits(Alignment& a, const std::vector<int>& ops) {
+    if (ops.empty()) return;
+    Context& c = context_for(a);
+    std::lock_guard<std::mutex> lk(c.lock());
+    std::vector<Alignment*> one{&a};
+    c.upload(one);
+    check(ona_apply_edits(c.engine(), 0, 1, (int)(ops.size() / 4), ops.data()));
+    c.download(one);
+}
+
 std::vector<std::vector<Alignment*> > rankGeneration(const std::vector<Alignment*>& in, bool crowding) {
     std::vector<std::vector<Alignment*> > fronts(1);  // nsga-ii.cpp:16: there is always a front 0
     if (in.empty()) return fronts;

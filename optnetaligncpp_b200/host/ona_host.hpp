@@ -71,6 +71,9 @@ Scratch score_from_scratch(const Alignment& a);
 void seed_counters(Alignment& a);
 // apply an ordered list of doSwap(x,y) to `a` on the GPU (incremental counter updates)
 void apply_swaps(Alignment& a, const std::vector<int>& xy);
+// apply an ordered list of {kind, a, b, c} edits (ONA_EDIT_*: doSwap, mask flip, onBit, UPMX step
+// with mask AND/OR) to `a` on the GPU -- the partial-alignment operators, bit for bit
+void apply_edits(Alignment& a, const std::vector<int>& ops);
 
 
 // nsgaiimain.cpp:157-175 as ONE engine call (ona_nsga2_rank): nonDominatedSort(in)

@@ -259,6 +259,61 @@ void orc_do_swap(OrcAln* a, int x, int y) {
     a->ind += ((newInducedX - oldInducedX) + (newInducedY - oldInducedY));
 }
 
+/* Ordered edit lists of the variation operators (ops [nops][4] = kind, a, b, c; kind < 0 skipped):
+ *   0 doSwap(a, b)                              Alignment.cpp:491-520
+ *   1 mutate's mask flip at a                   :468-480
+ *   2 onBit(a)                                  :522-533
+ *   3 one UPMX step: position a takes image b (= par2->aln[a]); c bit0 = par2->alnMask[a],
+ *     bit1 = the coin flip, bit2 = --total      :197-252
+ * Same statement order as the reference, so the fp64 accumulators follow the same sequence. */
+void orc_apply_edits(OrcAln* a, const int* ops, int nops) {
+    const OrcProblem* p = a->p;
+    for (int o = 0; o < nops; ++o) {
+        const int kind = ops[4 * o], u = ops[4 * o + 1], v = ops[4 * o + 2], w = ops[4 * o + 3];
+        if (kind < 0) continue;
+        if (kind == 0) {
+            orc_do_swap(a, u, v);
+        } else if (kind == 1 || kind == 2) {
+            const int i = u;
+            int oldConserved = orc_conserved_count(a, i, a->aln[i], a->mask[i], -1);
+            int oldInduced = orc_induced_count(a, a->aln[i], -1);
+            const uint8_t old = a->mask[i];
+            a->mask[i] = kind == 2 ? 1 : !old;
+            int newConserved = orc_conserved_count(a, i, a->aln[i], a->mask[i], -1);
+            int newInduced = orc_induced_count(a, a->aln[i], -1);
+            update_score(p, p->S, &a->bits, i, a->aln[i], a->aln[i], old, a->mask[i]);
+            update_score(p, p->G, &a->goc, i, a->aln[i], a->aln[i], old, a->mask[i]);
+            a->cons += (newConserved - oldConserved);
+            a->ind += (newInduced - oldInduced);
+        } else {
+            const int i = u, temp1 = a->aln[i], temp2 = v, j = a->alnInv[temp2];
+            int oldConservedI = orc_conserved_count(a, i, a->aln[i], a->mask[i], -1);
+            int oldConservedJ = orc_conserved_count(a, j, a->aln[j], a->mask[j], i);
+            int oldInducedI = orc_induced_count(a, a->aln[i], -1);
+            int oldInducedJ = orc_induced_count(a, a->aln[j], a->aln[i]);
+            a->aln[i] = temp2;
+            a->alnInv[temp2] = i;
+            a->aln[j] = temp1;
+            a->alnInv[temp1] = j;
+            const uint8_t temp1Mask = a->mask[i], par1bool = a->mask[j], par2bool = (uint8_t)(w & 1);
+            if (!(w & 4)) {
+                a->mask[j] = temp1Mask;
+                a->mask[i] = (w & 2) ? (par1bool && par2bool) : (par1bool || par2bool);
+            }
+            int newConservedI = orc_conserved_count(a, i, a->aln[i], a->mask[i], -1);
+            int newConservedJ = orc_conserved_count(a, j, a->aln[j], a->mask[j], i);
+            int newInducedI = orc_induced_count(a, a->aln[j], -1);
+            int newInducedJ = orc_induced_count(a, a->aln[i], a->aln[j]);
+            update_score(p, p->S, &a->bits, i, temp1, temp2, temp1Mask, a->mask[i]);
+            update_score(p, p->G, &a->goc, i, temp1, temp2, temp1Mask, a->mask[i]);
+            update_score(p, p->S, &a->bits, j, temp2, temp1, par1bool, a->mask[j]);
+            update_score(p, p->G, &a->goc, j, temp2, temp1, par1bool, a->mask[j]);
+            a->cons += ((newConservedI - oldConservedI) + (newConservedJ - oldConservedJ));
+            a->ind += ((newInducedI - oldInducedI) + (newInducedJ - oldInducedJ));
+        }
+    }
+}
+
 /* Alignment.cpp:693-699 */
 static double fast_ics(const OrcAln* a) {
     double denom = (double)a->ind;

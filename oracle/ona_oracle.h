@@ -60,6 +60,9 @@ int orc_conserved_count(const OrcAln*, int n1, int n2, int mask, int ignore); /*
 int orc_induced_count(const OrcAln*, int n2, int ignore);                     /* :812-826 */
 void orc_do_swap(OrcAln*, int x, int y);                                      /* :491-520 */
 void orc_compute_fitness(OrcAln*, const int* names, int M, double* out);      /* :559-602 */
+/* ordered {kind,a,b,c} edits: doSwap / mutate's mask flip :468-480 / onBit :522-533 / UPMX step
+ * :197-252 (see ona_oracle.c) */
+void orc_apply_edits(OrcAln*, const int* ops, int nops);
 
 /* localSearch.cpp */
 void orc_hill_climb_replay(OrcAln*, const int* xy, long iters, const int* names, int M, int obj,

@@ -66,6 +66,7 @@ def lib():
     L.orc_time_hill_climb.argtypes = [vp, C.c_int, I32P, C.c_long, I32P, C.c_int, C.c_int, C.c_int]
     L.orc_time_full_fitness.restype = C.c_double
     L.orc_time_full_fitness.argtypes = [vp, C.c_int, I32P, C.c_int, C.c_long, C.c_int, vp]
+    L.orc_apply_edits.argtypes = [vp, I32P, C.c_int]
     L.orc_nsga2.restype = C.c_int
     L.orc_nsga2.argtypes = [C.c_int, C.c_int] + [vp] * 9
     L.orc_dominates.restype = C.c_int
@@ -157,6 +158,10 @@ class Aln:
 
     def do_swap(self, x, y):
         lib().orc_do_swap(self.h, int(x), int(y))
+
+    def apply_edits(self, ops):
+        ops = _i32(ops).reshape(-1, 4)
+        lib().orc_apply_edits(self.h, ops.reshape(-1), len(ops))
 
     def compute_fitness(self, names):
         names = _i32(names)

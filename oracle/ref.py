@@ -88,6 +88,10 @@ def lib():
     L.ref_aln_induced_count.argtypes = [vp, C.c_int, C.c_int]
     L.ref_aln_mutate.argtypes = [vp, C.c_uint32, C.c_float, C.c_int]
     L.ref_aln_on_bit.argtypes = [vp, C.c_int]
+    L.ref_gen_mutate_ops.restype = C.c_int
+    L.ref_gen_mutate_ops.argtypes = [C.c_uint32, C.c_int, C.c_float, C.c_int, vp, C.c_int]
+    L.ref_gen_cross_draws.restype = C.c_int
+    L.ref_gen_cross_draws.argtypes = [C.c_uint32, C.c_int, C.c_float, C.c_int, vp, vp, C.c_int]
     L.ref_aln_crossover.restype = vp
     L.ref_aln_crossover.argtypes = [C.c_uint32, C.c_float, vp, vp, C.c_int]
     L.ref_correct_hill_climb.argtypes = [vp, C.c_uint32, C.c_int, I32P, C.c_int, C.c_int]
@@ -300,6 +304,28 @@ class Aln:
                                      _opt(r["bits"]), _opt(r["goc"]), _opt(r["fit"]),
                                      _opt(r["improved"]), _opt(r["snd"]))
         return r
+
+
+def gen_mutate_ops(seed, size, mutswappb, total):
+    """the edit list Alignment::mutate(mt19937(seed), mutswappb, total) performs (Alignment.cpp:451-480)"""
+    ops = np.zeros((2 * size, 4), np.int32)
+    n = lib().ref_gen_mutate_ops(seed, size, mutswappb, int(total), ops.ctypes.data, len(ops))
+    return ops[:n].copy()
+
+
+def gen_cross_ops(seed, cxswappb, p1_state, p2_state, total):
+    """(primary parent is p1?, edit list) of the UPMX constructor Alignment(mt19937(seed), cxswappb,
+    p1, p2, total) (Alignment.cpp:152-256); p?_state = (aln, mask) arrays of the two parents."""
+    size = len(p1_state[0])
+    first, sel = C.c_int(0), np.zeros((size, 2), np.int32)
+    n = lib().ref_gen_cross_draws(seed, size, cxswappb, int(total), C.addressof(first), sel.ctypes.data, size)
+    par2 = p2_state if first.value else p1_state
+    ops = np.zeros((n, 4), np.int32)
+    ops[:, 0] = 3
+    ops[:, 1] = sel[:n, 0]
+    ops[:, 2] = np.asarray(par2[0])[sel[:n, 0]]
+    ops[:, 3] = (np.asarray(par2[1])[sel[:n, 0]] != 0) | (sel[:n, 1] << 1) | (4 if total else 0)
+    return bool(first.value), ops
 
 
 def gen_xy_stream(seed, n1, n2, iters):

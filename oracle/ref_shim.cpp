@@ -218,6 +218,49 @@ void* ref_aln_crossover(uint32_t seed, float cxswappb, void* p1, void* p2, int t
                          total != 0);
 }
 
+// The PRNG draws of Alignment::mutate (Alignment.cpp:451-466) and of the UPMX constructor
+// (:159-166, :197-198, :223) restated, like ref_gen_xy_stream, so that the very same edit list can
+// be fed to the GPU: they depend on the generator only, never on the alignment.  Tests pin them
+// by comparing the replayed list against the real mutate / constructor.
+//   ops: [cap][4] = {kind, a, b, c} as include/ona_b200.h (ONA_EDIT_*); returns the count.
+int ref_gen_mutate_ops(uint32_t seed, int size, float mutswappb, int total, int* ops, int cap) {
+    RandGenT prng(seed);
+    std::uniform_real_distribution<float> fltgen(0.0, 1.0);
+    std::uniform_int_distribution<int> intgen(0, size - 2);
+    int n = 0;
+    for (int i = 0; i < size; i++) {
+        if (fltgen(prng) < mutswappb) {
+            int swapIndex = intgen(prng);
+            if (swapIndex >= i) swapIndex++;
+            if (n < cap) { ops[4 * n] = 0; ops[4 * n + 1] = i; ops[4 * n + 2] = swapIndex; ops[4 * n + 3] = 0; }
+            n++;
+        }
+        if (!total && fltgen(prng) < mutswappb) {
+            if (n < cap) { ops[4 * n] = 1; ops[4 * n + 1] = i; ops[4 * n + 2] = 0; ops[4 * n + 3] = 0; }
+            n++;
+        }
+    }
+    return n;
+}
+// first_is_p1: whether the constructor's first coin made p1 the primary parent;  sel: [cap][2] =
+// {i, coin (0 under --total)} for every index the crossover touches.
+int ref_gen_cross_draws(uint32_t seed, int size, float cxswappb, int total, int* first_is_p1, int* sel,
+                        int cap) {
+    RandGenT prng(seed);
+    std::uniform_int_distribution<int> coinFlip(0, 1);
+    std::uniform_real_distribution<float> fltgen(0.0, 1.0);
+    *first_is_p1 = coinFlip(prng) ? 1 : 0;
+    int n = 0;
+    for (int i = 0; i < size; i++) {
+        if (fltgen(prng) < cxswappb) {
+            const int coin = total ? 0 : coinFlip(prng);
+            if (n < cap) { sel[2 * n] = i; sel[2 * n + 1] = coin; }
+            n++;
+        }
+    }
+    return n;
+}
+
 // ------------------------------------------------------------ local search
 // the real thing: correctHillClimb with mt19937(seed)  (localSearch.cpp:18-55)
 void ref_correct_hill_climb(void* av, uint32_t seed, int iters, const int* names, int M, int obj) {

@@ -30,6 +30,11 @@ def nsga_golden():
     return dict(np.load(os.path.join(GOLDEN, "nsga2.npz")))
 
 
+@pytest.fixture(scope="session")
+def edits_golden():
+    return dict(np.load(os.path.join(GOLDEN, "edits.npz")))
+
+
 def dense_from_coo(n1, n2, r, c, v):
     S = np.zeros((n1, n2), np.float64)
     S[r, c] = v

@@ -17,6 +17,10 @@ Outputs
                      results of the compiled reference on the seeded matrices of
                      tests/nsga_cases.py:GOLDEN_CASES, plus the two known-answer cases of the
                      reference's own suite (tests.cpp:355-437).
+  edits.npz          partial-alignment variation operators on the small pair: the edit lists that
+                     Alignment::mutate / the UPMX constructor / onBit perform for given seeds
+                     (Alignment.cpp:152-256, :451-486, :522-533) and the reference's state, counters
+                     and fp64 accumulators afterwards (network arrays: small_pair.npz).
 Nothing here is read at test time except the .npz files.
 """
 import os
@@ -163,6 +167,48 @@ def small_pair():
     print("small_pair.npz written", ctr)
 
 
+def edits():
+    pair = synth.make_pair(n1=120, n2=150, m1=500, m2=560, max_deg=30, seed=synth.DEFAULT_SEED + 9,
+                           annotations=True, n_terms=60, terms_per_node=5, bit_density=0.01,
+                           bit_decimals=True)
+    d = tempfile.mkdtemp()
+    paths = synth.write_text(pair, os.path.join(d, "s"))
+    n1, n2 = ref.Net(paths["net1"]), ref.Net(paths["net2"])
+    B = ref.Dict.load_blast(n1, n2, paths["sim"])
+    G = ref.Dict.load_goc(n1, n2, paths["annos1"], paths["annos2"])
+    out = {}
+
+    def put(tag, a):
+        al, _, m = a.state()
+        out[tag + "_aln"], out[tag + "_mask"], out[tag + "_counters"] = al, m, np.array(a.counters())
+
+    for c, total in enumerate([False, False, True]):
+        a = ref.Aln(n1, n2, B, G)
+        a.shuf(2 + c, total=total)
+        b = ref.Aln(n1, n2, B, G)
+        b.shuf(12 + c, total=total)
+        put("c%d_start" % c, a)
+        put("c%d_other" % c, b)
+        out["c%d_mutate_ops" % c] = ref.gen_mutate_ops(20 + c, n2.n, 0.05, total)
+        a.mutate(20 + c, 0.05, total)
+        put("c%d_mutated" % c, a)
+        first, cops = ref.gen_cross_ops(30 + c, 0.25, (a.state()[0], a.state()[2]),
+                                        (b.state()[0], b.state()[2]), total)
+        child = ref.Aln.crossover(30 + c, 0.25, a, b, total)
+        out["c%d_cross_first" % c] = np.array(int(first))
+        out["c%d_cross_ops" % c] = cops
+        put("c%d_child" % c, child)
+        m = child.state()[2]
+        xs = np.array(list(np.flatnonzero(m == 0)[:4]) + [0, n2.n - 1], np.int32)
+        for x in xs:
+            child.on_bit(int(x))
+        out["c%d_onbit_x" % c] = xs
+        put("c%d_onbit" % c, child)
+    np.savez_compressed(os.path.join(OUT, "edits.npz"), **out)
+    print("edits.npz written;", [len(out["c%d_cross_ops" % c]) for c in range(3)], "UPMX steps,",
+          [len(out["c%d_mutate_ops" % c]) for c in range(3)], "mutate edits")
+
+
 def nsga2():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import nsga_cases
@@ -189,5 +235,6 @@ def nsga2():
 if __name__ == "__main__":
     assert ref.available(), "build oracle/_ref first (make -C oracle)"
     nsga2()
+    edits()
     small_pair()
     example_pair()

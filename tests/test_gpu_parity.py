@@ -533,3 +533,68 @@ def test_goc_table_built_on_device_from_term_sets(mid):
     assert np.array_equal(a0, a1) and np.array_equal(c0["goc"], c1["goc"])
     for p in range(P):
         assert r1["goc"][p] == port.Aln(prob, aln[p]).counters()[3]
+
+
+# ------------------------------------------------------------------ edit lists (partial operators)
+class _EngineObj:
+    def __init__(self, e, aln, mask, ctr):
+        self.e = e
+        e.upload(aln[None], mask[None])
+        e.set_counters([int(ctr[0])], [int(ctr[1])], [float(ctr[2])], [float(ctr[3])])
+
+    def apply_edits(self, ops):
+        self.e.apply_edits(np.asarray(ops, np.int32).reshape(1, -1, 4))
+
+    def snapshot(self):
+        a, _, m = self.e.download()
+        c = self.e.counters()
+        return a[0], m[0], (int(c["cons"][0]), int(c["ind"][0]), float(c["bits"][0]), float(c["goc"][0]))
+
+
+@pytest.mark.parametrize("c", [0, 1, 2])
+def test_edit_lists_golden(edits_golden, small_golden, c):
+    """ona_apply_edits: mutate's mask flips, UPMX with mask AND/OR, onBit -- permutation, mask,
+    integer counters and fp64 accumulators exactly as the reference left them."""
+    from test_oracle_golden import replay_edits_golden
+    g = small_golden
+    e = engine_for_golden(g, ALL, g["S"], g["G"])
+    replay_edits_golden(edits_golden, lambda aln, mask, ctr: _EngineObj(e, aln, mask, ctr), c)
+
+
+def test_edit_lists_random_against_oracle():
+    """random mixed edit lists (self-loops, dummy positions, i == j UPMX steps, ragged rows) on a
+    batch of partial individuals, against orc_apply_edits; objectives refreshed from the result."""
+    pair = synth.make_pair(n1=300, n2=380, m1=1500, m2=1700, max_deg=60, seed=5, loop_frac=0.08,
+                           annotations=True, n_terms=120, bit_density=0.02)
+    S, G = synth.dense_bits(pair), synth.dense_goc(pair)
+    prob = port.Problem(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2, S, G)
+    e = engine.Engine.from_pair(pair, ALL, use_goc=True, goc_dense=G)
+    rng = np.random.default_rng(3)
+    P, nops = 12, 90
+    aln, _ = synth.random_population(pair, P, seed=9)
+    mask = (rng.random((P, pair.n2)) < 0.8).astype(np.uint8)
+    e.upload(aln, mask)
+    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL)
+    c0 = e.counters()
+    ops = np.zeros((P, nops, 4), np.int32)
+    ops[..., 0] = rng.integers(-1, 4, (P, nops))
+    ops[..., 1] = rng.integers(0, pair.n2, (P, nops))
+    ops[..., 2] = rng.integers(0, pair.n2, (P, nops))
+    ops[..., 3] = rng.integers(0, 8, (P, nops))
+    same = rng.random((P, nops)) < 0.1           # UPMX step whose wanted image is already there
+    ops[..., 2] = np.where(same & (ops[..., 0] == 3), aln[np.arange(P)[:, None], ops[..., 1]], ops[..., 2])
+    e.apply_edits(ops)
+    a, inv, m = e.download()
+    c1 = e.counters()
+    for p in range(P):
+        o = port.Aln(prob, aln[p], mask[p])
+        o.set_counters(int(c0["cons"][p]), int(c0["ind"][p]), float(c0["bits"][p]), float(c0["goc"][p]))
+        o.apply_edits(ops[p])
+        oa, oi, om = o.state()
+        assert np.array_equal(a[p], oa) and np.array_equal(inv[p], oi) and np.array_equal(m[p], om), p
+        assert (int(c1["cons"][p]), int(c1["ind"][p]), float(c1["bits"][p]), float(c1["goc"][p])) == o.counters(), p
+        assert np.array_equal(c1["fit"][p], o.compute_fitness(ALL), equal_nan=True), p
+    with pytest.raises(engine.OnaError):
+        e.apply_edits(np.array([[[7, 0, 0, 0]]], np.int32))
+    with pytest.raises(engine.OnaError):
+        e.apply_edits(np.array([[[0, 0, pair.n2, 0]]], np.int32))

@@ -99,6 +99,43 @@ def test_refseed_truncation_hazard():
     assert port.lib().orc_refseed_conserved(5, 0) == 0
 
 
+# ------------------------------------------------------------------ variation operators' edit lists
+def replay_edits_golden(g, make, c):
+    """shared by the oracle test here and the GPU test: `make(aln, mask, counters)` returns an
+    object with apply_edits(ops) and snapshot() -> (aln, mask, counters)"""
+    def check(obj, tag):
+        al, m, ctr = obj.snapshot()
+        assert np.array_equal(al, g[tag + "_aln"]) and np.array_equal(m, g[tag + "_mask"]), tag
+        assert tuple(ctr) == tuple(g[tag + "_counters"]), (tag, ctr, g[tag + "_counters"])
+    a = make(g["c%d_start_aln" % c], g["c%d_start_mask" % c], g["c%d_start_counters" % c])
+    a.apply_edits(g["c%d_mutate_ops" % c])
+    check(a, "c%d_mutated" % c)
+    src = "c%d_mutated" % c if int(g["c%d_cross_first" % c]) else "c%d_other" % c
+    child = make(g[src + "_aln"], g[src + "_mask"], g[src + "_counters"])
+    child.apply_edits(g["c%d_cross_ops" % c])
+    check(child, "c%d_child" % c)
+    child.apply_edits([[2, int(x), 0, 0] for x in g["c%d_onbit_x" % c]])
+    check(child, "c%d_onbit" % c)
+
+
+@pytest.mark.parametrize("c", [0, 1, 2])
+def test_edit_lists_golden(edits_golden, small_problem, c):
+    """mutate with mask flips, UPMX with mask AND/OR, onBit (Alignment.cpp:152-256, :451-486,
+    :522-533): state, integer counters and fp64 accumulators exactly as the reference left them."""
+    class Obj:
+        def __init__(self, aln, mask, ctr):
+            self.a = port.Aln(small_problem, aln, mask)
+            self.a.set_counters(int(ctr[0]), int(ctr[1]), float(ctr[2]), float(ctr[3]))
+
+        def apply_edits(self, ops):
+            self.a.apply_edits(ops)
+
+        def snapshot(self):
+            al, _, m = self.a.state()
+            return al, m, self.a.counters()
+    replay_edits_golden(edits_golden, Obj, c)
+
+
 # ------------------------------------------------------------------ NSGA-II ranking (nsga-ii.cpp:14-118)
 NSGA_KEYS = ("dom_rank", "front_order", "front_offsets", "order_after", "crowd_dist", "norm")
 

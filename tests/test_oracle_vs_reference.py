@@ -124,6 +124,48 @@ def test_refseed_formula_matches_compiled_reference(world):
     assert hits >= 0
 
 
+# ------------------------------------------------------------------ variation operators
+@pytest.mark.parametrize("total", [False, True])
+def test_edit_replay_is_mutate_crossover_onbit(world, total):
+    """the generated edit lists (ref_gen_mutate_ops / ref_gen_cross_draws) replayed by
+    orc_apply_edits == the real Alignment::mutate / UPMX constructor / onBit: permutation,
+    mask, counters and fp64 accumulators, exactly."""
+    w = world
+    n2 = w["pair"].n2
+
+    def mirror(a):
+        st = a.state()
+        o = port.Aln(w["prob"], st[0], st[2])
+        o.set_counters(*a.counters())
+        return o
+
+    def same(a, o, tag):
+        assert all(np.array_equal(x, y) for x, y in zip(a.state(), o.state())), tag
+        assert a.counters() == o.counters(), (tag, a.counters(), o.counters())
+
+    for t in range(8):
+        a = ref.Aln(w["n1"], w["n2"], w["B"], w["G"])
+        a.shuf(100 + t, total=total)
+        b = ref.Aln(w["n1"], w["n2"], w["B"], w["G"])
+        b.shuf(200 + t, total=total)
+        o = mirror(a)
+        ops = ref.gen_mutate_ops(300 + t, n2, 0.03, total)
+        a.mutate(300 + t, 0.03, total)
+        o.apply_edits(ops)
+        same(a, o, ("mutate", t))
+        first, cops = ref.gen_cross_ops(400 + t, 0.2, (a.state()[0], a.state()[2]),
+                                        (b.state()[0], b.state()[2]), total)
+        child = ref.Aln.crossover(400 + t, 0.2, a, b, total)
+        oc = mirror(a if first else b)
+        oc.apply_edits(cops)
+        same(child, oc, ("cross", t))
+        m = child.state()[2]
+        for x in list(np.flatnonzero(m == 0)[:3]) + [0, n2 - 1]:
+            child.on_bit(int(x))
+            oc.apply_edits([[2, int(x), 0, 0]])
+            same(child, oc, ("onbit", t, x))
+
+
 # ------------------------------------------------------------------ NSGA-II ranking
 def test_gnu_sort_restatement_matches_std_sort():
     """orc_gnu_sort_by_key places tied keys exactly where this toolchain's std::sort does
