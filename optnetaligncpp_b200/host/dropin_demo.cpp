@@ -147,6 +147,11 @@ int main(int argc, char** argv) {
         report("pon", child);
         correctHillClimb(h, &child, false, iters, names);
         report("pclimb", child);
+        // on-disk format either side of the path: save a partial alignment, load it back through
+        // the alignment-file constructor (Alignment.cpp:49-138), which re-seeds the counters
+        child.save(prefix + "_partial.aln");
+        Alignment loaded(net1, net2, prefix + "_partial.aln", bit, goc);
+        report("pload", loaded);
     } catch (exception& e) {
         cerr << "error: " << e.what() << endl;
         return 1;

@@ -88,6 +88,8 @@ def lib():
     L.ref_aln_induced_count.argtypes = [vp, C.c_int, C.c_int]
     L.ref_aln_mutate.argtypes = [vp, C.c_uint32, C.c_float, C.c_int]
     L.ref_aln_on_bit.argtypes = [vp, C.c_int]
+    L.ref_aln_load.restype = vp
+    L.ref_aln_load.argtypes = [vp, vp, C.c_char_p, vp, vp]
     L.ref_gen_mutate_ops.restype = C.c_int
     L.ref_gen_mutate_ops.argtypes = [C.c_uint32, C.c_int, C.c_float, C.c_int, vp, C.c_int]
     L.ref_gen_cross_draws.restype = C.c_int
@@ -201,6 +203,12 @@ class Aln:
             return
         self.h = _check(lib().ref_aln_new(net1.h, net2.h, bit.h if bit else None,
                                           goc.h if goc else None), "Alignment()")
+
+    @staticmethod
+    def load(net1, net2, path, bit=None, goc=None):
+        """the alignment-file constructor (Alignment.cpp:49-138)"""
+        return Aln(_h=_check(lib().ref_aln_load(net1.h, net2.h, path.encode(), bit.h if bit else None,
+                                               goc.h if goc else None), "Alignment(file)"))
 
     def clone(self):
         return Aln(_h=lib().ref_aln_clone(self.h))

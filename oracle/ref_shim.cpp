@@ -139,6 +139,13 @@ void* ref_aln_new(void* n1, void* n2, void* bit, void* goc) {
     return a;
     REF_CATCH(nullptr)
 }
+// the alignment-file constructor (Alignment.cpp:49-138)
+void* ref_aln_load(void* n1, void* n2, const char* path, void* bit, void* goc) {
+    REF_TRY
+    return new Alignment(static_cast<Network*>(n1), static_cast<Network*>(n2), std::string(path),
+                         static_cast<BLASTDict*>(bit), static_cast<GOCDict*>(goc));
+    REF_CATCH(nullptr)
+}
 void* ref_aln_clone(void* a) { return new Alignment(*static_cast<Alignment*>(a)); }
 void ref_aln_free(void* a) { delete static_cast<Alignment*>(a); }
 

@@ -105,3 +105,9 @@ def test_dropin_matches_reference(with_goc):
     check(rest[5][2:], "pon", child)
     child.correct_hill_climb(seed + 8000, iters, names)
     check(rest[6], "pclimb", child)
+    # Alignment::save of a partial alignment + the alignment-file constructor
+    loaded = ref.Aln.load(n1, n2, os.path.join(d, "out_partial.aln"), B, G)
+    check(rest[7], "pload", loaded)
+    sa, sl = child.state(), loaded.state()
+    live = sa[2][:pair.n1] != 0
+    assert np.array_equal(sl[0][:pair.n1][live], sa[0][:pair.n1][live])
