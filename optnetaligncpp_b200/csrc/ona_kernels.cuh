@@ -707,8 +707,15 @@ struct RoundSlot {
 // neighbourhoods of its images (alnInv[] gathers).  Adjacency is symmetric, so each test asks
 // BOTH nodes' Bloom signatures (false-positive rate squared) before the exact adjacency bit is
 // loaded; the rare exact probes are independent predicated loads.
-__device__ __forceinline__ bool commit_conflicts(const DevGraph& g, const RoundSlot& j, const RoundSlot& i) {
+// u1 / u2: the unions n1x|n1y and n2x|n2y of j's signatures -- if none of i's four ids is in
+// them, none of the eight pair tests below can fire, which settles most pairs after four tests.
+__device__ __forceinline__ uint4 bloom_or(const uint4& a, const uint4& b) {
+    return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, 0u);
+}
+__device__ __forceinline__ bool commit_conflicts(const DevGraph& g, const RoundSlot& j, const uint4& u1,
+                                                 const uint4& u2, const RoundSlot& i) {
     const bool same = (j.x == i.x) | (j.x == i.y) | (j.y == i.x) | (j.y == i.y);
+    if (!(bloom_has(u1, i.x) | bloom_has(u1, i.y) | bloom_has(u2, i.ax) | bloom_has(u2, i.ay))) return same;
     const bool xir = i.x < g.n1, yir = i.y < g.n1;
     const bool h0 = xir & bloom_has(j.n1x, i.x) & bloom_has(i.n1x, j.x);
     const bool h1 = yir & bloom_has(j.n1x, i.y) & bloom_has(i.n1y, j.x);
@@ -736,6 +743,9 @@ __device__ __forceinline__ bool commit_conflicts(const DevGraph& g, const RoundS
                           (w4 >> (i.ax & 31)) | (w5 >> (i.ay & 31)) | (w6 >> (i.ax & 31)) | (w7 >> (i.ay & 31))) & 1u;
     return same | (hit != 0u);
 }
+__device__ __forceinline__ bool commit_conflicts(const DevGraph& g, const RoundSlot& j, const RoundSlot& i) {
+    return commit_conflicts(g, j, bloom_or(j.n1x, j.n1y), bloom_or(j.n2x, j.n2y), i);
+}
 
 template <typename T, int G>
 __global__ void __launch_bounds__(kRound * G)
@@ -749,6 +759,8 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
     __shared__ RoundSlot s_slot[kRound];
     __shared__ unsigned s_conf[kRound];
     __shared__ long long s_pos;
+    __shared__ double s_fc[kMaxObj];            // objectives of the current state
+    __shared__ double s_fn[kRound][kMaxObj];    // objectives each proposal would give (last decide)
     constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
     constexpr int kWarps = kRound * G / 32;
 
@@ -767,6 +779,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
     cur.C = pop.cons[p]; cur.I = pop.ind[p]; cur.size = pop.size[p];
     cur.bits = pop.bits[p]; cur.goc = pop.goc[p];
     long long n_acc = 0;
+    if (threadIdx.x < ob.M) s_fc[threadIdx.x] = objective(ob.names[threadIdx.x], cur, g.E1);
     __syncthreads();
 
     for (;;) {
@@ -817,10 +830,11 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
         {
             const int j = lane;
             const RoundSlot& sj = s_slot[j];
+            const uint4 u1 = bloom_or(sj.n1x, sj.n1y), u2 = bloom_or(sj.n2x, sj.n2y);
             unsigned bits = 0u;
             for (int i = warp; i < nvalid - 1; i += kWarps) {
                 const RoundSlot& si = s_slot[i];
-                if (j > i && j < nvalid && commit_conflicts(g, sj, si)) bits |= 1u << i;
+                if (j > i && j < nvalid && commit_conflicts(g, sj, u1, u2, si)) bits |= 1u << i;
             }
             if (bits) atomicOr(&s_conf[j], bits);
         }
@@ -846,7 +860,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                 if (need_decide) {
                     nw = apply_delta(cur, dc, di, sd);
                     double unused;
-                    acc = judge_move(ob, obj, cur, nullptr, nw, g.E1, nullptr, false, unused);
+                    acc = judge_move(ob, obj, cur, s_fc, nw, g.E1, s_fn[c], false, unused);
                     undo_accumulators(nw, sd, ub, ug);
                     const bool pert = !acc && (__double_as_longlong(ub) != __double_as_longlong(cur.bits) ||
                                                __double_as_longlong(ug) != __double_as_longlong(cur.goc));
@@ -857,6 +871,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     ev = __ballot_sync(0xffffffffu, acc || pert);
                     ties = __ballot_sync(0xffffffffu, tie);
                     need_decide = false;
+                    __syncwarp();   // s_fn rows are read across lanes by the commit below
                 }
                 // next thing that needs attention: an accept / perturbing reject, or a proposal
                 // whose score went stale (dirty) and must be re-scored before it is judged
@@ -935,6 +950,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     cur.goc = __shfl_sync(0xffffffffu, nw.goc, e);
                     acc_mask |= 1u << e;
                     n_acc++;
+                    if (c < ob.M) s_fc[c] = s_fn[e][c];   // the new state's objectives were just computed by lane e
                     // later proposals whose scores this commit makes stale (precomputed pair tests)
                     dirty_mask |= __ballot_sync(0xffffffffu, ((conf >> e) & 1u) != 0u && c > e) & vmask;
                     start = e + 1;
@@ -944,6 +960,8 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     // rejected, but the undo left different accumulator bits: carry them forward
                     cur.bits = __shfl_sync(0xffffffffu, ub, e);
                     cur.goc = __shfl_sync(0xffffffffu, ug, e);
+                    if (c < ob.M) s_fc[c] = objective(ob.names[c], cur, g.E1);
+                    __syncwarp();
                     start = e + 1;
                     need_decide = true;
                 }
