@@ -67,6 +67,7 @@ int main(int argc, char** argv) {
             printf("\n");
             aln->save(prefix + "_" + to_string(t) + ".aln");
         }
+        ona_host::writeResults(prefix + "_res", alns, names);  // .info + .aln, steadystate.cpp:339-395
         // operators that precede the hot loop for every child (steadystate.cpp:222-232)
         for (int t = 0; t < nthreads; t++) {
             RandGenT g(seed + 2000 + t), m(seed + 3000 + t);

@@ -1,7 +1,9 @@
 // see ona_host.hpp
 #include "ona_host.hpp"
 
+#include <algorithm>
 #include <cstdlib>
+#include <fstream>
 #include <memory>
 #include <tuple>
 
@@ -213,6 +215,31 @@ std::vector<std::vector<Alignment*> > rankGeneration(const std::vector<Alignment
     for (int f = 0; f < nf; f++)
         for (int k = offs[f]; k < offs[f + 1]; k++) fronts[f].push_back(in[src[k]]);
     return fronts;
+}
+
+void writeResults(const std::string& outprefix, const std::vector<Alignment*>& alns,
+                  const std::vector<fitnessName>& fitnessNames) {
+    std::ofstream info(outprefix + ".info");
+    if (!info) throw std::runtime_error("cannot write " + outprefix + ".info");
+    const fitnessName columns[] = {ECFit, ICSFit, S3Fit, GOCFit, BitscoreSumFit, EvalsSumFit, SizeFit, ICSTimesEC, S3Variant};
+    info << "filename";
+    for (fitnessName col : columns) {
+        info << '\t' << fitnessNameToStr(col);
+        if (std::find(fitnessNames.begin(), fitnessNames.end(), col) != fitnessNames.end()) info << "*";
+    }
+    info << std::endl;
+    for (size_t i = 0; i < alns.size(); i++) {
+        const Alignment* a = alns[i];
+        const std::string file = outprefix + "_" + std::to_string(i) + ".aln";
+        a->save(file);
+        info << file << '\t' << a->fastEC() << '\t' << a->fastICS() << '\t' << a->fastS3() << '\t';
+        if (a->gocs) info << a->currGOC << '\t';
+        else info << '?' << '\t';
+        // one accumulator serves both BLAST columns in the reference as well (:375-380)
+        if (a->bitscores) info << a->currBitscore << '\t' << a->currBitscore << '\t';
+        else info << '?' << '\t' << '?' << '\t';
+        info << a->alnSize() << '\t' << a->icsTimesEC() << '\t' << a->s3Variant() << std::endl;
+    }
 }
 
 }  // namespace ona_host

@@ -85,4 +85,13 @@ void apply_edits(Alignment& a, const std::vector<int>& ops);
 // nobody else -- are left empty.
 std::vector<std::vector<Alignment*> > rankGeneration(const std::vector<Alignment*>& in, bool crowding = true);
 
+
+// The result files optnetalign writes for its archive (steadystate.cpp:339-395):
+//   <outprefix>.info       TSV, one row per alignment: file name, EC, ICS, S3, GOC, BitscoreSum,
+//                          EvalsSum, Size, ICS*EC, S3Variant; a '*' after the names of the
+//                          optimised objectives; '?' where the score data was not given
+//   <outprefix>_<i>.aln    Alignment::save
+void writeResults(const std::string& outprefix, const std::vector<Alignment*>& alns,
+                  const std::vector<fitnessName>& fitnessNames);
+
 }  // namespace ona_host

@@ -198,6 +198,9 @@ void ref_aln_do_swap(void* a, int x, int y) { static_cast<Alignment*>(a)->doSwap
 void ref_aln_compute_fitness(void* av, const int* names, int M, double* out) {
     Alignment* a = static_cast<Alignment*>(av);
     std::vector<fitnessName> fn = to_names(names, M);
+    // computeFitness sizes the vector on first use only (Alignment.cpp:560-562): keep a caller
+    // that switches objective lists from writing past it
+    if ((int)a->fitness.size() != M) a->fitness.assign(M, 0.0);
     a->computeFitness(fn);
     for (int i = 0; i < M; ++i) out[i] = a->fitness[i];
 }

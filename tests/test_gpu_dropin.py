@@ -59,6 +59,22 @@ def test_dropin_matches_reference(with_goc):
         saved = [l.split() for l in open(os.path.join(d, "out_%d.aln" % t))]
         assert len(saved) == pair.n1
         assert all(int(u[1:]) == i and int(v[1:]) == al[i] for i, (u, v) in enumerate(saved))
+    # the archive's result files (steadystate.cpp:339-395): header with '*' on the optimised
+    # objectives, one TSV row per alignment in the stream's default %g formatting, '?' without data
+    info = [l.rstrip("\n").split("\t") for l in open(os.path.join(d, "out_res.info"))]
+    starred = {"S3", "BitscoreSum"} | ({"GOC"} if with_goc else set())
+    cols = ["EC", "ICS", "S3", "GOC", "BitscoreSum", "EvalsSum", "Size", "ICS*EC", "S3Variant"]
+    assert info[0] == ["filename"] + [c + ("*" if c in starred else "") for c in cols]
+    assert len(info) == 1 + nthreads
+    for t in range(nthreads):
+        a = climbed[t]
+        f = dict(zip(range(10), a.compute_fitness(list(range(10)))))   # fitnessName order, Network.h:31
+        c = a.counters()
+        want = [os.path.join(d, "out_res_%d.aln" % t), "%g" % f[1], "%g" % f[0], "%g" % f[6],
+                "%g" % c[3] if with_goc else "?", "%g" % c[2], "%g" % c[2], "%g" % a.aln_size(),
+                "%g" % f[8], "%g" % f[9]]
+        assert info[1 + t] == want, (info[1 + t], want)
+        assert open(os.path.join(d, "out_res_%d.aln" % t)).read() == open(os.path.join(d, "out_%d.aln" % t)).read()
     for t in range(nthreads):
         child = ref.Aln.crossover(seed + 2000 + t, 0.1, climbed[t], climbed[0], True)
         child.mutate(seed + 3000 + t, 0.005, True)
