@@ -3,7 +3,7 @@
 // of this directory (plus the reference's own Network.cpp, blastinfo.cpp, goc.cpp, nsga-ii.cpp).
 // It is what tests/test_gpu_dropin.py runs to show that reference callers work unchanged:
 //
-//   dropin_demo net1 net2 sim|- annos1|- annos2|- seed iters nthreads out_prefix
+//   dropin_demo net1 net2 sim|- annos1|- annos2|- seed iters nthreads out_prefix [steepest]
 //
 // Per thread t: Alignment(net1,net2,bit,goc); shuf(mt19937(seed+t)); computeFitness;
 // correctHillClimb(mt19937(seed+1000+t), iters, obj=-1); then mutate + a crossover with thread
@@ -45,6 +45,21 @@ int main(int argc, char** argv) {
         if (bit) names.push_back(BitscoreSumFit);
         if (goc) names.push_back(GOCFit);
 
+        if (argc > 10 && string(argv[10]) == "steepest") {
+            // the threaded exhaustive search (localSearch.cpp:122-203): every scan of the n1 x n2
+            // grid is one pass of the swap-delta kernel here
+            RandGenT g(seed);
+            Alignment a(net1, net2, bit, goc);
+            a.shuf(g, false, false, true);
+            a.computeFitness(names);
+            steepestAscentHillClimb(&a, names, nthreads, false);
+            printf("steepest cons %d ind %d bits %.17g goc %.17g", a.currConservedCount, a.currInducedCount,
+                   bit ? a.currBitscore : 0.0, goc ? a.currGOC : 0.0);
+            for (double f : a.fitness) printf(" %.17g", f);
+            printf("\n");
+            a.save(prefix + "_steepest.aln");
+            return 0;
+        }
         vector<Alignment*> alns(nthreads, nullptr);
         vector<thread> ts;
         for (int t = 0; t < nthreads; t++) {
@@ -116,6 +131,16 @@ int main(int argc, char** argv) {
                 }
             }
             printf("nsga2 fronts %zu %s\n", nfronts, same ? "identical" : "DIFFERENT");
+        }
+        {   // proportionalSearch (localSearch.cpp:60-84): 500-iteration climbs on one objective or another
+            Alignment ps(*alns[0]);
+            ps.computeFitness(names);
+            RandGenT g(seed + 9000);
+            proportionalSearch(g, &ps, true, 6, names, 0, 0.5);
+            printf("propsearch cons %d ind %d bits %.17g goc %.17g", ps.currConservedCount, ps.currInducedCount,
+                   bit ? ps.currBitscore : 0.0, goc ? ps.currGOC : 0.0);
+            for (double f : ps.fitness) printf(" %.17g", f);
+            printf("\n");
         }
         Alignment probe(*alns[0]);
         printf("snd %.17g\n", swapNormalizedDelta(probe, names, 3, 7));

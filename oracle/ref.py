@@ -88,6 +88,8 @@ def lib():
     L.ref_aln_induced_count.argtypes = [vp, C.c_int, C.c_int]
     L.ref_aln_mutate.argtypes = [vp, C.c_uint32, C.c_float, C.c_int]
     L.ref_aln_on_bit.argtypes = [vp, C.c_int]
+    L.ref_steepest_ascent.argtypes = [vp, I32P, C.c_int, C.c_int]
+    L.ref_proportional_search.argtypes = [vp, C.c_uint32, C.c_int, I32P, C.c_int, C.c_int, C.c_double]
     L.ref_aln_load.restype = vp
     L.ref_aln_load.argtypes = [vp, vp, C.c_char_p, vp, vp]
     L.ref_gen_mutate_ops.restype = C.c_int
@@ -289,6 +291,16 @@ class Aln:
         names = _i32(names)
         self.compute_fitness(names)
         lib().ref_correct_hill_climb(self.h, seed, iters, names, len(names), obj)
+
+    def proportional_search(self, seed, iters, names, obj, proportion):
+        """proportionalSearch(mt19937(seed), ...) (localSearch.cpp:60-84)"""
+        names = _i32(names)
+        lib().ref_proportional_search(self.h, seed, iters, names, len(names), obj, proportion)
+
+    def steepest_ascent(self, names, nthreads=2):
+        """steepestAscentHillClimb until convergence (localSearch.cpp:122-203)"""
+        names = _i32(names)
+        lib().ref_steepest_ascent(self.h, names, len(names), nthreads)
 
     def hill_climb_replay(self, xy, names, obj=-1, want_accepted=False):
         xy, names = _i32(xy).reshape(-1), _i32(names)

@@ -280,6 +280,26 @@ void ref_correct_hill_climb(void* av, uint32_t seed, int iters, const int* names
     correctHillClimb(g, a, true, iters, fn, obj);
 }
 
+// proportionalSearch (localSearch.cpp:60-84) with mt19937(seed)
+void ref_proportional_search(void* av, uint32_t seed, int iters, const int* names, int M, int obj,
+                             double proportion) {
+    Alignment* a = static_cast<Alignment*>(av);
+    std::vector<fitnessName> fn = to_names(names, M);
+    if ((int)a->fitness.size() != M) a->fitness.assign(M, 0.0);
+    a->computeFitness(fn);
+    RandGenT g(seed);
+    proportionalSearch(g, a, true, iters, fn, obj, proportion);
+}
+
+// steepestAscentHillClimb (localSearch.cpp:122-203) until no swap improves
+void ref_steepest_ascent(void* av, const int* names, int M, int nthreads) {
+    Alignment* a = static_cast<Alignment*>(av);
+    std::vector<fitnessName> fn = to_names(names, M);
+    if ((int)a->fitness.size() != M) a->fitness.assign(M, 0.0);
+    a->computeFitness(fn);
+    steepestAscentHillClimb(a, fn, nthreads, false);
+}
+
 // the (x,y) proposals correctHillClimb would draw from mt19937(seed):
 // same two distribution objects, same draw order as localSearch.cpp:21-28.
 void ref_gen_xy_stream(uint32_t seed, int n1, int n2, long iters, int* xy) {

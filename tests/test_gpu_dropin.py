@@ -89,12 +89,20 @@ def test_dropin_matches_reference(with_goc):
     # nsga-ii.cpp (linked unchanged): fronts, member order, domRank, crowdDist, fitnessNormalized
     got = lines[2 * nthreads]
     assert got[0] == "nsga2" and int(got[2]) >= 1 and got[3] == "identical", got
+    # proportionalSearch (localSearch.cpp:60-84)
+    ps = climbed[0].clone()
+    ps.proportional_search(seed + 9000, 6, names, 0, 0.5)
+    got = lines[2 * nthreads + 1]
+    c = ps.counters()
+    assert got[0] == "propsearch" and (int(got[2]), int(got[4])) == (c[0], c[1])
+    assert float(got[6]) == c[2] and float(got[8]) == c[3]
+    assert [float(v) for v in got[9:]] == list(ps.compute_fitness(names))
     snd = climbed[0].swap_normalized_delta(names, 3, 7)
-    got = float(lines[2 * nthreads + 1][1])
+    got = float(lines[2 * nthreads + 2][1])
     assert got == snd or (np.isnan(got) and np.isnan(snd))
 
     # partial alignments (mask flips, mask AND/OR, onBit go through ona_apply_edits): exact too
-    rest = lines[2 * nthreads + 2:]
+    rest = lines[2 * nthreads + 3:]
 
     def check(row, tag, a):
         assert row[0] == tag, row
@@ -127,3 +135,33 @@ def test_dropin_matches_reference(with_goc):
     sa, sl = child.state(), loaded.state()
     live = sa[2][:pair.n1] != 0
     assert np.array_equal(sl[0][:pair.n1][live], sa[0][:pair.n1][live])
+
+
+@pytest.mark.skipif(not os.path.exists(DEMO) or not ref.available(),
+                    reason="drop-in demo / compiled reference not built (dev container only)")
+def test_dropin_steepest_ascent_matches_reference():
+    """steepestAscentHillClimb (localSearch.cpp:122-203) through the drop-in: every scan of the
+    n1 x n2 grid is one ona_steepest_step; same swaps, same final alignment as the reference's
+    threaded CPU scan (integer bit scores, so the reference's swap/un-swap leaves no fp residue)."""
+    pair = synth.make_pair(n1=60, n2=80, m1=200, m2=260, max_deg=15, seed=43, bit_density=0.03)
+    d = tempfile.mkdtemp()
+    paths = synth.write_text(pair, os.path.join(d, "w"))
+    seed = 5
+    out = subprocess.run([DEMO, paths["net1"], paths["net2"], paths["sim"], "-", "-", str(seed), "0", "2",
+                          os.path.join(d, "out"), "steepest"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    got = out.stdout.strip().splitlines()[-1].split()
+    n1, n2 = ref.Net(paths["net1"]), ref.Net(paths["net2"])
+    B = ref.Dict.load_blast(n1, n2, paths["sim"])
+    a = ref.Aln(n1, n2, B, None)
+    a.shuf(seed)
+    start = a.counters()
+    a.steepest_ascent([6, 2], nthreads=2)
+    c = a.counters()
+    assert c != start                       # the search did move
+    assert got[0] == "steepest" and (int(got[2]), int(got[4])) == (c[0], c[1])
+    assert float(got[6]) == c[2]
+    assert [float(v) for v in got[9:]] == list(a.compute_fitness([6, 2]))
+    saved = [l.split() for l in open(os.path.join(d, "out_steepest.aln"))]
+    al = a.state()[0]
+    assert all(int(u[1:]) == i and int(v[1:]) == al[i] for i, (u, v) in enumerate(saved))
