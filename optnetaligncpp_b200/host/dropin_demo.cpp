@@ -173,6 +173,19 @@ int main(int argc, char** argv) {
         report("pon", child);
         correctHillClimb(h, &child, false, iters, names);
         report("pclimb", child);
+        // the other ways the drivers build a starting alignment (steadystate.cpp:92-118): greedy
+        // best-score matching and the size-controlled random starts
+        if (bit) {
+            Alignment gm(net1, net2, bit, goc);
+            gm.greedyMatch(true);
+            report("greedy", gm);
+        }
+        for (int v = 0; v < 2; v++) {
+            RandGenT g(seed + 9500 + v);
+            Alignment a(net1, net2, bit, goc);
+            a.shuf(g, v == 0, v == 1, false);
+            report(v == 0 ? "uniformsize" : "smallstart", a);
+        }
         // on-disk format either side of the path: save a partial alignment, load it back through
         // the alignment-file constructor (Alignment.cpp:49-138), which re-seeds the counters
         child.save(prefix + "_partial.aln");

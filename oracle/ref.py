@@ -88,6 +88,7 @@ def lib():
     L.ref_aln_induced_count.argtypes = [vp, C.c_int, C.c_int]
     L.ref_aln_mutate.argtypes = [vp, C.c_uint32, C.c_float, C.c_int]
     L.ref_aln_on_bit.argtypes = [vp, C.c_int]
+    L.ref_aln_greedy_match.argtypes = [vp, C.c_int]
     L.ref_steepest_ascent.argtypes = [vp, I32P, C.c_int, C.c_int]
     L.ref_proportional_search.argtypes = [vp, C.c_uint32, C.c_int, I32P, C.c_int, C.c_int, C.c_double]
     L.ref_aln_load.restype = vp
@@ -276,6 +277,9 @@ class Aln:
 
     def induced_count(self, n2, ignore):
         return lib().ref_aln_induced_count(self.h, n2, ignore)
+
+    def greedy_match(self, bit=True):
+        lib().ref_aln_greedy_match(self.h, int(bit))
 
     def on_bit(self, x):
         lib().ref_aln_on_bit(self.h, int(x))

@@ -221,6 +221,7 @@ void ref_aln_mutate(void* a, uint32_t seed, float mutswappb, int total) {
     RandGenT g(seed);
     static_cast<Alignment*>(a)->mutate(g, mutswappb, total != 0);
 }
+void ref_aln_greedy_match(void* a, int bit) { static_cast<Alignment*>(a)->greedyMatch(bit != 0); }
 void ref_aln_on_bit(void* a, int x) { static_cast<Alignment*>(a)->onBit(x); }
 void* ref_aln_crossover(uint32_t seed, float cxswappb, void* p1, void* p2, int total) {
     RandGenT g(seed);

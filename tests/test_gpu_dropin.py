@@ -129,9 +129,17 @@ def test_dropin_matches_reference(with_goc):
     check(rest[5][2:], "pon", child)
     child.correct_hill_climb(seed + 8000, iters, names)
     check(rest[6], "pclimb", child)
+    # greedyMatch and the size-controlled random starts (steadystate.cpp:92-118)
+    gm = ref.Aln(n1, n2, B, G)
+    gm.greedy_match(True)
+    check(rest[7], "greedy", gm)
+    for v, tag in enumerate(("uniformsize", "smallstart")):
+        a = ref.Aln(n1, n2, B, G)
+        a.shuf(seed + 9500 + v, uniformsize=(v == 0), smallstart=(v == 1), total=False)
+        check(rest[8 + v], tag, a)
     # Alignment::save of a partial alignment + the alignment-file constructor
     loaded = ref.Aln.load(n1, n2, os.path.join(d, "out_partial.aln"), B, G)
-    check(rest[7], "pload", loaded)
+    check(rest[10], "pload", loaded)
     sa, sl = child.state(), loaded.state()
     live = sa[2][:pair.n1] != 0
     assert np.array_equal(sl[0][:pair.n1][live], sa[0][:pair.n1][live])
