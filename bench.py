@@ -97,7 +97,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """GPU sections start here (warm-up onwards): samples before it are idle readings"""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc:
@@ -107,11 +111,12 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
         sm, smax, reasons, loaded = [], 0.0, set(), []
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for t, r in self.rows:
             try:
                 sm.append(float(r[1]))
                 smax = max(smax, float(r[2]))
-                if len(r) > 8 and float(r[8]) >= 10.0:
+                if t >= t_mark:
                     loaded.append(float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                                     "sw_power_cap"), r[4:8]):
@@ -121,7 +126,7 @@ class ClockSampler:
                 pass
         busy = loaded or [v for v in sm if v > 0]
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax or None,
-                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(loaded)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_gpu_sections": len(loaded)}
 
 
 # ------------------------------------------------------------------ reference CPU arm
@@ -315,6 +320,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.2)
+    sampler.mark()
     for w in range(max(args.warmup, 0)):
         step(seed=10_000 + w)
     barrier()
