@@ -700,6 +700,7 @@ __device__ __forceinline__ bool bloom_has(const uint4& sg, int id) {
 struct RoundSlot {
     int x, y, ax, ay, dc, di;
     uint4 n1x, n1y, n2x, n2y;  // Bloom signatures of N1(x), N1(y), N2(a_x), N2(a_y)
+    ScoreDelta sd;             // score-table part of the delta (looked up next to the walk)
 };
 
 // Does the score of proposal j read anything that committing proposal i writes?  Its own
@@ -822,6 +823,9 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
             } else if (gl == 3) {
                 sl.n2x = __ldg(g.sig2 + cx.ax);
                 sl.n2y = __ldg(g.sig2 + cx.ay);
+                if (G < 8) sl.sd = score_delta<T>(g, S, Gt, s_aln, x, y);
+            } else if (gl == 4) {
+                sl.sd = score_delta<T>(g, S, Gt, s_aln, x, y);
             }
         }
         __syncthreads();
@@ -846,7 +850,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
             RoundSlot& me = s_slot[c];
             const int x = me.x, y = me.y;
             int dc = me.dc, di = me.di;
-            ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, x, y);
+            ScoreDelta sd = me.sd;
             unsigned conf = s_conf[c];
             const unsigned lt_mask = (1u << c) - 1u;
 
