@@ -302,6 +302,7 @@ k_nsga_rank_small(const double* __restrict__ fit, const unsigned char* __restric
         for (int q = warp; q < P; q += 32) {  // :41-49
             if (count[q] <= 0) continue;
             uint32_t d = lane < W ? (dom[(size_t)q * W + lane] & front[lane]) : 0u;
+            if (!__any_sync(0xffffffffu, d != 0u)) continue;   // no dominator of q in this front
             int hit = __popc(d), mp = -1;
             while (d) {
                 const int b = __ffs(d) - 1;
