@@ -335,7 +335,10 @@ __device__ __forceinline__ QuadPlan make_plan(const DevGraph& g, const SwapCtx& 
 // one branch-free item routine for all four lists, so that the lanes of a warp (each on its
 // own candidate, or all on one hub) stay converged whatever the individual list lengths are.
 // `seen` must be OR-reduced over the lanes that share a candidate before special_terms.
-template <typename T>
+// Prefetch: request the quad of the next iteration before the current one is scored (pays when a
+// group of lanes shares one candidate, as in the hill climb; thread-per-candidate walks already
+// overlap their round trips across the lanes' candidates).
+template <typename T, bool Prefetch = false>
 __device__ __forceinline__ void walk_plan(const DevGraph& g, const T* s_aln, const T* s_inv,
                                           const SwapCtx& c, const QuadPlan& p, int first, int stride,
                                           int& dc, int& di, int& seen) {
@@ -352,10 +355,30 @@ __device__ __forceinline__ void walk_plan(const DevGraph& g, const T* s_aln, con
         if (c.my) rs.sy = __ldg(g.sig2 + c.ay);
     }
     const int coefx = c.Lx_new - c.Lx_old, coefy = c.Ly_new - c.Ly_old;
+    int l_next = 0;
+    int4 t_next = make_int4(0, 0, 0, 0);
+    if (Prefetch && first < p.e3) {
+        l_next = (first >= p.e0 ? 1 : 0) + (first >= p.e1 ? 1 : 0) + (first >= p.e2 ? 1 : 0);
+        t_next = __ldg((l_next < 2 ? g.cq1 : g.cq2) +
+                       (l_next == 0 ? p.b0 : l_next == 1 ? p.b1 : l_next == 2 ? p.b2 : p.b3) + first);
+    }
     for (int q = first; q < p.e3; q += stride) {
-        const int l = (q >= p.e0 ? 1 : 0) + (q >= p.e1 ? 1 : 0) + (q >= p.e2 ? 1 : 0);
-        const int idx = (l == 0 ? p.b0 : l == 1 ? p.b1 : l == 2 ? p.b2 : p.b3) + q;
-        const int4 t = __ldg((l < 2 ? g.cq1 : g.cq2) + idx);
+        int l;
+        int4 t;
+        if (!Prefetch) {
+            l = (q >= p.e0 ? 1 : 0) + (q >= p.e1 ? 1 : 0) + (q >= p.e2 ? 1 : 0);
+            const int idx = (l == 0 ? p.b0 : l == 1 ? p.b1 : l == 2 ? p.b2 : p.b3) + q;
+            t = __ldg((l < 2 ? g.cq1 : g.cq2) + idx);
+        } else {
+            l = l_next;
+            t = t_next;
+            const int qn = q + stride;
+            if (qn < p.e3) {
+                l_next = (qn >= p.e0 ? 1 : 0) + (qn >= p.e1 ? 1 : 0) + (qn >= p.e2 ? 1 : 0);
+                t_next = __ldg((l_next < 2 ? g.cq1 : g.cq2) +
+                               (l_next == 0 ? p.b0 : l_next == 1 ? p.b1 : l_next == 2 ? p.b2 : p.b3) + qn);
+            }
+        }
         QuadCtx qc;
         qc.cons = l < 2;
         qc.table = qc.cons ? static_cast<const void*>(s_aln) : static_cast<const void*>(s_inv);

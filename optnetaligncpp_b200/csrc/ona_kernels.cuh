@@ -806,7 +806,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
             const SwapCtx cx = make_ctx<T>(g, s_aln, x, y);
             const QuadPlan pl4 = make_plan(g, cx);
             int dc, di, seen;
-            walk_plan<T>(g, s_aln, s_inv, cx, pl4, gl, G, dc, di, seen);
+            walk_plan<T, (G >= 8)>(g, s_aln, s_inv, cx, pl4, gl, G, dc, di, seen);
             dc = group_sum<G>(dc, gmask);
             di = group_sum<G>(di, gmask);
 #pragma unroll
@@ -889,7 +889,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     const SwapCtx cx = make_ctx<T>(g, s_aln, xe, ye);
                     const QuadPlan pl4 = make_plan(g, cx);
                     int rdc, rdi, seen;
-                    walk_plan<T>(g, s_aln, s_inv, cx, pl4, lane, 32, rdc, rdi, seen);
+                    walk_plan<T, (G >= 8)>(g, s_aln, s_inv, cx, pl4, lane, 32, rdc, rdi, seen);
                     rdc = warp_sum<int>(rdc);
                     rdi = warp_sum<int>(rdi);
                     seen = (int)__reduce_or_sync(0xffffffffu, (unsigned)seen);
