@@ -469,14 +469,16 @@ __device__ __forceinline__ void undo_accumulators(const Scalars& after, const Sc
 //   obj == -2: unconditional (ona_apply_swaps).
 //   curfit: the current state's objectives (any address space), or nullptr to derive them
 //           from `cur`;  fit_out (nullable): receives the new objectives.
+//   names: the objective list in shared memory (nullptr: read it from the kernel parameters; the
+//          indexed constant-bank load is slow on a single warp's critical path)
 __device__ __forceinline__ bool judge_move(const DevObjectives& ob, int obj, const Scalars& cur,
                                            const double* curfit, const Scalars& nw,
                                            unsigned long long E1, double* fit_out, bool want_snd,
-                                           double& snd) {
+                                           double& snd, const int* names = nullptr) {
     bool any_lt = false, obj_le = false, oneNeg = false;
     double sumSq = 0.0;
     for (int j = 0; j < ob.M; ++j) {
-        const int name = ob.names[j];
+        const int name = names ? names[j] : ob.names[j];
         const double fn = objective(name, nw, E1);
         const double fc = curfit ? curfit[j] : objective(name, cur, E1);
         if (fit_out) fit_out[j] = fn;

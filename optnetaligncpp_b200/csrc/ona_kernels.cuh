@@ -760,6 +760,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
     __shared__ RoundSlot s_slot[kRound];
     __shared__ unsigned s_conf[kRound];
     __shared__ long long s_pos;
+    __shared__ int s_names[kMaxObj];            // the objective list
     __shared__ double s_fc[kMaxObj];            // objectives of the current state
     __shared__ double s_fn[kRound][kMaxObj];    // objectives each proposal would give (last decide)
     constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
@@ -780,7 +781,10 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
     cur.C = pop.cons[p]; cur.I = pop.ind[p]; cur.size = pop.size[p];
     cur.bits = pop.bits[p]; cur.goc = pop.goc[p];
     long long n_acc = 0;
-    if (threadIdx.x < ob.M) s_fc[threadIdx.x] = objective(ob.names[threadIdx.x], cur, g.E1);
+    if (threadIdx.x < ob.M) {
+        s_names[threadIdx.x] = ob.names[threadIdx.x];
+        s_fc[threadIdx.x] = objective(ob.names[threadIdx.x], cur, g.E1);
+    }
     __syncthreads();
 
     for (;;) {
@@ -864,7 +868,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                 if (need_decide) {
                     nw = apply_delta(cur, dc, di, sd);
                     double unused;
-                    acc = judge_move(ob, obj, cur, s_fc, nw, g.E1, s_fn[c], false, unused);
+                    acc = judge_move(ob, obj, cur, s_fc, nw, g.E1, s_fn[c], false, unused, s_names);
                     undo_accumulators(nw, sd, ub, ug);
                     const bool pert = !acc && (__double_as_longlong(ub) != __double_as_longlong(cur.bits) ||
                                                __double_as_longlong(ug) != __double_as_longlong(cur.goc));

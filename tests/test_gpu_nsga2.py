@@ -111,6 +111,16 @@ def test_full_size_invariants(eng):
     assert np.array_equal(r["crowd_dist"][mem], want)
 
 
+def test_edge_shapes(eng, small_path):
+    """one row, identical rows, 16 objectives, all-zero and all-negative objectives (normalisation by a
+    maximum that stays 0.0: inf / NaN exactly as the reference produces them)"""
+    rng = np.random.default_rng(8)
+    cases = [np.array([[0.3, 0.7]]), np.full((37, 3), 0.25), rng.random((90, 16)),
+             np.round(rng.random((64, 16)), 1), np.zeros((20, 2)), -rng.random((50, 2))]
+    for i, f in enumerate(cases):
+        nsga_cases.assert_same(eng.nsga2_rank(f), port.nsga2(f), i)
+
+
 def test_device_buffers_and_island_gather(eng):
     """ona_nsga2_rank_dev on torch device tensors, as used on the all-gathered objective rows."""
     import torch

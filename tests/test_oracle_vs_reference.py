@@ -203,3 +203,14 @@ def test_nsga2_matches_reference_live():
         nsga_cases.assert_same(port.nsga2(f, hn, nm), ref.nsga2(f, hn, nm), (t, kind, P, M))
         a, b = f[int(rng.integers(0, P))], f[int(rng.integers(0, P))]
         assert port.dominates(a, b) == ref.dominates(a, b)
+
+
+def test_nsga2_edge_shapes_match_reference():
+    """one row, identical rows, 16 objectives, a population that is one long chain or one flat front"""
+    import nsga_cases
+    rng = np.random.default_rng(8)
+    cases = [np.array([[0.3, 0.7]]), np.full((37, 3), 0.25), rng.random((90, 16)),
+             np.round(rng.random((64, 16)), 1), nsga_cases.make_case("chain", 130, 3, 1),
+             nsga_cases.make_case("single_front", 257, 4, 2), np.zeros((20, 2)), -rng.random((50, 2))]
+    for i, f in enumerate(cases):
+        nsga_cases.assert_same(port.nsga2(f), ref.nsga2(f), i)
