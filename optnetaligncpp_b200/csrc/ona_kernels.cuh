@@ -701,7 +701,40 @@ struct RoundSlot {
     int x, y, ax, ay, dc, di;
     uint4 n1x, n1y, n2x, n2y;  // Bloom signatures of N1(x), N1(y), N2(a_x), N2(a_y)
     ScoreDelta sd;             // score-table part of the delta (looked up next to the walk)
+    uint32_t orx, ory;         // packed aln[x], aln[y] right before this proposal was committed
 };
+
+// Proposal (u, w) has just been committed; ru / rw are the packed aln[u], aln[w] from before it.
+// Brings the delta (dc, di) of a LATER proposal (xj, yj) that shares no position with it up to date
+// without walking its lists again: in the lists of xj / yj only the items t = u and t = w changed
+// (they traded image and mask bit), in the lists of a_xj / a_yj only the images a_u, a_w (they
+// traded pre-images).  With D(v) = my*A2[a_yj][v] - mx*A2[a_xj][v] (the item term of quad_item):
+//   dc += ([u in N1(xj)] - [w in N1(xj)] - [u in N1(yj)] + [w in N1(yj)]) * (m_w*D(a_w) - m_u*D(a_u))
+//   di += sum over v in {a_u, a_w}, list owner o in {a_xj, a_yj}:  coef_o * A2[o][v] * (alive'(v) - alive(v))
+template <typename T>
+__device__ __forceinline__ void correct_delta(const DevGraph& g, const T* s_aln, int xj, int yj, int u, int w,
+                                              uint32_t ru, uint32_t rw, int& dc, int& di) {
+    constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
+    const SwapCtx cj = make_ctx<T>(g, s_aln, xj, yj);
+    const int au = (int)(ru & MASK), aw = (int)(rw & MASK);
+    const int mu = (ru & FLAG) ? 0 : 1, mw = (rw & FLAG) ? 0 : 1;
+    const int pxu = probe(g, cj.ax, au), pxw = probe(g, cj.ax, aw);
+    const int pyu = probe(g, cj.ay, au), pyw = probe(g, cj.ay, aw);
+    const bool ur = u < g.n1, wr = w < g.n1;
+    auto adj1 = [&](int a, int b) {
+        return (int)((__ldg(g.adj1 + (size_t)a * g.W1 + (b >> 5)) >> (b & 31)) & 1u);
+    };
+    const int inXu = (cj.xr && ur) ? adj1(xj, u) : 0, inXw = (cj.xr && wr) ? adj1(xj, w) : 0;
+    const int inYu = (cj.yr && ur) ? adj1(yj, u) : 0, inYw = (cj.yr && wr) ? adj1(yj, w) : 0;
+    const int Tu = mu * (cj.my * pyu - cj.mx * pxu), Tw = mw * (cj.my * pyw - cj.mx * pxw);
+    dc += ((inXu - inXw) - (inYu - inYw)) * (Tw - Tu);
+    if (induced_changes(cj)) {
+        const int coefx = cj.Lx_new - cj.Lx_old, coefy = cj.Ly_new - cj.Ly_old;
+        const int dau = ((wr ? 1 : 0) - (ur ? 1 : 0)) * mu;   // image a_u moved from position u to w
+        const int daw = ((ur ? 1 : 0) - (wr ? 1 : 0)) * mw;
+        di += coefx * (pxu * dau + pxw * daw) + coefy * (pyu * dau + pyw * daw);
+    }
+}
 
 // Does the score of proposal j read anything that committing proposal i writes?  Its own
 // positions, the net1 neighbourhoods of its positions (aln[] gathers) and the net2
@@ -929,6 +962,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     const unsigned commit = run & (jd >= 32 ? 0xffffffffu : ((1u << jd) - 1u));
                     if ((commit >> c) & 1u) {  // disjoint positions and images: parallel commits are race-free
                         const uint32_t rx = s_aln[x], ry = s_aln[y];
+                        me.orx = rx; me.ory = ry;
                         s_aln[x] = (T)ry;
                         s_aln[y] = (T)rx;
                         s_inv[ry & MASK] = (T)((uint32_t)x | (ry & FLAG));
@@ -936,7 +970,18 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     }
                     acc_mask |= commit;
                     n_acc += __popc(commit);
-                    dirty_mask |= __ballot_sync(0xffffffffu, (conf & commit & lt_mask) != 0u) & vmask;
+                    __syncwarp();
+                    // later proposals that read what these commits wrote: a shared position means a
+                    // new row of its own (full re-score when its turn comes); otherwise the few
+                    // changed items are corrected in place
+                    bool stale_row = false, corrected = false;
+                    for (unsigned m = conf & commit & lt_mask; m; m &= m - 1u) {
+                        const RoundSlot& si = s_slot[__ffs(m) - 1];
+                        if ((x == si.x) | (x == si.y) | (y == si.x) | (y == si.y)) stale_row = true;
+                        else { correct_delta<T>(g, s_aln, x, y, si.x, si.y, si.orx, si.ory, dc, di); corrected = true; }
+                    }
+                    dirty_mask |= __ballot_sync(0xffffffffu, stale_row) & vmask;
+                    if (__any_sync(0xffffffffu, corrected)) need_decide = true;
                     start = min(jd, ne);
                     __syncwarp();
                     continue;
@@ -944,12 +989,14 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                 const bool e_acc = __shfl_sync(0xffffffffu, (int)acc, e) != 0;
                 if (e_acc) {
                     // commit proposal e: doSwap's state change, Alignment.cpp:496-504,516-519
+                    const int xe = __shfl_sync(0xffffffffu, x, e), ye = __shfl_sync(0xffffffffu, y, e);
+                    const uint32_t ru = s_aln[xe], rw = s_aln[ye];
+                    __syncwarp();
                     if (c == e) {
-                        const uint32_t rx = s_aln[x], ry = s_aln[y];
-                        s_aln[x] = (T)ry;
-                        s_aln[y] = (T)rx;
-                        s_inv[ry & MASK] = (T)((uint32_t)x | (ry & FLAG));
-                        s_inv[rx & MASK] = (T)((uint32_t)y | (rx & FLAG));
+                        s_aln[x] = (T)rw;
+                        s_aln[y] = (T)ru;
+                        s_inv[rw & MASK] = (T)((uint32_t)x | (rw & FLAG));
+                        s_inv[ru & MASK] = (T)((uint32_t)y | (ru & FLAG));
                     }
                     cur.C = __shfl_sync(0xffffffffu, nw.C, e);
                     cur.I = __shfl_sync(0xffffffffu, nw.I, e);
@@ -959,8 +1006,16 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     acc_mask |= 1u << e;
                     n_acc++;
                     if (c < ob.M) s_fc[c] = s_fn[e][c];   // the new state's objectives were just computed by lane e
-                    // later proposals whose scores this commit makes stale (precomputed pair tests)
-                    dirty_mask |= __ballot_sync(0xffffffffu, ((conf >> e) & 1u) != 0u && c > e) & vmask;
+                    // later proposals that read what this commit wrote (precomputed pair tests): a
+                    // shared position means a new row of its own (full re-score when its turn comes);
+                    // otherwise the few changed items are corrected in place
+                    __syncwarp();
+                    bool stale_row = false;
+                    if (((conf >> e) & 1u) != 0u && c > e) {
+                        if ((x == xe) | (x == ye) | (y == xe) | (y == ye)) stale_row = true;
+                        else correct_delta<T>(g, s_aln, x, y, xe, ye, ru, rw, dc, di);
+                    }
+                    dirty_mask |= __ballot_sync(0xffffffffu, stale_row) & vmask;
                     start = e + 1;
                     need_decide = true;   // later decisions see new current objectives
                     __syncwarp();
