@@ -598,3 +598,37 @@ def test_edit_lists_random_against_oracle():
         e.apply_edits(np.array([[[7, 0, 0, 0]]], np.int32))
     with pytest.raises(engine.OnaError):
         e.apply_edits(np.array([[[0, 0, pair.n2, 0]]], np.int32))
+
+
+# ------------------------------------------------------------------ every hill-climb instantiation
+@pytest.mark.parametrize("group", ["4", "8", "16"])
+@pytest.mark.parametrize("total", [True, False])
+def test_hill_climb_every_group_size(monkeypatch, group, total):
+    """k_hill_climb<T, G> for G = 4 (what populations above 3 x SMs get), 8 and 16, forced through
+    ONA_GROUP, on a small dense pair where almost every commit touches later proposals of its round
+    (in-place corrections, shared positions, dummies, self-loops, masks): accept bits, permutation,
+    counters and accumulators equal the oracle's sequential loop."""
+    monkeypatch.setenv("ONA_GROUP", group)
+    pair = synth.make_pair(n1=70, n2=90, m1=700, m2=900, max_deg=40, seed=31, loop_frac=0.1,
+                           annotations=True, n_terms=40, bit_density=0.2, bit_decimals=True)
+    S, G = synth.dense_bits(pair), synth.dense_goc(pair)
+    prob = port.Problem(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2, S, G)
+    names = [engine.S3, engine.BITSCORE_SUM, engine.GOC, engine.ICS]
+    P, iters = 6, 3000
+    aln, mask = synth.random_population(pair, P, seed=32, total=total)
+    e = engine.Engine.from_pair(pair, names, use_goc=True, goc_dense=G)
+    e.upload(aln, mask)
+    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL)
+    rng = np.random.default_rng(33)
+    xy = rng.integers(0, pair.n2, (P, iters, 2)).astype(np.int32)     # any positions, x == y included
+    objs = np.array([-1, 0, 1, 2, 3, -1])
+    acc, nacc = e.hill_climb(xy=xy, objs=objs, want_accepted=True)
+    a, inv, m = e.download()
+    c = e.counters()
+    for p in range(P):
+        o = port.Aln(prob, aln[p], None if mask is None else mask[p])
+        want = o.hill_climb_replay(xy[p], names, obj=int(objs[p]), want_accepted=True)
+        assert np.array_equal(acc[p], want), (group, p)
+        st = o.state()
+        assert np.array_equal(a[p], st[0]) and np.array_equal(inv[p], st[1]) and np.array_equal(m[p], st[2])
+        assert (int(c["cons"][p]), int(c["ind"][p]), float(c["bits"][p]), float(c["goc"][p])) == o.counters()
