@@ -868,7 +868,19 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
         __syncthreads();
         // ---- phase 1b: all warps build the pair masks.  conf[j] bit i (i < j): committing
         //      proposal i would make proposal j's score stale
-        {
+        if (nvalid == kRound) {
+            // full round: the 496 pairs (j > i) folded so that every lane of every step has one --
+            // step f pairs column i = f (lanes j = f+1..31) with column i = 30-f (its f+1 rows
+            // j = 31-f..31 on lanes 0..f); 16 steps instead of 31 half-empty ones
+            for (int f = warp; f < kRound / 2; f += kWarps) {
+                int j = lane, i = f;
+                if (lane <= f) {
+                    j = f < kRound / 2 - 1 ? kRound - 1 - f + lane : -1;
+                    i = kRound - 2 - f;
+                }
+                if (j >= 0 && commit_conflicts(g, s_slot[j], s_slot[i])) atomicOr(&s_conf[j], 1u << i);
+            }
+        } else {
             const int j = lane;
             const RoundSlot& sj = s_slot[j];
             const uint4 u1 = bloom_or(sj.n1x, sj.n1y), u2 = bloom_or(sj.n2x, sj.n2y);
