@@ -76,7 +76,11 @@ typedef struct ona_score_table {
  * fitnessNames vector every computeFitness/correctHillClimb call receives
  * (argParsing.h:212-271 fixes its order).
  *   rowptr/col : CSR of Network::adjList in adjList order (Network.cpp:89-92: a self-loop
- *                is listed once).  Duplicate edge lines are rejected.
+ *                is listed once).  Duplicate edge lines ("a b" and "b a", repeated lines) are
+ *                accepted and keep their copies, as adjList does: the incremental counters
+ *                (conservedCount / inducedCount, :791-826) and fastICSDenominator (:667-690) weigh
+ *                such an edge by its multiplicity while edges.size(), adjMatrix and the set-based
+ *                ics() (:604-661) do not -- mirrored exactly.
  *   num_edges1 : net1->edges.size(), the EC / S3 denominator term (Alignment.cpp:536,541). */
 typedef struct ona_problem {
     int n1, n2; /* |V(net1)| <= |V(net2)| (argParsing.h:207-210) */
@@ -118,7 +122,10 @@ int ona_set_island_offset(ona_engine* e, long long first_global_individual);
  * [count][n2] (a permutation of V2 per row; positions >= n1 are the dummy nodes of
  * Alignment.cpp:25-34), mask is [count][n2] bytes or NULL for all-true (--total).
  * alnInv is rebuilt on the device.  Counters are NOT touched: follow with
- * ona_full_fitness(seed_mode != 0) or ona_pop_set_counters. */
+ * ona_full_fitness(seed_mode != 0) or ona_pop_set_counters.
+ * ona_pop_resize keeps the state of slots [0, min(old, new)) (permutation, mask, counters,
+ * objective rows); slots added by a grow are zero-filled and must be uploaded before any
+ * scoring call touches them.  On allocation failure the old population stays valid. */
 int ona_pop_resize(ona_engine* e, int num_slots);
 int ona_pop_upload(ona_engine* e, int first, int count, const int* aln, const unsigned char* mask);
 int ona_pop_download(ona_engine* e, int first, int count, int* aln, int* aln_inv,
@@ -140,10 +147,13 @@ int ona_pop_get_counters(ona_engine* e, int first, int count, int* conserved, in
  * Alignment::shuf and the constructors (Alignment.cpp:437-446, 43-46, 129-137): sumBLAST
  * (:701-710), sumGOC (:712-722), fastICSDenominator (:667-690), ics() (:604-661), then
  * computeFitness (:559-602).  Outputs are [count] ([count][M] for fitness), any may be NULL:
- * conserved_true = |mapped E1 /\ induced E2|, conserved_refseed = the reference's seed value. */
+ * conserved_true = the exact value of the counter doSwap maintains (|mapped E1 /\ induced E2|;
+ * with duplicate edge lines each edge weighted by its adjList multiplicity), induced =
+ * fastICSDenominator, ics = ics() (ratio of the two edge SETS), conserved_refseed =
+ * (int)(ics * induced), the reference's seed value. */
 int ona_full_fitness(ona_engine* e, int first, int count, int seed_mode, int* conserved_true,
                      int* conserved_refseed, int* induced, double* bitscore, double* goc,
-                     double* size, double* fitness);
+                     double* size, double* fitness, double* ics);
 /* same, nothing leaves the device (results stay in the slots / the device fitness matrix) */
 int ona_full_fitness_dev(ona_engine* e, int first, int count, int seed_mode);
 

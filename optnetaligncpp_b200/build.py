@@ -1,4 +1,5 @@
 """Builds the CUDA engine in-tree: optnetaligncpp_b200/libona_b200.so (sm_100a only)."""
+import glob
 import os
 import shutil
 import subprocess
@@ -7,8 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libona_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "ona_engine.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("ona_device.cuh", "ona_kernels.cuh")] + [
-    os.path.join(ROOT, "include", "ona_b200.h")]
+# every file under csrc/ is a dependency (ona_engine.cu includes all the .cuh headers)
+DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*"))) + [os.path.join(ROOT, "include", "ona_b200.h")]
 
 
 def nvcc_path():

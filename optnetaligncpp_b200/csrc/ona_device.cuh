@@ -70,6 +70,13 @@ struct DevGraph {
     const uint4* sig1;  // same for net1 (hill-climb conflict tests)
     const uint32_t* adj1;  // net1 adjacency bit matrix [n1][W1] (hill-climb conflict tests)
     int W1;
+    // Duplicate edge lines ("a b" + "b a", repeated lines): the reference keeps every copy in
+    // adjList (Network.cpp:89-92), so its incremental counters weigh such an edge by its
+    // multiplicity while `edges`, adjMatrix and the set-based ics() do not.  The CSR / quad CSR
+    // above keep the copies; the unique edge lists carry the multiplicities (null = all 1).
+    const int* ew1;
+    const int* ew2;
+    int dup;  // any duplicate in either network
 };
 
 // BLASTDict / GOCDict on the device: dense fp64 matrix, or an open-addressing hash of the
@@ -296,16 +303,31 @@ constexpr int kSeenXinX = 1, kSeenYinY = 2, kSeenAXinAX = 4, kSeenAYinAX = 8, kS
 //   edge x-y:         cancels (the image pair is only mirrored); y's copy is the `ignore` (:493)
 //   self-loop at a_x: Lx_new - Lx_old;  self-loop at a_y: Ly_new - Ly_old        (:820)
 //   edge a_x-a_y:     (Lx_new & Ly_new) - (Lx_old & Ly_old); a_y's copy is the `ignore` (:495)
+// With duplicate edge lines (g.dup) every term is weighted by how often the list holds the id.
+__device__ __noinline__ int list_multiplicity(const int* rp, const int* col, int row, int id) {
+    int m = 0;
+    for (int k = __ldg(rp + row); k < __ldg(rp + row + 1); ++k) m += __ldg(col + k) == id ? 1 : 0;
+    return m;
+}
 __device__ __forceinline__ void special_terms(const DevGraph& g, const SwapCtx& c, int seen, int& dc,
                                               int& di) {
     if (seen & (kSeenXinX | kSeenYinY)) {
         const int sx = probe(g, c.ax, c.ax), sy = probe(g, c.ay, c.ay);
-        if (seen & kSeenXinX) dc += (c.my & sy) - (c.mx & sx);
-        if (seen & kSeenYinY) dc += (c.mx & sx) - (c.my & sy);
+        const int wx = g.dup && (seen & kSeenXinX) ? list_multiplicity(g.rp1, g.col1, c.x, c.x) : 1;
+        const int wy = g.dup && (seen & kSeenYinY) ? list_multiplicity(g.rp1, g.col1, c.y, c.y) : 1;
+        if (seen & kSeenXinX) dc += wx * ((c.my & sy) - (c.mx & sx));
+        if (seen & kSeenYinY) dc += wy * ((c.mx & sx) - (c.my & sy));
     }
-    if (seen & kSeenAXinAX) di += c.Lx_new - c.Lx_old;
-    if (seen & kSeenAYinAY) di += c.Ly_new - c.Ly_old;
-    if (seen & kSeenAYinAX) di += (c.Lx_new & c.Ly_new) - (c.Lx_old & c.Ly_old);
+    if (!g.dup) {
+        if (seen & kSeenAXinAX) di += c.Lx_new - c.Lx_old;
+        if (seen & kSeenAYinAY) di += c.Ly_new - c.Ly_old;
+        if (seen & kSeenAYinAX) di += (c.Lx_new & c.Ly_new) - (c.Lx_old & c.Ly_old);
+    } else {
+        if (seen & kSeenAXinAX) di += list_multiplicity(g.rp2, g.col2, c.ax, c.ax) * (c.Lx_new - c.Lx_old);
+        if (seen & kSeenAYinAY) di += list_multiplicity(g.rp2, g.col2, c.ay, c.ay) * (c.Ly_new - c.Ly_old);
+        if (seen & kSeenAYinAX)
+            di += list_multiplicity(g.rp2, g.col2, c.ax, c.ay) * ((c.Lx_new & c.Ly_new) - (c.Lx_old & c.Ly_old));
+    }
 }
 
 // The (up to) four quad lists of one candidate as one index space [0, e3):

@@ -110,9 +110,14 @@ int upload(ona_engine* e, const std::vector<V>& h, const V** out) {
     return ONA_OK;
 }
 
-int check_csr(const char* what, int n, const int* rp, const int* col, int ncols) {
+// Duplicate adjacency entries are legal: the reference pushes every edge line into adjList
+// (Network.cpp:89-92) and only its `edges` set and adjMatrix de-duplicate, so "a b" + "b a" or a
+// repeated line makes the adjList-based counters count that edge with its multiplicity.
+// *has_dups reports whether any row lists a column more than once.
+int check_csr(const char* what, int n, const int* rp, const int* col, int ncols, bool* has_dups) {
     if (!rp || !col) return fail(ONA_ERR_INVALID, std::string(what) + ": null CSR");
     if (rp[0] != 0) return fail(ONA_ERR_INVALID, std::string(what) + ": rowptr[0] != 0");
+    *has_dups = false;
     std::vector<int> row;
     for (int u = 0; u < n; ++u) {
         if (rp[u + 1] < rp[u]) return fail(ONA_ERR_INVALID, std::string(what) + ": rowptr not monotone");
@@ -120,24 +125,33 @@ int check_csr(const char* what, int n, const int* rp, const int* col, int ncols)
         std::sort(row.begin(), row.end());
         for (size_t k = 0; k < row.size(); ++k) {
             if (row[k] < 0 || row[k] >= ncols)
-                return fail(ONA_ERR_INVALID, std::string(what) + ": column id out of range");
-            if (k && row[k] == row[k - 1])
-                return fail(ONA_ERR_INVALID, std::string(what) +
-                                                 ": duplicate edge (the reference's adjList-based "
-                                                 "counters and set-based ics() disagree on such input)");
+                return fail(ONA_ERR_INVALID, std::string(what) + ": column id out of range in row " +
+                                                 std::to_string(u));
+            if (k && row[k] == row[k - 1]) *has_dups = true;
         }
     }
     return ONA_OK;
 }
 
-// unique undirected edges (u <= v) of a symmetric adjList CSR
-void unique_edges(int n, const int* rp, const int* col, std::vector<int>& eu, std::vector<int>& ev) {
+// unique undirected edges (u <= v) of a symmetric adjList CSR, in adjList order of their first
+// appearance; ew[k] = how many times row u lists v (all 1 without duplicate edge lines)
+void unique_edges(int n, const int* rp, const int* col, std::vector<int>& eu, std::vector<int>& ev,
+                  std::vector<int>& ew) {
+    std::vector<int> seen_at(n, -1), slot(n, 0);
     for (int u = 0; u < n; ++u)
-        for (int k = rp[u]; k < rp[u + 1]; ++k)
-            if (col[k] >= u) {
-                eu.push_back(u);
-                ev.push_back(col[k]);
+        for (int k = rp[u]; k < rp[u + 1]; ++k) {
+            const int v = col[k];
+            if (v < u) continue;
+            if (seen_at[v] == u) {
+                ew[slot[v]]++;
+                continue;
             }
+            seen_at[v] = u;
+            slot[v] = (int)eu.size();
+            eu.push_back(u);
+            ev.push_back(v);
+            ew.push_back(1);
+        }
 }
 
 // BLASTDict/GOCDict -> device table.  Sparse tables (density < 1/16) become an
@@ -183,21 +197,18 @@ int build_table(ona_engine* e, const ona_score_table& t, int n1, int n2, DevTabl
     }
     if (!t.dense && !(t.rows && t.cols && t.vals)) return ONA_OK;
     const size_t cells = (size_t)n1 * (size_t)n2;
-    std::vector<unsigned long long> keys;
-    std::vector<double> vals;
+    // count the non-zeros first: a dense table (GOC: ~20 % non-zero) must not be copied into
+    // 16-byte (key, value) pairs on the host just to find out that it stays dense
+    size_t nnz = 0;
     if (t.dense) {
-        for (size_t i = 0; i < cells; ++i)
-            if (t.dense[i] != 0.0) {
-                keys.push_back(i);
-                vals.push_back(t.dense[i]);
-            }
+        for (size_t i = 0; i < cells; ++i) nnz += t.dense[i] != 0.0 ? 1 : 0;
     } else {
         for (long long k = 0; k < t.nnz; ++k) {
             if (t.rows[k] < 0 || t.rows[k] >= n1 || t.cols[k] < 0 || t.cols[k] >= n2)
                 return fail(ONA_ERR_INVALID, "score table: index out of range");
         }
+        nnz = (size_t)t.nnz;
     }
-    const size_t nnz = t.dense ? keys.size() : (size_t)t.nnz;
     if (nnz * 16 >= cells) {  // dense on the device
         std::vector<double> h;
         const double* src = t.dense;
@@ -235,9 +246,10 @@ int build_table(ona_engine* e, const ona_score_table& t, int n1, int n2, DevTabl
             h = (h + 1) & (cap - 1);
         }
     };
-    if (t.dense)
-        for (size_t k = 0; k < keys.size(); ++k) put(keys[k], vals[k]);
-    else
+    if (t.dense) {
+        for (size_t i = 0; i < cells; ++i)
+            if (t.dense[i] != 0.0) put(i, t.dense[i]);
+    } else
         for (long long k = 0; k < t.nnz; ++k)
             put((unsigned long long)t.rows[k] * (unsigned long long)n2 + (unsigned long long)t.cols[k], t.vals[k]);
     std::vector<uint4> rowsig(n1, make_uint4(0, 0, 0, 0));
@@ -405,6 +417,9 @@ void free_pop(ona_engine* e) {
 }  // namespace
 
 #define LOCK(e) std::lock_guard<std::mutex> _lk((e)->mu); cudaSetDevice((e)->device)
+// null check + engine mutex: every argument check that reads engine state (population size,
+// objective count) runs under the lock, so resize / set_objectives from other threads cannot race it
+#define ENTER(e) if (!(e)) return fail(ONA_ERR_INVALID, "null engine"); LOCK(e)
 #define TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
 extern "C" {
@@ -442,8 +457,9 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
         return fail(ONA_ERR_INVALID, "need 1..10 objectives");
     for (int j = 0; j < pr->num_objectives; ++j)
         if (pr->objectives[j] < 0 || pr->objectives[j] > 9) return fail(ONA_ERR_INVALID, "unknown objective id");
-    TRY(check_csr("net1", pr->n1, pr->rowptr1, pr->col1, pr->n1));
-    TRY(check_csr("net2", pr->n2, pr->rowptr2, pr->col2, pr->n2));
+    bool dups1 = false, dups2 = false;
+    TRY(check_csr("net1", pr->n1, pr->rowptr1, pr->col1, pr->n1, &dups1));
+    TRY(check_csr("net2", pr->n2, pr->rowptr2, pr->col2, pr->n2, &dups2));
 
     CU(cudaSetDevice(device));
     ona_engine* e = new ona_engine();
@@ -485,17 +501,21 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
         if ((rc = upload<uint32_t>(e, bits, &g.adj2))) return bail(rc);
     }
     {
-        std::vector<int> eu, ev;
-        unique_edges(pr->n1, pr->rowptr1, pr->col1, eu, ev);
+        std::vector<int> eu, ev, ew;
+        unique_edges(pr->n1, pr->rowptr1, pr->col1, eu, ev, ew);
         g.ne1 = (int)eu.size();
         if ((rc = upload<int>(e, eu, &g.eu1))) return bail(rc);
         if ((rc = upload<int>(e, ev, &g.ev1))) return bail(rc);
+        if (dups1 && (rc = upload<int>(e, ew, &g.ew1))) return bail(rc);
         eu.clear();
         ev.clear();
-        unique_edges(pr->n2, pr->rowptr2, pr->col2, eu, ev);
+        ew.clear();
+        unique_edges(pr->n2, pr->rowptr2, pr->col2, eu, ev, ew);
         g.ne2 = (int)eu.size();
         if ((rc = upload<int>(e, eu, &g.eu2))) return bail(rc);
         if ((rc = upload<int>(e, ev, &g.ev2))) return bail(rc);
+        if (dups2 && (rc = upload<int>(e, ew, &g.ew2))) return bail(rc);
+        g.dup = (dups1 || dups2) ? 1 : 0;
     }
     for (int net = 0; net < 2; ++net) {  // quad-padded CSR (rows padded with -1 to multiples of 4)
         const int n = net ? pr->n2 : pr->n1;
@@ -625,7 +645,7 @@ int ona_synchronize(ona_engine* e) {
 long long ona_kernel_launches(const ona_engine* e) { return e ? e->launches : 0; }
 
 int ona_set_island_offset(ona_engine* e, long long off) {
-    if (!e) return fail(ONA_ERR_INVALID, "null engine");
+    ENTER(e);
     e->island_offset = off;
     return ONA_OK;
 }
@@ -658,34 +678,52 @@ int ona_pop_resize(ona_engine* e, int P) {
     LOCK(e);
     CU(cudaStreamSynchronize(e->stream));
     if (P == e->P) return ONA_OK;
-    free_pop(e);
-    if (P == 0) return ONA_OK;
+    if (P == 0) {
+        free_pop(e);
+        return ONA_OK;
+    }
+    // slots [0, min(old, new)) keep their state (aln, inv, counters, objectives); new slots are
+    // zero-filled and must be uploaded before use
     const size_t row = (size_t)e->pop.n2p;
-    CU(cudaMalloc(&e->pop.aln, (size_t)P * row * 4));
-    CU(cudaMalloc(&e->pop.inv, (size_t)P * row * 4));
-    CU(cudaMalloc(&e->pop.cons, (size_t)P * 4));
-    CU(cudaMalloc(&e->pop.ind, (size_t)P * 4));
-    CU(cudaMalloc(&e->pop.size, (size_t)P * 4));
-    CU(cudaMalloc(&e->pop.bits, (size_t)P * 8));
-    CU(cudaMalloc(&e->pop.goc, (size_t)P * 8));
-    CU(cudaMalloc(&e->pop.fit, (size_t)P * e->ob.M * 8));
-    CU(cudaMemsetAsync(e->pop.aln, 0, (size_t)P * row * 4, e->stream));
-    CU(cudaMemsetAsync(e->pop.inv, 0, (size_t)P * row * 4, e->stream));
-    CU(cudaMemsetAsync(e->pop.cons, 0, (size_t)P * 4, e->stream));
-    CU(cudaMemsetAsync(e->pop.ind, 0, (size_t)P * 4, e->stream));
-    CU(cudaMemsetAsync(e->pop.size, 0, (size_t)P * 4, e->stream));
-    CU(cudaMemsetAsync(e->pop.bits, 0, (size_t)P * 8, e->stream));
-    CU(cudaMemsetAsync(e->pop.goc, 0, (size_t)P * 8, e->stream));
-    CU(cudaMemsetAsync(e->pop.fit, 0, (size_t)P * e->ob.M * 8, e->stream));
+    const int keep = std::min(P, e->P);
+    DevPop np = e->pop;
+    np.aln = np.inv = nullptr;
+    np.cons = np.ind = np.size = nullptr;
+    np.bits = np.goc = np.fit = nullptr;
+    auto grow = [&](auto** dst, auto* src, size_t per) -> cudaError_t {
+        cudaError_t ce = cudaMalloc(dst, (size_t)P * per);
+        if (ce != cudaSuccess) return ce;
+        if ((ce = cudaMemsetAsync(*dst, 0, (size_t)P * per, e->stream)) != cudaSuccess) return ce;
+        if (keep && src) ce = cudaMemcpyAsync(*dst, src, (size_t)keep * per, cudaMemcpyDeviceToDevice, e->stream);
+        return ce;
+    };
+    cudaError_t ce = cudaSuccess;
+    if (ce == cudaSuccess) ce = grow(&np.aln, e->pop.aln, row * 4);
+    if (ce == cudaSuccess) ce = grow(&np.inv, e->pop.inv, row * 4);
+    if (ce == cudaSuccess) ce = grow(&np.cons, e->pop.cons, 4);
+    if (ce == cudaSuccess) ce = grow(&np.ind, e->pop.ind, 4);
+    if (ce == cudaSuccess) ce = grow(&np.size, e->pop.size, 4);
+    if (ce == cudaSuccess) ce = grow(&np.bits, e->pop.bits, 8);
+    if (ce == cudaSuccess) ce = grow(&np.goc, e->pop.goc, 8);
+    if (ce == cudaSuccess) ce = grow(&np.fit, e->pop.fit, (size_t)e->ob.M * 8);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) {  // the old population stays valid
+        cudaFree(np.aln); cudaFree(np.inv); cudaFree(np.cons); cudaFree(np.ind);
+        cudaFree(np.size); cudaFree(np.bits); cudaFree(np.goc); cudaFree(np.fit);
+        return fail(ce == cudaErrorMemoryAllocation ? ONA_ERR_NOMEM : ONA_ERR_CUDA,
+                    std::string("ona_pop_resize: ") + cudaGetErrorString(ce));
+    }
+    free_pop(e);
+    e->pop = np;
     e->P = P;
     return ONA_OK;
 }
 
 int ona_pop_upload(ona_engine* e, int first, int count, const int* aln, const unsigned char* mask) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (!aln) return fail(ONA_ERR_INVALID, "null aln");
     if (count == 0) return ONA_OK;
-    LOCK(e);
     const int n2 = e->g.n2;
     const size_t n = (size_t)count * n2;
     for (size_t i = 0; i < n; ++i)
@@ -713,9 +751,9 @@ int ona_pop_upload(ona_engine* e, int first, int count, const int* aln, const un
 }
 
 int ona_pop_download(ona_engine* e, int first, int count, int* aln, int* aln_inv, unsigned char* mask) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (count == 0) return ONA_OK;
-    LOCK(e);
     const int n2 = e->g.n2;
     const size_t n = (size_t)count * n2;
     CU(e->t_xy.need(n));
@@ -734,9 +772,9 @@ int ona_pop_download(ona_engine* e, int first, int count, int* aln, int* aln_inv
 
 int ona_pop_set_counters(ona_engine* e, int first, int count, const int* cons, const int* ind,
                          const double* bits, const double* goc) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (count == 0) return ONA_OK;
-    LOCK(e);
     TRY(h2d(e, e->pop.cons + first, cons, (size_t)count));
     TRY(h2d(e, e->pop.ind + first, ind, (size_t)count));
     TRY(h2d(e, e->pop.bits + first, bits, (size_t)count));
@@ -750,9 +788,9 @@ int ona_pop_set_counters(ona_engine* e, int first, int count, const int* cons, c
 
 int ona_pop_get_counters(ona_engine* e, int first, int count, int* cons, int* ind, double* bits,
                          double* goc, double* size, double* fitness) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (count == 0) return ONA_OK;
-    LOCK(e);
     TRY(d2h(e, cons, e->pop.cons + first, (size_t)count));
     TRY(d2h(e, ind, e->pop.ind + first, (size_t)count));
     TRY(d2h(e, bits, e->pop.bits + first, (size_t)count));
@@ -778,23 +816,24 @@ static int full_fitness_impl(ona_engine* e, int first, int count, int seed_mode,
 }
 
 int ona_full_fitness_dev(ona_engine* e, int first, int count, int seed_mode) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (count == 0) return ONA_OK;
-    LOCK(e);
     FullOut out{};
     return full_fitness_impl(e, first, count, seed_mode, out);
 }
 
 int ona_full_fitness(ona_engine* e, int first, int count, int seed_mode, int* cons_true,
                      int* cons_ref, int* ind, double* bits, double* goc, double* size,
-                     double* fitness) {
+                     double* fitness, double* ics) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (count == 0) return ONA_OK;
-    LOCK(e);
     const size_t n = (size_t)count;
     CU(e->t_i0.need(n)); CU(e->t_i1.need(n)); CU(e->t_i2.need(n));
     CU(e->t_d0.need(n)); CU(e->t_d1.need(n)); CU(e->t_d2.need(n)); CU(e->t_d3.need(n * e->ob.M));
-    FullOut out{e->t_i0.p, e->t_i1.p, e->t_i2.p, e->t_d0.p, e->t_d1.p, e->t_d2.p, e->t_d3.p};
+    CU(e->t_d4.need(n));
+    FullOut out{e->t_i0.p, e->t_i1.p, e->t_i2.p, e->t_d0.p, e->t_d1.p, e->t_d2.p, e->t_d3.p, e->t_d4.p};
     TRY(full_fitness_impl(e, first, count, seed_mode, out));
     TRY(d2h(e, cons_true, e->t_i0.p, n));
     TRY(d2h(e, cons_ref, e->t_i1.p, n));
@@ -803,6 +842,7 @@ int ona_full_fitness(ona_engine* e, int first, int count, int seed_mode, int* co
     TRY(d2h(e, goc, e->t_d1.p, n));
     TRY(d2h(e, size, e->t_d2.p, n));
     TRY(d2h(e, fitness, e->t_d3.p, n * e->ob.M));
+    TRY(d2h(e, ics, e->t_d4.p, n));
     CU(cudaStreamSynchronize(e->stream));
     return ONA_OK;
 }
@@ -810,13 +850,13 @@ int ona_full_fitness(ona_engine* e, int first, int count, int seed_mode, int* co
 int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, int obj, int* cons,
                     int* ind, double* bits, double* goc, double* fitness, unsigned char* improved,
                     double* snd) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (!xy || K < 0) return fail(ONA_ERR_INVALID, "null proposals");
     if (obj < -1 || obj >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
     if (count == 0 || K == 0) return ONA_OK;
     const size_t n = (size_t)count * K;
     const int M = e->ob.M;
-    LOCK(e);
     CU(e->t_xy.need(2 * n));
     CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
     DevDeltaOut out{};
@@ -872,11 +912,11 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
 
 int ona_swap_deltas_rng(ona_engine* e, int first, int count, int K, unsigned long long seed, int obj,
                         int* num_improved, double* best_snd, int* best_xy) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (K < 0) return fail(ONA_ERR_INVALID, "K < 0");
     if (obj < -1 || obj >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
     if (count == 0 || K == 0) return ONA_OK;
-    LOCK(e);
     const int chunks = pick_chunks(e, count, K);
     DevDeltaOut out{};
     DeltaSummary sum{};
@@ -929,11 +969,11 @@ int ona_swap_deltas_dev(ona_engine* e, int first, int count, int K, const int* x
                         unsigned long long seed, int obj, int* cons_dev, int* ind_dev,
                         double* bits_dev, double* goc_dev, double* fit_dev,
                         unsigned char* improved_dev, double* snd_dev, int* num_improved_dev) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (K < 0) return fail(ONA_ERR_INVALID, "K < 0");
     if (obj < -1 || obj >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
     if (count == 0 || K == 0) return ONA_OK;
-    LOCK(e);
     DevDeltaOut out{cons_dev, ind_dev, bits_dev, goc_dev, fit_dev, improved_dev, snd_dev};
     DeltaSummary sum{};
     sum.num_improved = num_improved_dev;
@@ -941,8 +981,8 @@ int ona_swap_deltas_dev(ona_engine* e, int first, int count, int K, const int* x
 }
 
 int ona_steepest_step(ona_engine* e, int slot, double* best_delta, int* best_x, int* best_y) {
+    ENTER(e);
     TRY(check_range(e, slot, 1));
-    LOCK(e);
     const int n1 = e->g.n1, n2 = e->g.n2;
     const int slab = std::max(1, std::min(n1, (1 << 28) / n2));  // rows of the grid per launch
     double bv = -1.0;  // localSearch.cpp:134,141: bestDelta starts at -1 and only a larger value wins
@@ -981,10 +1021,10 @@ int ona_steepest_step(ona_engine* e, int slot, double* best_delta, int* best_x, 
 
 int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long long seed,
                       long long start, int* xy) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (!xy || K < 0) return fail(ONA_ERR_INVALID, "null output");
     if (count == 0 || K == 0) return ONA_OK;
-    LOCK(e);
     const size_t n = (size_t)count * K;
     CU(e->t_xy.need(2 * n));
     k_rng_proposals<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->g.n1, e->g.n2, count, K, seed,
@@ -999,6 +1039,7 @@ int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long 
 int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const int* xy,
                    unsigned long long seed, const int* objs, unsigned char* accepted,
                    long long* num_accepted) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (iters < 0) return fail(ONA_ERR_INVALID, "iters < 0");
     if (count == 0 || iters == 0) {
@@ -1009,7 +1050,6 @@ int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const i
         for (int i = 0; i < count; ++i)
             if (objs[i] < -1 || objs[i] >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
     const size_t n = (size_t)count * (size_t)iters;
-    LOCK(e);
     CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
     const int* xy_dev = nullptr;
     if (xy) {
@@ -1037,6 +1077,7 @@ int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const i
 
 int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters, const int* xy,
                            unsigned long long seed, const int* objs, long long* num_applied) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (iters < 0) return fail(ONA_ERR_INVALID, "iters < 0");
     if (count == 0 || iters == 0) {
@@ -1047,7 +1088,6 @@ int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters,
         for (int i = 0; i < count; ++i)
             if (objs[i] < -1 || objs[i] >= e->ob.M) return fail(ONA_ERR_INVALID, "objective index out of range");
     const size_t n = (size_t)count * (size_t)iters;
-    LOCK(e);
     CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
     const int* xy_dev = nullptr;
     if (xy) {
@@ -1089,11 +1129,11 @@ int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters,
 }
 
 int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* xy) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (!xy || nswaps < 0) return fail(ONA_ERR_INVALID, "null swap list");
     if (count == 0 || nswaps == 0) return ONA_OK;
     const size_t n = (size_t)count * nswaps;
-    LOCK(e);
     CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
     CU(e->t_xy.need(2 * n));
     TRY(h2d(e, e->t_xy.p, xy, 2 * n));
@@ -1102,11 +1142,11 @@ int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* 
 }
 
 int ona_apply_edits(ona_engine* e, int first, int count, int nops, const int* ops) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (!ops || nops < 0) return fail(ONA_ERR_INVALID, "null edit list");
     if (count == 0 || nops == 0) return ONA_OK;
     const size_t n = (size_t)count * nops;
-    LOCK(e);
     CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
     CU(e->t_xy.need(4 * n));
     TRY(h2d(e, e->t_xy.p, ops, 4 * n));
@@ -1120,10 +1160,10 @@ int ona_apply_edits(ona_engine* e, int first, int count, int nops, const int* op
 }
 
 int ona_export_fitness_dev(ona_engine* e, int first, int count, double* dst_dev) {
+    ENTER(e);
     TRY(check_range(e, first, count));
     if (!dst_dev) return fail(ONA_ERR_INVALID, "null destination");
     if (count == 0) return ONA_OK;
-    LOCK(e);
     CU(cudaMemcpyAsync(dst_dev, e->pop.fit + (size_t)first * e->ob.M, (size_t)count * e->ob.M * 8,
                        cudaMemcpyDeviceToDevice, e->stream));
     return ONA_OK;

@@ -113,6 +113,9 @@ __device__ __forceinline__ V block_sum(V v, V* scratch) {
 //   bits / goc = sum_{i<n1, mask[i]} S[i][aln[i]]                            sumBLAST/sumGOC :701-722
 //   size       = #{i<n1 : mask[i]}                                           alnSize :724-732
 //   refseed    = (int)((C/I)*I)                                              :444-446  (hazard H1)
+// With duplicate edge lines (g.ew1 / g.ew2) the set-based ics() and the adjList-based
+// fastICSDenominator part ways: conserved / induced above are reported with multiplicities (what
+// the incremental counters track), ics = |set conserved| / |set induced|, refseed = (int)(ics * induced).
 // The individual's packed aln/inv are staged in shared memory once and gathered from there.
 // --------------------------------------------------------------------------------
 struct FullOut {
@@ -123,11 +126,12 @@ struct FullOut {
     double* goc;
     double* size;
     double* fit;
+    double* ics;
 };
 
 // partial results of one part of one individual, reduced by the last part to finish
 struct FullPartial {
-    int c, ind, sz, pad;
+    int c, ind, sz, cset, iset, pad;   // cset / iset: set-based counts (== c / ind without duplicate edges)
     double sb, sg;
 };
 
@@ -150,22 +154,30 @@ k_full_fitness(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop
     State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
     __syncthreads();
 
-    int c = 0, ind = 0, sz = 0;
+    int c = 0, ind = 0, sz = 0, cset = 0, iset = 0;
     {
         const int lo = (int)((long long)g.ne1 * part / parts), hi = (int)((long long)g.ne1 * (part + 1) / parts);
 #pragma unroll 4
         for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
             const uint32_t ru = s_aln[__ldg(g.eu1 + e)], rv = s_aln[__ldg(g.ev1 + e)];
-            if (!((ru | rv) & FLAG)) c += probe(g, (int)(ru & MASK), (int)(rv & MASK));
+            if (!((ru | rv) & FLAG)) {
+                const int hit = probe(g, (int)(ru & MASK), (int)(rv & MASK));
+                cset += hit;
+                if (g.ew1) c += hit * __ldg(g.ew1 + e);
+            }
         }
+        if (!g.ew1) c = cset;
     }
     {
         const int lo = (int)((long long)g.ne2 * part / parts), hi = (int)((long long)g.ne2 * (part + 1) / parts);
 #pragma unroll 4
         for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
             const uint32_t iu = s_inv[__ldg(g.eu2 + e)], iv = s_inv[__ldg(g.ev2 + e)];
-            ind += (iu < (uint32_t)g.n1 && iv < (uint32_t)g.n1) ? 1 : 0;
+            const int hit = (iu < (uint32_t)g.n1 && iv < (uint32_t)g.n1) ? 1 : 0;
+            iset += hit;
+            if (g.ew2) ind += hit * __ldg(g.ew2 + e);
         }
+        if (!g.ew2) ind = iset;
     }
     double sb = 0.0, sg = 0.0;
     double* seq_b = seq_scratch ? seq_scratch + (size_t)pl * 2 * g.n1 : nullptr;
@@ -194,11 +206,18 @@ k_full_fitness(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop
     c = block_sum<int>(c, red_i);
     ind = block_sum<int>(ind, red_i);
     sz = block_sum<int>(sz, red_i);
+    if (g.dup) {
+        cset = block_sum<int>(cset, red_i);
+        iset = block_sum<int>(iset, red_i);
+    } else {
+        cset = c;
+        iset = ind;
+    }
     sb = block_sum<double>(sb, red_d);
     sg = block_sum<double>(sg, red_d);
     if (threadIdx.x == 0) {
         FullPartial fp;
-        fp.c = c; fp.ind = ind; fp.sz = sz; fp.pad = 0; fp.sb = sb; fp.sg = sg;
+        fp.c = c; fp.ind = ind; fp.sz = sz; fp.cset = cset; fp.iset = iset; fp.pad = 0; fp.sb = sb; fp.sg = sg;
         partials[(size_t)pl * parts + part] = fp;
         __threadfence();
         s_last = atomicAdd(tickets + pl, 1u) == (unsigned)(parts - 1);
@@ -221,16 +240,17 @@ k_full_fitness(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop
     }
     if (threadIdx.x == 0) {
         tickets[pl] = 0;  // ready for the next launch
-        c = 0; ind = 0; sz = 0; sb = 0.0; sg = 0.0;
+        c = 0; ind = 0; sz = 0; cset = 0; iset = 0; sb = 0.0; sg = 0.0;
         const volatile FullPartial* fp = partials + (size_t)pl * parts;
         for (int q = 0; q < parts; ++q) {
-            c += fp[q].c; ind += fp[q].ind; sz += fp[q].sz;
+            c += fp[q].c; ind += fp[q].ind; sz += fp[q].sz; cset += fp[q].cset; iset += fp[q].iset;
             sb += fp[q].sb; sg += fp[q].sg;
         }
         if (sequential) { sb = s_seq[0]; sg = s_seq[1]; }
-        // currConservedCount = ics()*denom, truncated (Alignment.cpp:445); ics()==0 when denom==0
+        // ics() is the ratio of the two edge SETS (:604-661; 0 when the induced set is empty);
+        // currConservedCount = ics()*denom, truncated (:445), denom = fastICSDenominator (adjList-based)
         const double denom = (double)ind;
-        const double ics = denom == 0.0 ? 0.0 : __ddiv_rn((double)c, denom);
+        const double ics = iset == 0 ? 0.0 : __ddiv_rn((double)cset, (double)iset);
         const int cref = __double2int_rz(__dmul_rn(ics, denom));
         Scalars s;
         s.C = (seed_mode == 2) ? cref : c;
@@ -256,6 +276,7 @@ k_full_fitness(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop
         if (out.bits) out.bits[pl] = sb;
         if (out.goc) out.goc[pl] = sg;
         if (out.size) out.size[pl] = (double)sz;
+        if (out.ics) out.ics[pl] = ics;
     }
 }
 
@@ -708,7 +729,9 @@ struct RoundSlot {
 // Brings the delta (dc, di) of a LATER proposal (xj, yj) that shares no position with it up to date
 // without walking its lists again: in the lists of xj / yj only the items t = u and t = w changed
 // (they traded image and mask bit), in the lists of a_xj / a_yj only the images a_u, a_w (they
-// traded pre-images).  With D(v) = my*A2[a_yj][v] - mx*A2[a_xj][v] (the item term of quad_item):
+// traded pre-images).  Adjacency BITS stand for list membership here, so this is only used on
+// graphs without duplicate edge lines (g.dup == 0; with duplicates the proposal is re-scored).
+// With D(v) = my*A2[a_yj][v] - mx*A2[a_xj][v] (the item term of quad_item):
 //   dc += ([u in N1(xj)] - [w in N1(xj)] - [u in N1(yj)] + [w in N1(yj)]) * (m_w*D(a_w) - m_u*D(a_u))
 //   di += sum over v in {a_u, a_w}, list owner o in {a_xj, a_yj}:  coef_o * A2[o][v] * (alive'(v) - alive(v))
 template <typename T>
@@ -989,7 +1012,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     bool stale_row = false, corrected = false;
                     for (unsigned m = conf & commit & lt_mask; m; m &= m - 1u) {
                         const RoundSlot& si = s_slot[__ffs(m) - 1];
-                        if ((x == si.x) | (x == si.y) | (y == si.x) | (y == si.y)) stale_row = true;
+                        if ((x == si.x) | (x == si.y) | (y == si.x) | (y == si.y) | (g.dup != 0)) stale_row = true;
                         else { correct_delta<T>(g, s_aln, x, y, si.x, si.y, si.orx, si.ory, dc, di); corrected = true; }
                     }
                     dirty_mask |= __ballot_sync(0xffffffffu, stale_row) & vmask;
@@ -1024,7 +1047,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
                     __syncwarp();
                     bool stale_row = false;
                     if (((conf >> e) & 1u) != 0u && c > e) {
-                        if ((x == xe) | (x == ye) | (y == xe) | (y == ye)) stale_row = true;
+                        if ((x == xe) | (x == ye) | (y == xe) | (y == ye) | (g.dup != 0)) stale_row = true;
                         else correct_delta<T>(g, s_aln, x, y, xe, ye, ru, rw, dc, di);
                     }
                     dirty_mask |= __ballot_sync(0xffffffffu, stale_row) & vmask;

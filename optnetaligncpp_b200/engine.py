@@ -87,7 +87,7 @@ def load_library(build_if_missing=True):
     L.ona_pop_download.argtypes = [vp, ci, ci, vp, vp, vp]
     L.ona_pop_set_counters.argtypes = [vp, ci, ci, vp, vp, vp, vp]
     L.ona_pop_get_counters.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp]
-    L.ona_full_fitness.argtypes = [vp, ci, ci, ci] + [vp] * 7
+    L.ona_full_fitness.argtypes = [vp, ci, ci, ci] + [vp] * 8
     L.ona_full_fitness_dev.argtypes = [vp, ci, ci, ci]
     L.ona_swap_deltas.argtypes = [vp, ci, ci, ci, vp, ci] + [vp] * 7
     L.ona_swap_deltas_rng.argtypes = [vp, ci, ci, ci, C.c_ulonglong, ci, vp, vp, vp]
@@ -209,10 +209,13 @@ class Engine:
 
     # ---- population
     def resize(self, P):
+        """ona_pop_resize: slots below min(old, new) keep their state, new slots are empty."""
         self._check(self.L.ona_pop_resize(self.h, int(P)))
         self.P = int(P)
 
     def upload(self, aln, mask=None, first=0):
+        """ona_pop_upload into slots first..first+len(aln); grows the population when the range
+        ends beyond it (slots uploaded earlier keep their state)."""
         aln = _i32(aln).reshape(-1, self.n2)
         if first + len(aln) > self.P:
             self.resize(first + len(aln))
@@ -250,10 +253,10 @@ class Engine:
         r = dict(cons_true=np.empty(count, np.int32), cons_ref=np.empty(count, np.int32),
                  ind=np.empty(count, np.int32), bits=np.empty(count, np.float64),
                  goc=np.empty(count, np.float64), size=np.empty(count, np.float64),
-                 fit=np.empty((count, self.M), np.float64))
+                 fit=np.empty((count, self.M), np.float64), ics=np.empty(count, np.float64))
         self._check(self.L.ona_full_fitness(self.h, first, count, seed_mode, _ptr(r["cons_true"]),
                                             _ptr(r["cons_ref"]), _ptr(r["ind"]), _ptr(r["bits"]),
-                                            _ptr(r["goc"]), _ptr(r["size"]), _ptr(r["fit"])))
+                                            _ptr(r["goc"]), _ptr(r["size"]), _ptr(r["fit"]), _ptr(r["ics"])))
         return r
 
     def full_fitness_dev(self, first=0, count=None, seed_mode=SEED_REFCOMPAT):

@@ -90,9 +90,10 @@ Alignment::Alignment(const Network* n1, const Network* n2, string filename, cons
 
 // Alignment.cpp:152-256 -- UPMX crossover.  The child starts as parent 1; for every index i
 // chosen with probability cxswappb it takes parent 2's image and the displaced image moves to
-// where that image was: under --total exactly doSwap(i, alnInv[par2.aln[i]]) (:197-252), so
-// the ordered swap list is built on the host (it needs only the two permutations and the
-// PRNG) and applied on the GPU with incremental counter updates.
+// where that image was (:197-252).  With every mask bit on that is exactly
+// doSwap(i, alnInv[par2.aln[i]]), so the ordered swap list is built on the host (it needs only
+// the two permutations and the PRNG) and applied on the GPU with incremental counter updates;
+// otherwise the step list is replayed by ona_apply_edits (ONA_EDIT_CROSS).
 Alignment::Alignment(RandGenT& prng, float cxswappb, const Alignment& p1, const Alignment& p2, bool total) {
     uniform_int_distribution<int> coinFlip(0, 1);
     uniform_real_distribution<float> fltgen(0.0, 1.0);
@@ -110,7 +111,22 @@ Alignment::Alignment(RandGenT& prng, float cxswappb, const Alignment& p1, const 
     currConservedCount = par1->currConservedCount; currInducedCount = par1->currInducedCount;
 
     const int size = (int)aln.size();
-    if (total) {
+    // Under --total the reference leaves the mask bits where they are (the mask writes sit behind
+    // `if(!total)`, :219-227), whereas doSwap exchanges them (:502-504): the two only coincide when
+    // every bit of parent 1 is on.  A greedyMatch individual (--total --seeding) or a loaded partial
+    // alignment has bits off, so those parents take the edit path with the `total` flag set.
+    const bool allOn = find(alnMask.begin(), alnMask.end(), false) == alnMask.end();
+    if (total && !allOn) {
+        vector<int> ops;
+        for (int i = 0; i < size; i++) {
+            if (!(fltgen(prng) < cxswappb)) continue;   // no coin flip under --total (:222)
+            ops.push_back(ONA_EDIT_CROSS);
+            ops.push_back(i);
+            ops.push_back(par2->aln[i]);
+            ops.push_back((par2->alnMask[i] ? 1 : 0) | 4);
+        }
+        ona_host::apply_edits(*this, ops);
+    } else if (total) {
         vector<node> a = aln, inv = alnInv;   // scratch copies that track the running permutation
         vector<int> swaps;
         for (int i = 0; i < size; i++) {
@@ -286,11 +302,8 @@ void Alignment::computeFitness(const vector<fitnessName>& fitnessNames) {
     fitnessValid = true;
 }
 
-// Alignment.cpp:604-661 -- set-based ICS: exact conserved / exact induced, both on the GPU
-double Alignment::ics() const {
-    const ona_host::Scratch s = ona_host::score_from_scratch(*this);
-    return s.induced == 0 ? 0.0 : double(s.cons_true) / double(s.induced);
-}
+// Alignment.cpp:604-661 -- set-based ICS: |conserved edge set| / |induced edge set|, counted on the GPU
+double Alignment::ics() const { return ona_host::score_from_scratch(*this).ics; }
 // Alignment.cpp:667-690
 double Alignment::fastICSDenominator() const { return double(ona_host::score_from_scratch(*this).induced); }
 // Alignment.cpp:701-722 (index-order fp64 sums)

@@ -179,6 +179,13 @@ int main(int argc, char** argv) {
             Alignment gm(net1, net2, bit, goc);
             gm.greedyMatch(true);
             report("greedy", gm);
+            // --total --seeding: a greedyMatch individual (mask bits off on every position >= n1)
+            // as a crossover parent; the reference leaves the mask bits in place under --total
+            for (int v = 0; v < 4; v++) {
+                RandGenT cg(seed + 9700 + v);
+                Alignment gchild(cg, 0.3f, gm, *alns[0], true);
+                report("gcx", gchild);
+            }
         }
         for (int v = 0; v < 2; v++) {
             RandGenT g(seed + 9500 + v);

@@ -138,7 +138,7 @@ Scratch score_from_scratch(const Alignment& a) {
     check(ona_pop_upload(c.engine(), 0, 1, aln.data(), any_off ? mask.data() : nullptr));
     Scratch s{};
     check(ona_full_fitness(c.engine(), 0, 1, ONA_SEED_NONE | ONA_SUM_SEQUENTIAL, &s.cons_true, &s.cons_refseed,
-                           &s.induced, &s.bits, &s.goc, &s.size, nullptr));
+                           &s.induced, &s.bits, &s.goc, &s.size, nullptr, &s.ics));
     return s;
 }
 

@@ -64,7 +64,7 @@ Context& context_for(const Network* n1, const Network* n2, const BLASTDict* bit,
 // from-scratch counters of one alignment (Alignment.cpp:437-446 idiom) on the GPU
 struct Scratch {
     int cons_true, cons_refseed, induced;
-    double bits, goc, size;
+    double bits, goc, size, ics;
 };
 Scratch score_from_scratch(const Alignment& a);
 // seed a's cached counters from scratch exactly like the reference's constructors / shuf

@@ -34,11 +34,12 @@ class NetPair:
 
     @property
     def E1(self):
-        return len(self.edges1)
+        # net1->edges.size(): the reference's edge SET (Network.cpp:87) -- duplicate lines count once
+        return self.meta.get("E1", len(self.edges1))
 
     @property
     def E2(self):
-        return len(self.edges2)
+        return self.meta.get("E2", len(self.edges2))
 
 
 def adjlist_csr(n, edges):
@@ -295,6 +296,34 @@ def random_candidates(pair, P, K, seed):
     y = rng.integers(0, pair.n2 - 1, (P, K))
     y = y + (y >= x)
     return np.stack([x, y], axis=-1).astype(np.int32)
+
+
+def with_duplicate_lines(pair, n_dup, seed=0):
+    """The same pair with n_dup extra edge LINES per network, each a copy of an earlier line --
+    half of them reversed ("b a" after "a b"), self-loops included -- inserted at random places
+    after their original, so that the parser's node numbering is unchanged.  The reference keeps
+    every copy in adjList but not in its `edges` set or adjMatrix (Network.cpp:87-92)."""
+    import copy
+    rng = np.random.default_rng(seed)
+    out = copy.copy(pair)
+    out.meta = dict(pair.meta)
+    out.meta["E1"] = pair.E1
+    out.meta["E2"] = pair.E2
+    for tag, n in (("1", pair.n1), ("2", pair.n2)):
+        edges = [tuple(int(z) for z in e) for e in getattr(pair, "edges" + tag)]
+        src = rng.integers(0, len(edges), n_dup)
+        # insert from the back so earlier insert positions stay valid; a line copied twice gets two copies
+        ins = sorted(((int(rng.integers(k + 1, len(edges) + 1)), k) for k in src), reverse=True)
+        orig = list(edges)
+        for pos, k in ins:
+            u, v = orig[k]
+            edges.insert(pos, (v, u) if rng.random() < 0.5 else (u, v))
+        e = np.array(edges, np.int32)
+        setattr(out, "edges" + tag, e)
+        rp, col = adjlist_csr(n, e)
+        setattr(out, "rp" + tag, rp)
+        setattr(out, "col" + tag, col)
+    return out
 
 
 def write_text(pair, prefix, p1="a", p2="b"):

@@ -17,6 +17,9 @@ struct OrcProblem {
     const int *rp1, *col1, *rp2, *col2; /* owned copies */
     uint32_t* adj2;                     /* n2 x words bit matrix == Network::adjMatrix of net2 */
     int words;
+    uint8_t *first1, *first2; /* per CSR entry: first copy of that column in its row.  Duplicate edge
+                                 lines stay in adjList (Network.cpp:89-92) but not in the `edges`
+                                 set (:87) that ics() iterates */
     const double *S, *G; /* borrowed dense n1 x n2 */
 };
 
@@ -36,6 +39,17 @@ static int* dup_ints(const int* a, long n) {
     return r;
 }
 
+static uint8_t* first_copies(int n, const int* rp, const int* col) {
+    uint8_t* f = (uint8_t*)malloc((size_t)(rp[n] > 0 ? rp[n] : 1));
+    for (int u = 0; u < n; ++u)
+        for (int k = rp[u]; k < rp[u + 1]; ++k) {
+            f[k] = 1;
+            for (int j = rp[u]; j < k; ++j)
+                if (col[j] == col[k]) { f[k] = 0; break; }
+        }
+    return f;
+}
+
 /* Network.cpp:99-109 -- adjMatrix[i][j] = true for every adjList entry */
 OrcProblem* orc_problem_create(int n1, int n2, long E1, const int* rp1, const int* col1,
                                const int* rp2, const int* col2, const double* S, const double* G) {
@@ -51,12 +65,14 @@ OrcProblem* orc_problem_create(int n1, int n2, long E1, const int* rp1, const in
             p->adj2[(size_t)i * p->words + (j >> 5)] |= 1u << (j & 31);
         }
     p->S = S; p->G = G;
+    p->first1 = first_copies(n1, rp1, col1);
+    p->first2 = first_copies(n2, rp2, col2);
     return p;
 }
 void orc_problem_free(OrcProblem* p) {
     if (!p) return;
     free((void*)p->rp1); free((void*)p->col1); free((void*)p->rp2); free((void*)p->col2);
-    free(p->adj2); free(p);
+    free(p->adj2); free(p->first1); free(p->first2); free(p);
 }
 static inline int adj2_bit(const OrcProblem* p, int u, int v) {
     return (p->adj2[(size_t)u * p->words + (v >> 5)] >> (v & 31)) & 1u;
@@ -84,20 +100,22 @@ long orc_induced_true(const OrcAln* a) {
  * v2Unaligned = images of masked-off positions and of dummies (:609-619);
  * inducedES = net2 edges with both ends aligned (:622-627); mappedNet1ES =
  * images of net1 edges with both ends masked on (:629-635); aln is a
- * permutation, so distinct edges have distinct images and set sizes are counts
- * (inputs have no duplicate edge lines). */
-static void ics_parts(const OrcAln* a, long* num, long* den) {
+ * permutation, so distinct edges have distinct images and set sizes are counts of
+ * the DISTINCT edges (first copies; duplicate edge lines are not in `edges`).
+ * *mult (nullable): the same numerator with every copy counted -- the value the adjList-based
+ * incremental counter (doSwap, :491-520) holds for this alignment. */
+static void ics_parts(const OrcAln* a, long* num, long* den, long* mult) {
     const OrcProblem* p = a->p;
     uint8_t* v2un = (uint8_t*)calloc((size_t)p->n2, 1);
     for (int i = 0; i < p->n2; ++i) {
         if (!a->mask[i]) v2un[a->aln[i]] = 1;
         if (i >= p->n1) v2un[a->aln[i]] = 1;
     }
-    long d = 0, c = 0;
+    long d = 0, c = 0, cm = 0;
     for (int u = 0; u < p->n2; ++u)
         for (int k = p->rp2[u]; k < p->rp2[u + 1]; ++k) {
             int v = p->col2[k];
-            if (v >= u && !v2un[u] && !v2un[v]) ++d; /* each undirected edge once */
+            if (v >= u && p->first2[k] && !v2un[u] && !v2un[v]) ++d; /* each undirected edge once */
         }
     for (int u = 0; u < p->n1; ++u)
         for (int k = p->rp1[u]; k < p->rp1[u + 1]; ++k) {
@@ -106,14 +124,18 @@ static void ics_parts(const OrcAln* a, long* num, long* den) {
             if (!a->mask[u] || !a->mask[v]) continue; /* v1Unaligned (:610-611,631) */
             int iu = a->aln[u], iv = a->aln[v];
             /* member of inducedES: a net2 edge whose ends are both aligned */
-            if (adj2_bit(p, iu, iv) && !v2un[iu] && !v2un[iv]) ++c;
+            if (adj2_bit(p, iu, iv) && !v2un[iu] && !v2un[iv]) {
+                ++cm;
+                if (p->first1[k]) ++c;
+            }
         }
     free(v2un);
     *num = c; *den = d;
+    if (mult) *mult = cm;
 }
-long orc_conserved_true(const OrcAln* a) { long n, d; ics_parts(a, &n, &d); return n; }
+long orc_conserved_true(const OrcAln* a) { long n, d, m; ics_parts(a, &n, &d, &m); return m; }
 double orc_ics(const OrcAln* a) {
-    long n, d; ics_parts(a, &n, &d);
+    long n, d; ics_parts(a, &n, &d, NULL);
     if ((double)d == 0.0) return 0.0; /* :639-641 */
     return (double)n / (double)d;     /* :658-659 */
 }
@@ -122,6 +144,12 @@ int orc_refseed_conserved(long C, long I) {
     double denom = (double)I;
     double ics = (denom == 0.0) ? 0.0 : (double)C / denom;
     volatile double prod = ics * denom;
+    return (int)prod;
+}
+/* the same with the two factors as the reference has them: ics() is the ratio of the two edge
+ * SETS, denom = fastICSDenominator() (they only differ with duplicate edge lines) */
+int orc_refseed_from_ics(double ics, long denom) {
+    volatile double prod = ics * (double)denom;
     return (int)prod;
 }
 /* Alignment.cpp:701-710 */
@@ -163,12 +191,9 @@ OrcAln* orc_aln_create(const OrcProblem* p, const int* aln, const uint8_t* mask)
     /* Alignment.cpp:437-446 */
     a->bits = orc_sum_blast(a);
     a->goc = orc_sum_goc(a);
-    long C, I;
-    ics_parts(a, &C, &I);
     long denom = orc_induced_true(a);
-    a->cons = orc_refseed_conserved(C, denom);
+    a->cons = orc_refseed_from_ics(orc_ics(a), denom);
     a->ind = (int)denom;
-    (void)I;
     return a;
 }
 OrcAln* orc_aln_clone(const OrcAln* s) {
@@ -524,10 +549,8 @@ static void* job_full_fitness(void* v) {
         OrcAln* a = j->alns[k % j->nalns];
         a->bits = orc_sum_blast(a);
         a->goc = orc_sum_goc(a);
-        long C, I;
-        ics_parts(a, &C, &I);
         long denom = orc_induced_true(a);
-        a->cons = orc_refseed_conserved(C, denom);
+        a->cons = orc_refseed_from_ics(orc_ics(a), denom);
         a->ind = (int)denom;
         orc_compute_fitness(a, j->names, j->M, 0);
         s += a->fitness[0];

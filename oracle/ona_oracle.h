@@ -47,10 +47,13 @@ void orc_aln_get_counters(const OrcAln*, int* cons, int* ind, double* bits, doub
 void orc_aln_set_counters(OrcAln*, int cons, int ind, double bits, double goc);
 
 /* from-scratch pieces */
-long orc_conserved_true(const OrcAln*);        /* |mapped E1 /\ induced E2|, numerator of ics() :604-661 */
+long orc_conserved_true(const OrcAln*);        /* |mapped E1 /\ induced E2| (numerator of ics() :604-661), every
+                                                  adjList copy of a duplicate edge line counted: the exact
+                                                  value of the counter doSwap maintains */
 long orc_induced_true(const OrcAln*);          /* fastICSDenominator :667-690 */
 double orc_ics(const OrcAln*);                 /* :604-661 */
 int orc_refseed_conserved(long C, long I);     /* (int)(ics()*denom) :445 */
+int orc_refseed_from_ics(double ics, long denom);
 double orc_sum_blast(const OrcAln*);           /* :701-710 */
 double orc_sum_goc(const OrcAln*);             /* :712-722 */
 double orc_aln_size(const OrcAln*);            /* :724-732 */

@@ -50,6 +50,8 @@ def lib():
         getattr(L, f).argtypes = [vp]
     L.orc_refseed_conserved.restype = C.c_int
     L.orc_refseed_conserved.argtypes = [C.c_long, C.c_long]
+    L.orc_refseed_from_ics.restype = C.c_int
+    L.orc_refseed_from_ics.argtypes = [C.c_double, C.c_long]
     L.orc_conserved_count.restype = C.c_int
     L.orc_conserved_count.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.orc_induced_count.restype = C.c_int

@@ -24,10 +24,13 @@ DEMO = os.path.join(ROOT, "optnetaligncpp_b200", "host", "_build", "dropin_demo"
 
 @pytest.mark.skipif(not os.path.exists(DEMO) or not ref.available(),
                     reason="drop-in demo / compiled reference not built (dev container only)")
+@pytest.mark.parametrize("lines", ["plain", "duplicate-lines"])
 @pytest.mark.parametrize("with_goc", [False, True])
-def test_dropin_matches_reference(with_goc):
+def test_dropin_matches_reference(with_goc, lines):
     pair = synth.make_pair(n1=400, n2=520, m1=2000, m2=2300, max_deg=60, seed=41,
                            annotations=with_goc, n_terms=200, bit_density=0.01)
+    if lines == "duplicate-lines":      # "a b" + "b a", repeated lines: legal input upstream
+        pair = synth.with_duplicate_lines(pair, 150, seed=8)
     d = tempfile.mkdtemp()
     paths = synth.write_text(pair, os.path.join(d, "w"))
     seed, iters, nthreads = 77, 4000, 3
@@ -68,7 +71,9 @@ def test_dropin_matches_reference(with_goc):
     assert len(info) == 1 + nthreads
     for t in range(nthreads):
         a = climbed[t]
-        f = dict(zip(range(10), a.compute_fitness(list(range(10)))))   # fitnessName order, Network.h:31
+        # (on a clone: computeFitness never shrinks Alignment::fitness, and swapNormalizedDelta
+        # below reads whatever that vector holds, localSearch.cpp:90)
+        f = dict(zip(range(10), a.clone().compute_fitness(list(range(10)))))   # fitnessName order, Network.h:31
         c = a.counters()
         want = [os.path.join(d, "out_res_%d.aln" % t), "%g" % f[1], "%g" % f[0], "%g" % f[6],
                 "%g" % c[3] if with_goc else "?", "%g" % c[2], "%g" % c[2], "%g" % a.aln_size(),
@@ -133,13 +138,21 @@ def test_dropin_matches_reference(with_goc):
     gm = ref.Aln(n1, n2, B, G)
     gm.greedy_match(True)
     check(rest[7], "greedy", gm)
+    # --total --seeding: the greedyMatch individual (mask bits off on the dummies) as a UPMX parent;
+    # under --total the reference leaves mask bits in place (Alignment.cpp:219-227), doSwap would move them
+    as_par1 = 0
+    for v in range(4):
+        gchild = ref.Aln.crossover(seed + 9700 + v, 0.3, gm, climbed[0], True)
+        check(rest[8 + v], "gcx", gchild)
+        as_par1 += int(not gchild.state()[2].all())
+    assert 0 < as_par1 < 4          # both parent orders were exercised
     for v, tag in enumerate(("uniformsize", "smallstart")):
         a = ref.Aln(n1, n2, B, G)
         a.shuf(seed + 9500 + v, uniformsize=(v == 0), smallstart=(v == 1), total=False)
-        check(rest[8 + v], tag, a)
+        check(rest[12 + v], tag, a)
     # Alignment::save of a partial alignment + the alignment-file constructor
     loaded = ref.Aln.load(n1, n2, os.path.join(d, "out_partial.aln"), B, G)
-    check(rest[10], "pload", loaded)
+    check(rest[14], "pload", loaded)
     sa, sl = child.state(), loaded.state()
     live = sa[2][:pair.n1] != 0
     assert np.array_equal(sl[0][:pair.n1][live], sa[0][:pair.n1][live])

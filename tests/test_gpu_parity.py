@@ -329,13 +329,109 @@ def test_error_behaviour():
     with pytest.raises(engine.OnaError):
         e.hill_climb(iters=10, objs=[3, 3])
     col = pair.col1.copy()
-    col[pair.rp1[5]:pair.rp1[5] + 2] = col[pair.rp1[5]] if pair.rp1[6] - pair.rp1[5] >= 2 else col[pair.rp1[5]]
-    if pair.rp1[6] - pair.rp1[5] >= 2:
-        with pytest.raises(engine.OnaError, match="duplicate"):
-            engine.Engine(pair.n1, pair.n2, pair.E1, pair.rp1, col, pair.rp2, pair.col2, [engine.S3])
+    col[3] = pair.n1                                     # column id outside the network
+    with pytest.raises(engine.OnaError, match="out of range"):
+        engine.Engine(pair.n1, pair.n2, pair.E1, pair.rp1, col, pair.rp2, pair.col2, [engine.S3])
     # empty inputs are no-ops
     e.hill_climb(iters=0)
     e.swap_deltas(np.empty((2, 0, 2), np.int32))
+
+
+def test_resize_keeps_uploaded_slots():
+    """growing the population (explicitly or through upload(first=...)) keeps earlier slots:
+    permutation, mask, counters and objective rows."""
+    pair = synth.make_pair(n1=120, n2=150, m1=500, m2=560, max_deg=30, seed=14, bit_density=0.02)
+    e = engine.Engine.from_pair(pair, [engine.S3, engine.BITSCORE_SUM])
+    aln, mask = synth.random_population(pair, 7, seed=2, total=False)
+    e.upload(aln[:3], mask[:3])
+    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
+    c0, s0 = e.counters(), e.download()
+    e.upload(aln[3:], mask[3:], first=3)                 # grows 3 -> 7
+    assert e.P == 7
+    e.full_fitness(first=3, count=4, seed_mode=engine.SEED_REFCOMPAT)
+    c1, s1 = e.counters(), e.download()
+    for k in c0:
+        assert np.array_equal(c1[k][:3], c0[k], equal_nan=True), k
+    assert all(np.array_equal(a[:3], b) for a, b in zip(s1, s0))
+    assert np.array_equal(s1[0][3:], aln[3:]) and np.array_equal(s1[2][3:], mask[3:])
+    e.resize(5)                                          # shrink keeps the first 5
+    c2 = e.counters()
+    for k in c1:
+        assert np.array_equal(c2[k], c1[k][:5], equal_nan=True), k
+    # the whole population scored at once equals the piecewise result
+    r = e.full_fitness(seed_mode=engine.SEED_NONE)
+    assert np.array_equal(r["cons_ref"], c2["cons"]) and np.array_equal(r["ind"], c2["ind"])
+
+
+@pytest.mark.parametrize("total", [True, False])
+def test_duplicate_edge_lines_match_oracle(total):
+    """Edge lists with "a b" + "b a" and repeated lines (self-loops too) are legal reference input:
+    adjList keeps every copy, so conservedCount / inducedCount / fastICSDenominator weigh such an
+    edge by its multiplicity while edges.size(), adjMatrix and the set-based ics() see it once
+    (Network.cpp:87-92).  The oracle is pinned on exactly this input against the
+    compiled reference (tests/test_oracle_vs_reference.py, "duplicate-lines")."""
+    base = synth.make_pair(n1=300, n2=380, m1=1500, m2=1700, max_deg=60, seed=15, loop_frac=0.06,
+                           annotations=True, n_terms=120, bit_density=0.02)
+    pair = synth.with_duplicate_lines(base, 200, seed=4)
+    assert len(pair.col1) > len(base.col1) and pair.E1 == base.E1
+    S, G = synth.dense_bits(pair), synth.dense_goc(pair)
+    prob = port.Problem(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2, S, G)
+    names = [engine.S3, engine.ICS, engine.EC, engine.BITSCORE_SUM, engine.GOC, engine.SIZE]
+    P, K = 10, 3000
+    aln, mask = synth.random_population(pair, P, seed=6, total=total)
+    e = engine.Engine.from_pair(pair, names, use_goc=True, goc_dense=G)
+    e.upload(aln, mask)
+    r = e.full_fitness(seed_mode=engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL)
+    orc = [port.Aln(prob, aln[p], None if mask is None else mask[p]) for p in range(P)]
+    differ = 0
+    for p in range(P):
+        c = orc[p].counters()
+        assert (r["cons_ref"][p], r["ind"][p]) == (c[0], c[1])
+        assert r["cons_true"][p] == orc[p].conserved_true() and r["ics"][p] == orc[p].ics()
+        assert r["ind"][p] == orc[p].induced_true()
+        assert np.array_equal(r["fit"][p], orc[p].compute_fitness(names), equal_nan=True)
+        differ += int(r["ics"][p] * r["ind"][p] != r["cons_true"][p])
+    assert differ > 0                                    # the multiplicities do matter on this input
+    # candidates biased towards the duplicated edges' endpoints (self-loops and the a_x - a_y edge)
+    rng = np.random.default_rng(11)
+    xy = rng.integers(0, pair.n2, (P, K, 2)).astype(np.int32)
+    d = e.swap_deltas(xy, obj=-1)
+    for p in range(P):
+        o = orc[p].swap_delta_records(xy[p], names, obj=-1, want_snd=True)
+        for k in ("cons", "ind", "improved"):
+            assert np.array_equal(d[k][p], o[k]), (p, k)
+        for k in ("bits", "goc", "fit", "snd"):
+            assert np.array_equal(d[k][p], o[k], equal_nan=True), (p, k)
+    iters = 8000
+    hxy = synth.random_candidates(pair, P, iters, seed=78)
+    objs = np.array([-1, 0, 1, 3, 4] * 2)
+    acc, nacc = e.hill_climb(xy=hxy, objs=objs, want_accepted=True)
+    a, inv, m = e.download()
+    c = e.counters()
+    for p in range(P):
+        oacc = orc[p].hill_climb_replay(hxy[p], names, obj=int(objs[p]), want_accepted=True)
+        assert np.array_equal(acc[p], oacc), p
+        st = orc[p].state()
+        assert np.array_equal(a[p], st[0]) and np.array_equal(inv[p], st[1]) and np.array_equal(m[p], st[2])
+        assert (c["cons"][p], c["ind"][p], c["bits"][p], c["goc"][p]) == orc[p].counters()
+    assert acc.sum() > 0
+    # variation operators on the same graphs
+    ops = np.zeros((P, 60, 4), np.int32)
+    ops[..., 0] = rng.integers(0, 4, (P, 60))
+    ops[..., 1] = rng.integers(0, pair.n2, (P, 60))
+    ops[..., 2] = rng.integers(0, pair.n2, (P, 60))
+    ops[..., 3] = rng.integers(0, 8, (P, 60))
+    e.apply_edits(ops)
+    c = e.counters()
+    for p in range(P):
+        orc[p].apply_edits(ops[p])
+        assert (c["cons"][p], c["ind"][p], c["bits"][p], c["goc"][p]) == orc[p].counters(), p
+    # the throughput climb keeps the counters equal to a (multiplicity-weighted) recount
+    e.full_fitness(seed_mode=engine.SEED_TRUE)
+    e.hill_climb_batched(iters=4096, seed=5)
+    c = e.counters()
+    r = e.full_fitness(seed_mode=engine.SEED_NONE)
+    assert np.array_equal(c["cons"], r["cons_true"]) and np.array_equal(c["ind"], r["ind"])
 
 
 def test_steepest_step_matches_exhaustive_oracle_scan():
