@@ -6,7 +6,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB = os.path.join(HERE, "libona_b200.so")
+# ONA_LIB_PATH: load a prebuilt variant instead (kernel A/B experiments, profiles/kernel_ab.py)
+LIB = os.environ.get("ONA_LIB_PATH") or os.path.join(HERE, "libona_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "ona_engine.cu")]
 # every file under csrc/ is a dependency (ona_engine.cu includes all the .cuh headers)
 DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*"))) + [os.path.join(ROOT, "include", "ona_b200.h")]
@@ -34,7 +35,7 @@ def stale():
 
 def build(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a: cross-compiles without a GPU."""
-    if not force and not stale():
+    if os.environ.get("ONA_LIB_PATH") or (not force and not stale()):
         return LIB
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
            "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-ccbin", host_compiler(),

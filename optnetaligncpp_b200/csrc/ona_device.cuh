@@ -61,7 +61,7 @@ struct DevGraph {
     const int* rq1;
     const int4* cq1;
     const int* rq2;
-    const int4* cq2;
+    const int4* cq2;   // = cq1 + (number of net1 quads): both networks' rows live in one array
     // neighbourhood signature of every net2 node: three 32-bit Bloom words -- for every
     // neighbour j bit (j & 31) of .x, bit ((j >> 5) & 31) of .y and bit ((j >> 10) & 31) of .z
     // are set.  A clear bit proves "not adjacent" without touching the bit matrix, and one
@@ -77,6 +77,12 @@ struct DevGraph {
     const int* ew1;
     const int* ew2;
     int dup;  // any duplicate in either network
+    // fast swap-delta walk (k_swap_deltas_sorted<T, true>): per node, quad range packed as
+    // base << 8 | min(quads, 255) (255 = look it up in rq), and self-loop bits of both networks
+    const uint32_t* pk1;
+    const uint32_t* pk2;
+    const uint32_t* self1;
+    const uint32_t* self2;
 };
 
 // BLASTDict / GOCDict on the device: dense fp64 matrix, or an open-addressing hash of the
@@ -304,7 +310,7 @@ constexpr int kSeenXinX = 1, kSeenYinY = 2, kSeenAXinAX = 4, kSeenAYinAX = 8, kS
 //   self-loop at a_x: Lx_new - Lx_old;  self-loop at a_y: Ly_new - Ly_old        (:820)
 //   edge a_x-a_y:     (Lx_new & Ly_new) - (Lx_old & Ly_old); a_y's copy is the `ignore` (:495)
 // With duplicate edge lines (g.dup) every term is weighted by how often the list holds the id.
-__device__ __noinline__ int list_multiplicity(const int* rp, const int* col, int row, int id) {
+__device__ __forceinline__ int list_multiplicity(const int* rp, const int* col, int row, int id) {
     int m = 0;
     for (int k = __ldg(rp + row); k < __ldg(rp + row + 1); ++k) m += __ldg(col + k) == id ? 1 : 0;
     return m;
@@ -418,6 +424,177 @@ __device__ __forceinline__ void walk_plan(const DevGraph& g, const T* s_aln, con
         // what meeting sp0 / sp1 in this list means (0 = contributes nothing)
         if (is0) seen |= l == 0 ? kSeenXinX : l == 2 ? kSeenAXinAX : 0;
         if (is1) seen |= l == 1 ? kSeenYinY : l == 2 ? kSeenAYinAX : l == 3 ? kSeenAYinAY : 0;
+    }
+}
+
+// ------------------------------------------------ fast walk on precomputed node counts
+// For K candidates against ONE state most of the delta is a function of single nodes:
+//   cc(u) = sum over adjList1[u] entries t with mask bit on of A2[aln[u]][aln[t]]   (u < n1)
+//   ic(v) = number of adjList2[v] entries whose pre-image is a real, unmasked node  (v < n2)
+// (k_node_counts, once per individual per call).  With them the "old" halves of doSwap's
+// recounts (Alignment.cpp:492-495) and BOTH induced recounts are O(1), and what is left to walk is
+//   I(x, a_y) = sum over t in adjList1[x] \ {x,y} of m_t A2[a_y][aln[t]]      (if x real and m_y)
+//   I(y, a_x) = sum over t in adjList1[y] \ {x,y} of m_t A2[a_x][aln[t]]      (if y real and m_x)
+// each the size of an intersection of a net1 list with the pull-back of a net2 list, so it is
+// counted from whichever list is SHORTER: over adjList1[u] (gather aln, test row a of A2) or over
+// adjList2[a] (gather alnInv, test row u of A1).  PPI degrees are heavy-tailed, the minimum of two
+// independent degrees is not: 7.4 items per candidate instead of 21 on the yeast-fly pair, one
+// adjacency test per item instead of two, and hardly any hubs.  With duplicate edge lines (g.dup)
+// the two lists weigh an edge differently, so the net1 list is always the one walked.
+struct FastPlan {
+    int e0, e1;   // quads of walk 0 = [0,e0), of walk 1 = [e0,e1)
+    int b0, b1;   // cq index of quad q is b0 + q (walk 0) / b1 + q (walk 1; b1 is pre-shifted by -e0)
+    int side0, side1;  // 0: the net1 list is walked, 1: the net2 list
+};
+__device__ __forceinline__ void quad_range(const uint32_t* pk, const int* rq, int node, int& base, int& cnt) {
+    const uint32_t w = __ldg(pk + node);
+    base = (int)(w >> 8);     // index into the combined quad array (net1's rows, then net2's)
+    cnt = (int)(w & 255u);
+    if (cnt == 255) cnt = __ldg(rq + node + 1) - __ldg(rq + node);
+}
+__device__ __forceinline__ FastPlan make_fast_plan(const DevGraph& g, const SwapCtx& c) {
+    FastPlan p;
+    p.e0 = p.e1 = p.b0 = p.b1 = p.side0 = p.side1 = 0;
+    if (c.x == c.y) return p;
+    if (c.xr & (c.my != 0)) {   // I(x, a_y)
+        int b1l, q1l, b2l, q2l;
+        quad_range(g.pk1, g.rq1, c.x, b1l, q1l);
+        quad_range(g.pk2, g.rq2, c.ay, b2l, q2l);
+        p.side0 = (g.dup == 0 && q2l < q1l) ? 1 : 0;
+        p.b0 = p.side0 ? b2l : b1l;
+        p.e0 = p.side0 ? q2l : q1l;
+    }
+    int len1 = 0;
+    if (c.yr & (c.mx != 0)) {   // I(y, a_x)
+        int b1l, q1l, b2l, q2l;
+        quad_range(g.pk1, g.rq1, c.y, b1l, q1l);
+        quad_range(g.pk2, g.rq2, c.ax, b2l, q2l);
+        p.side1 = (g.dup == 0 && q2l < q1l) ? 1 : 0;
+        p.b1 = p.side1 ? b2l : b1l;
+        len1 = p.side1 ? q2l : q1l;
+    }
+    p.e1 = p.e0 + len1;
+    p.b1 -= p.e0;
+    return p;
+}
+
+// one walk in 32 bits: quad base (24) | quads (7) | side (1); quads beyond 127 only occur for
+// hub candidates (> kHubQuads quads), whose plan is rebuilt by the warp that walks them
+__device__ __forceinline__ uint2 pack_fast_plan(const FastPlan& p) {
+    const int len1 = p.e1 - p.e0, b1 = p.b1 + p.e0;
+    return make_uint2(((uint32_t)p.b0 << 8) | ((uint32_t)min(p.e0, 127) << 1) | (uint32_t)p.side0,
+                      ((uint32_t)b1 << 8) | ((uint32_t)min(len1, 127) << 1) | (uint32_t)p.side1);
+}
+__device__ __forceinline__ FastPlan unpack_fast_plan(const uint2& w) {
+    FastPlan p;
+    p.b0 = (int)(w.x >> 8);
+    p.e0 = (int)((w.x >> 1) & 127u);
+    p.side0 = (int)(w.x & 1u);
+    const int len1 = (int)((w.y >> 1) & 127u);
+    p.side1 = (int)(w.y & 1u);
+    p.e1 = p.e0 + len1;
+    p.b1 = (int)(w.y >> 8) - p.e0;
+    return p;
+}
+
+template <typename T>
+__device__ __forceinline__ int fast_item(const T* table, uint32_t lim, const uint4& sg, const uint32_t* row,
+                                         int sp0, int sp1, int t) {
+    constexpr uint32_t MASK = Pk<T>::MASK;
+    // side 0: r = packed aln[t], live = mask bit on (r < FLAG), id = image;  side 1: r = packed
+    // alnInv[t], live = pre-image real and unmasked (r < n1), id = pre-image.  Row padding (id n2)
+    // is masked off in both tables.
+    const uint32_t r = table[t];
+    const bool live = (t != sp0) & (t != sp1) & (r < lim);
+    const unsigned it = r & MASK, s0 = it & 31u, h1 = it >> 5;
+    const bool hit = live & ((((sg.x >> s0) & (sg.y >> (h1 & 31u)) & (sg.z >> ((it >> 10) & 31u))) & 1u) != 0u);
+    unsigned w = 0u;
+    if (hit) w = __ldg(row + h1);
+    return (int)((w >> s0) & 1u);
+}
+
+// I(x, a_y) and I(y, a_x) of one candidate: quads [first, first + stride, ...) of its plan
+template <typename T>
+__device__ __forceinline__ void walk_fast(const DevGraph& g, const T* s_aln, const T* s_inv, const SwapCtx& c,
+                                          const FastPlan& p, int first, int stride, int& ix, int& iy) {
+    constexpr uint32_t FLAG = Pk<T>::FLAG;
+    ix = 0;
+    iy = 0;
+    if (first >= p.e1) return;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    uint4 sg0 = zero4, sg1 = zero4;
+    const uint32_t *row0 = g.adj2, *row1 = g.adj2;
+    if (p.e0 > 0) {
+        sg0 = p.side0 ? __ldg(g.sig1 + c.x) : __ldg(g.sig2 + c.ay);
+        row0 = p.side0 ? g.adj1 + (size_t)c.x * (size_t)g.W1 : g.adj2 + (size_t)c.ay * (size_t)g.W;
+    }
+    if (p.e1 > p.e0) {
+        sg1 = p.side1 ? __ldg(g.sig1 + c.y) : __ldg(g.sig2 + c.ax);
+        row1 = p.side1 ? g.adj1 + (size_t)c.y * (size_t)g.W1 : g.adj2 + (size_t)c.ax * (size_t)g.W;
+    }
+    for (int q = first; q < p.e1; q += stride) {
+        const bool w1 = q >= p.e0;
+        const int4 t = __ldg(g.cq1 + (w1 ? p.b1 : p.b0) + q);
+        const int side = w1 ? p.side1 : p.side0;
+        const T* table = side ? s_inv : s_aln;
+        const uint32_t lim = side ? (uint32_t)g.n1 : FLAG;
+        const int sp0 = side ? c.ax : c.x, sp1 = side ? c.ay : c.y;
+        const uint4 sg = w1 ? sg1 : sg0;
+        const uint32_t* row = w1 ? row1 : row0;
+        const int n = fast_item<T>(table, lim, sg, row, sp0, sp1, t.x) + fast_item<T>(table, lim, sg, row, sp0, sp1, t.y) +
+                      fast_item<T>(table, lim, sg, row, sp0, sp1, t.z) + fast_item<T>(table, lim, sg, row, sp0, sp1, t.w);
+        if (w1) iy += n;
+        else ix += n;
+    }
+}
+
+__device__ __forceinline__ int bit_of(const uint32_t* bits, int i) {
+    return (int)((__ldg(bits + (i >> 5)) >> (i & 31)) & 1u);
+}
+// The closed forms around the two walked sums (see the derivation in DESIGN.md, section 4.1):
+// conservedCount before / after the exchange for x and y (Alignment.cpp:492-493, 506-507) and
+// inducedCount before / after for a_x and a_y (:494-495, 508-509), with the node counts standing
+// in for every sum that does not involve the partner node.
+//   nc: this individual's node counts, cc at [0, n1), ic at [ic_off, ic_off + n2)
+__device__ __forceinline__ void fast_delta(const DevGraph& g, const SwapCtx& c, const unsigned short* nc, int ic_off,
+                                           int ix, int iy, int& dc, int& di) {
+    dc = 0;
+    di = 0;
+    if (c.x == c.y) return;
+    // multiplicities of the entries that involve the exchanged nodes themselves
+    int sxx = 0, syy = 0, mxy = 0;
+    if (c.xr) sxx = bit_of(g.self1, c.x);
+    if (c.yr) syy = bit_of(g.self1, c.y);
+    if (c.xr & c.yr) mxy = (int)((__ldg(g.adj1 + (size_t)c.x * (size_t)g.W1 + (c.y >> 5)) >> (c.y & 31)) & 1u);
+    if (g.dup) {
+        if (sxx) sxx = list_multiplicity(g.rp1, g.col1, c.x, c.x);
+        if (syy) syy = list_multiplicity(g.rp1, g.col1, c.y, c.y);
+        if (mxy) mxy = list_multiplicity(g.rp1, g.col1, c.x, c.y);
+    }
+    const bool ich = induced_changes(c);
+    int a_xx = 0, a_yy = 0, a_xy = 0;
+    if (sxx | syy) { a_xx = probe(g, c.ax, c.ax); a_yy = probe(g, c.ay, c.ay); }
+    if (mxy != 0 || ich) a_xy = probe(g, c.ax, c.ay);
+    const int ccx = c.xr ? (int)__ldg(nc + c.x) : 0, ccy = c.yr ? (int)__ldg(nc + c.y) : 0;
+    const int xr = c.xr ? 1 : 0, yr = c.yr ? 1 : 0;
+    const int cX = c.mx * xr * ccx;
+    const int cY = c.my * yr * (ccy - mxy * c.mx * a_xy);
+    const int cXn = c.my * xr * (ix + sxx * c.my * a_yy + mxy * c.mx * a_xy);
+    const int cYn = c.mx * yr * (iy + syy * c.mx * a_xx);
+    dc = cXn + cYn - cX - cY;
+    if (ich) {
+        int s2x = bit_of(g.self2, c.ax), s2y = bit_of(g.self2, c.ay), m2 = a_xy;
+        if (g.dup) {
+            if (s2x) s2x = list_multiplicity(g.rp2, g.col2, c.ax, c.ax);
+            if (s2y) s2y = list_multiplicity(g.rp2, g.col2, c.ay, c.ay);
+            if (m2) m2 = list_multiplicity(g.rp2, g.col2, c.ax, c.ay);
+        }
+        const int icx = (int)__ldg(nc + ic_off + c.ax), icy = (int)__ldg(nc + ic_off + c.ay);
+        const int iX = c.Lx_old * icx;
+        const int iY = c.Ly_old * (icy - m2 * c.Lx_old);
+        const int iXn = c.Lx_new * (icx - s2x * c.Lx_old - m2 * c.Ly_old + s2x * c.Lx_new + m2 * c.Ly_new);
+        const int iYn = c.Ly_new * (icy - s2y * c.Ly_old - m2 * c.Lx_old + s2y * c.Ly_new);
+        di = iXn + iYn - iX - iY;
     }
 }
 

@@ -70,6 +70,10 @@ struct ona_engine {
     int group = 8;           // lanes per candidate in the hill-climb kernel's phase 1
     bool group_forced = false;
     int pipe_slices = 8;     // host-buffer pipeline depth of ona_swap_deltas
+    bool fast_ok = false;    // the fast swap-delta walk (node counts) is usable on this problem
+    int fast_min_k = 4096;   // ... and pays from this many candidates per individual on
+    int nc_ic_off = 0, nc_stride = 0;   // layout of one individual's node counts
+    DevBuf<unsigned short> t_nc;
     int sm_count = 148;
     size_t smem_optin = 0;
 
@@ -318,17 +322,53 @@ int launch_full(ona_engine* e, int first, int count, int seed_mode, int sequenti
     return ONA_OK;
 }
 
+size_t counts_smem(const ona_engine* e) {
+    return state_smem(e) + ((size_t)(e->g.n1 + 1) / 2 + (size_t)(e->g.n2 + 1) / 2) * 4;
+}
+
+// Node counts of slots first..first+count in their CURRENT state (recomputed by every swap-delta
+// call: nothing is cached across calls) for the fast walk; *nc = nullptr when the classic walk is
+// to be used (problem too large for the 16-bit counters, or too few candidates to pay for it).
+template <typename T>
+int prepare_counts_t(ona_engine* e, int first, int count) {
+    int rc = set_smem(k_node_counts<T>, counts_smem(e));
+    if (rc) return rc;
+    k_node_counts<T><<<count, kCountThreads, counts_smem(e), e->stream>>>(e->g, e->pop, first, e->t_nc.p,
+                                                                         e->nc_stride, e->nc_ic_off);
+    e->launches++;
+    CU(cudaGetLastError());
+    return ONA_OK;
+}
+int prepare_counts(ona_engine* e, int first, int count, int K, const unsigned short** nc) {
+    *nc = nullptr;
+    if (!e->fast_ok || K < e->fast_min_k) return ONA_OK;
+    CU(e->t_nc.need((size_t)count * e->nc_stride));
+    const int rc = e->small_ids ? prepare_counts_t<uint16_t>(e, first, count) : prepare_counts_t<uint32_t>(e, first, count);
+    if (rc) return rc;
+    *nc = e->t_nc.p;
+    return ONA_OK;
+}
+
+// nc: node counts of slot `first` onwards (prepare_counts), or nullptr for the classic walk
 template <typename T>
 int launch_deltas_sorted(ona_engine* e, int first, int count, int K, const int* xy_dev,
                          unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks,
-                         int grid_x0 = -1) {
+                         const unsigned short* nc, int grid_x0 = -1) {
     const size_t smem = state_smem(e);
-    int rc = set_smem(k_swap_deltas_sorted<T>, smem);
-    if (rc) return rc;
     dim3 grid(chunks, count);
-    k_swap_deltas_sorted<T><<<grid, kSortThreads, smem, e->stream>>>(
-        e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag,
-        grid_x0);
+    if (nc) {
+        int rc = set_smem(k_swap_deltas_sorted<T, true>, smem);
+        if (rc) return rc;
+        k_swap_deltas_sorted<T, true><<<grid, kSortThreads, smem, e->stream>>>(
+            e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag,
+            grid_x0, nc, e->nc_stride, e->nc_ic_off);
+    } else {
+        int rc = set_smem(k_swap_deltas_sorted<T, false>, smem);
+        if (rc) return rc;
+        k_swap_deltas_sorted<T, false><<<grid, kSortThreads, smem, e->stream>>>(
+            e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag,
+            grid_x0, nullptr, 0, 0);
+    }
     e->launches++;
     CU(cudaGetLastError());
     return ONA_OK;
@@ -344,10 +384,11 @@ int pick_chunks(const ona_engine* e, int count, int K) {
 }
 
 int launch_deltas(ona_engine* e, int first, int count, int K, const int* xy_dev,
-                  unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks) {
+                  unsigned long long seed, int obj, DevDeltaOut out, DeltaSummary sum, int chunks,
+                  const unsigned short* nc) {
     if (e->small_ids)
-        return launch_deltas_sorted<uint16_t>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
-    return launch_deltas_sorted<uint32_t>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks);
+        return launch_deltas_sorted<uint16_t>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks, nc);
+    return launch_deltas_sorted<uint32_t>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks, nc);
 }
 
 template <typename T, int G>
@@ -517,26 +558,54 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
         if (dups2 && (rc = upload<int>(e, ew, &g.ew2))) return bail(rc);
         g.dup = (dups1 || dups2) ? 1 : 0;
     }
-    for (int net = 0; net < 2; ++net) {  // quad-padded CSR (rows padded with -1 to multiples of 4)
-        const int n = net ? pr->n2 : pr->n1;
-        const int* rp = net ? pr->rowptr2 : pr->rowptr1;
-        const int* col = net ? pr->col2 : pr->col1;
-        std::vector<int> rq(n + 1, 0);
+    size_t max_row = 0;
+    {   // quad-padded CSR (rows padded with the dummy id n2 to multiples of 4 columns): net1's rows,
+        // then net2's, in one array; pk = base << 8 | min(quads, 255) per node for the fast walk
         std::vector<int4> cq;
-        for (int u = 0; u < n; ++u) {
-            rq[u] = (int)cq.size();
-            for (int k = rp[u]; k < rp[u + 1]; k += 4) {
-                int4 q = make_int4(pr->n2, pr->n2, pr->n2, pr->n2);  // dummy id: contributes nothing
-                q.x = col[k];
-                if (k + 1 < rp[u + 1]) q.y = col[k + 1];
-                if (k + 2 < rp[u + 1]) q.z = col[k + 2];
-                if (k + 3 < rp[u + 1]) q.w = col[k + 3];
-                cq.push_back(q);
+        std::vector<int> rq1v(pr->n1 + 1, 0), rq2v(pr->n2 + 1, 0);
+        std::vector<uint32_t> pk1(pr->n1, 0u), pk2(pr->n2, 0u);
+        size_t ncq1 = 0;
+        for (int net = 0; net < 2; ++net) {
+            const int n = net ? pr->n2 : pr->n1;
+            const int* rp = net ? pr->rowptr2 : pr->rowptr1;
+            const int* col = net ? pr->col2 : pr->col1;
+            std::vector<int>& rq = net ? rq2v : rq1v;
+            std::vector<uint32_t>& pk = net ? pk2 : pk1;
+            const size_t off = cq.size();
+            for (int u = 0; u < n; ++u) {
+                rq[u] = (int)(cq.size() - off);
+                max_row = std::max(max_row, (size_t)(rp[u + 1] - rp[u]));
+                for (int k = rp[u]; k < rp[u + 1]; k += 4) {
+                    int4 q = make_int4(pr->n2, pr->n2, pr->n2, pr->n2);  // dummy id: contributes nothing
+                    q.x = col[k];
+                    if (k + 1 < rp[u + 1]) q.y = col[k + 1];
+                    if (k + 2 < rp[u + 1]) q.z = col[k + 2];
+                    if (k + 3 < rp[u + 1]) q.w = col[k + 3];
+                    cq.push_back(q);
+                }
+                const size_t base = off + (size_t)rq[u], cnt = cq.size() - base;
+                pk[u] = (uint32_t)((base << 8) | std::min<size_t>(cnt, 255));
             }
+            rq[n] = (int)(cq.size() - off);
+            if (!net) ncq1 = cq.size();
         }
-        rq[n] = (int)cq.size();
-        if ((rc = upload<int>(e, rq, net ? &g.rq2 : &g.rq1))) return bail(rc);
-        if ((rc = upload<int4>(e, cq, net ? &g.cq2 : &g.cq1))) return bail(rc);
+        if ((rc = upload<int>(e, rq1v, &g.rq1))) return bail(rc);
+        if ((rc = upload<int>(e, rq2v, &g.rq2))) return bail(rc);
+        if ((rc = upload<int4>(e, cq, &g.cq1))) return bail(rc);
+        g.cq2 = g.cq1 + ncq1;
+        if ((rc = upload<uint32_t>(e, pk1, &g.pk1))) return bail(rc);
+        if ((rc = upload<uint32_t>(e, pk2, &g.pk2))) return bail(rc);
+        e->fast_ok = cq.size() < ((size_t)1 << 24) && max_row < 65536;
+        for (int net = 0; net < 2; ++net) {  // self-loop bits
+            const int n = net ? pr->n2 : pr->n1;
+            const int* rp = net ? pr->rowptr2 : pr->rowptr1;
+            const int* col = net ? pr->col2 : pr->col1;
+            std::vector<uint32_t> bits((n + 31) / 32 + 1, 0u);
+            for (int u = 0; u < n; ++u)
+                for (int k = rp[u]; k < rp[u + 1]; ++k)
+                    if (col[k] == u) bits[u >> 5] |= 1u << (u & 31);
+            if ((rc = upload<uint32_t>(e, bits, net ? &g.self2 : &g.self1))) return bail(rc);
+        }
     }
     g.W1 = (pr->n1 + 31) / 32;
     {
@@ -580,6 +649,14 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
         if (v == 4 || v == 8 || v == 16) { e->group = v; e->group_forced = true; }
     }
     if (const char* ps = getenv("ONA_PIPE_SLICES")) e->pipe_slices = std::max(1, std::min(kPipeSlices, atoi(ps)));
+    e->nc_ic_off = (pr->n1 + 7) / 8 * 8;
+    e->nc_stride = e->nc_ic_off + (pr->n2 + 7) / 8 * 8;
+    e->fast_ok = e->fast_ok && counts_smem(e) + 1024 <= e->smem_optin;
+    if (const char* fk = getenv("ONA_FAST_MIN_K")) {   // 0 = always, negative = never (tests, A/B runs)
+        const int v = atoi(fk);
+        if (v < 0) e->fast_ok = false;
+        else e->fast_min_k = v;
+    }
     if (cudaMalloc(&e->d_flag, sizeof(int)) != cudaSuccess) return bail(fail(ONA_ERR_CUDA, "cudaMalloc"));
     if (cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking) != cudaSuccess ||
@@ -602,7 +679,7 @@ void ona_engine_destroy(ona_engine* e) {
     e->t_i0.release(); e->t_i1.release(); e->t_i2.release(); e->t_xy.release();
     e->t_d0.release(); e->t_d1.release(); e->t_d2.release(); e->t_d3.release(); e->t_d4.release();
     e->t_seq.release(); e->t_u0.release(); e->t_mask.release(); e->t_l0.release();
-    e->t_part.release(); e->t_ticket.release(); e->t_claims.release();
+    e->t_part.release(); e->t_ticket.release(); e->t_claims.release(); e->t_nc.release();
     e->ns_dom.release(); e->ns_front.release(); e->ns_count.release(); e->ns_pos.release();
     e->ns_cnt.release(); e->ns_rank.release(); e->ns_order.release(); e->ns_offsets.release();
     e->ns_after.release(); e->ns_slot.release(); e->ns_old.release(); e->ns_keys.release();
@@ -872,6 +949,8 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
     // the kernel of slice i (engine stream) and the D2H of slice i-1 (copy-out stream); PCIe is
     // full duplex, so with pinned host buffers the call costs about max(H2D, kernel, D2H).
     const int slices = std::min(count, e->pipe_slices);
+    const unsigned short* nc = nullptr;
+    TRY(prepare_counts(e, first, count, K, &nc));         // once, for all the slices
     CU(cudaEventRecord(e->ev_k[0], e->stream));           // copy-in must follow the flag reset / prior work
     CU(cudaStreamWaitEvent(e->s_in, e->ev_k[0], 0));
     for (int sidx = 0; sidx < slices; ++sidx) {
@@ -890,7 +969,8 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
         if (o.fit) o.fit += off * M;
         if (o.improved) o.improved += off;
         if (o.snd) o.snd += off;
-        TRY(launch_deltas(e, first + f, cnt, K, e->t_xy.p + 2 * off, 0ull, obj, o, sum, pick_chunks(e, cnt, K)));
+        TRY(launch_deltas(e, first + f, cnt, K, e->t_xy.p + 2 * off, 0ull, obj, o, sum, pick_chunks(e, cnt, K),
+                          nc ? nc + (size_t)f * e->nc_stride : nullptr));
         CU(cudaEventRecord(e->ev_k[sidx], e->stream));
         CU(cudaStreamWaitEvent(e->s_out, e->ev_k[sidx], 0));
         auto back = [&](void* host, const void* dev, size_t bytes) -> cudaError_t {
@@ -930,7 +1010,9 @@ int ona_swap_deltas_rng(ona_engine* e, int first, int count, int K, unsigned lon
         sum.block_best = e->t_d4.p;
         sum.block_arg = e->t_l0.p;
     }
-    TRY(launch_deltas(e, first, count, K, nullptr, seed, obj, out, sum, chunks));
+    const unsigned short* nc = nullptr;
+    TRY(prepare_counts(e, first, count, K, &nc));
+    TRY(launch_deltas(e, first, count, K, nullptr, seed, obj, out, sum, chunks, nc));
     if (!num_improved && !want_best) return ONA_OK;  // fully asynchronous
     TRY(d2h(e, num_improved, e->t_i2.p, (size_t)count));
     std::vector<double> bv;
@@ -977,7 +1059,9 @@ int ona_swap_deltas_dev(ona_engine* e, int first, int count, int K, const int* x
     DevDeltaOut out{cons_dev, ind_dev, bits_dev, goc_dev, fit_dev, improved_dev, snd_dev};
     DeltaSummary sum{};
     sum.num_improved = num_improved_dev;
-    return launch_deltas(e, first, count, K, xy_dev, seed, obj, out, sum, pick_chunks(e, count, K));
+    const unsigned short* nc = nullptr;
+    TRY(prepare_counts(e, first, count, K, &nc));
+    return launch_deltas(e, first, count, K, xy_dev, seed, obj, out, sum, pick_chunks(e, count, K), nc);
 }
 
 int ona_steepest_step(ona_engine* e, int slot, double* best_delta, int* best_x, int* best_y) {
@@ -987,6 +1071,8 @@ int ona_steepest_step(ona_engine* e, int slot, double* best_delta, int* best_x, 
     const int slab = std::max(1, std::min(n1, (1 << 28) / n2));  // rows of the grid per launch
     double bv = -1.0;  // localSearch.cpp:134,141: bestDelta starts at -1 and only a larger value wins
     int bx = -1, by = -1;
+    const unsigned short* nc = nullptr;
+    TRY(prepare_counts(e, slot, 1, n1 * std::min(n2, 1 << 16), &nc));   // the whole grid scores one state
     std::vector<double> hv;
     std::vector<long long> hi;
     for (int x0 = 0; x0 < n1; x0 += slab) {
@@ -999,8 +1085,8 @@ int ona_steepest_step(ona_engine* e, int slot, double* best_delta, int* best_x, 
         DeltaSummary sum{};
         sum.block_best = e->t_d4.p;
         sum.block_arg = e->t_l0.p;
-        if (e->small_ids) TRY(launch_deltas_sorted<uint16_t>(e, slot, 1, K, nullptr, 0ull, -1, out, sum, chunks, x0));
-        else TRY(launch_deltas_sorted<uint32_t>(e, slot, 1, K, nullptr, 0ull, -1, out, sum, chunks, x0));
+        if (e->small_ids) TRY(launch_deltas_sorted<uint16_t>(e, slot, 1, K, nullptr, 0ull, -1, out, sum, chunks, nc, x0));
+        else TRY(launch_deltas_sorted<uint32_t>(e, slot, 1, K, nullptr, 0ull, -1, out, sum, chunks, nc, x0));
         hv.resize(chunks);
         hi.resize(chunks);
         TRY(d2h(e, hv.data(), e->t_d4.p, (size_t)chunks));

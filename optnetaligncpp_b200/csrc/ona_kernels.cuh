@@ -442,6 +442,63 @@ k_apply_edits(DevGraph g, DevTable S, DevTable Gt, DevPop pop, int first, int no
     }
 }
 
+// --------------------------------------------------------------------------------
+// Node counts for the fast swap-delta walk (ona_device.cuh, "fast walk"): one CTA per individual,
+//   cc[u] = sum over adjList1[u] entries t with mask bit on of A2[aln[u]][aln[t]]     u < n1
+//   ic[v] = number of adjList2[v] entries whose pre-image is real and unmasked         v < n2
+// accumulated over the UNIQUE edge lists (each edge feeds both of its ends; multiplicities of
+// duplicate edge lines from ew1 / ew2) with 16-bit shared-memory counters -- two per 32-bit word,
+// no carry between them because a count never exceeds a degree (< 65536, checked at engine
+// creation) -- and written to nc[pl][0..n1) / nc[pl][ic_off..ic_off+n2).
+// --------------------------------------------------------------------------------
+#ifndef ONA_COUNT_THREADS
+#define ONA_COUNT_THREADS 512
+#endif
+constexpr int kCountThreads = ONA_COUNT_THREADS;
+__device__ __forceinline__ void count_add(uint32_t* words, int i, int v) {
+    atomicAdd(words + (i >> 1), (uint32_t)v << ((i & 1) * 16));
+}
+template <typename T>
+__global__ void __launch_bounds__(kCountThreads)
+k_node_counts(DevGraph g, DevPop pop, int first, unsigned short* __restrict__ nc, int ncs, int ic_off) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
+    T *s_aln, *s_inv;
+    const int pl = blockIdx.x, p = first + pl;
+    const size_t state_bytes = sizeof(T) == 2 ? (size_t)2 * pop.n2p * 2 : 0;
+    uint32_t* s_cc = reinterpret_cast<uint32_t*>(smem_raw + state_bytes);
+    const int wc = (g.n1 + 1) / 2, wi = (g.n2 + 1) / 2;
+    uint32_t* s_ic = s_cc + wc;
+    for (int i = threadIdx.x; i < wc + wi; i += blockDim.x) s_cc[i] = 0u;
+    State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
+    __syncthreads();
+    for (int e = threadIdx.x; e < g.ne1; e += blockDim.x) {
+        const int u = __ldg(g.eu1 + e), v = __ldg(g.ev1 + e);
+        const uint32_t ru = s_aln[u], rv = s_aln[v];
+        const bool mu = !(ru & FLAG), mv = !(rv & FLAG);
+        if ((mu | mv) && probe(g, (int)(ru & MASK), (int)(rv & MASK))) {
+            const int w = g.ew1 ? __ldg(g.ew1 + e) : 1;
+            if (mv) count_add(s_cc, u, w);
+            if (mu && u != v) count_add(s_cc, v, w);
+        }
+    }
+    for (int e = threadIdx.x; e < g.ne2; e += blockDim.x) {
+        const int v = __ldg(g.eu2 + e), w2 = __ldg(g.ev2 + e);
+        const bool av = s_inv[v] < (uint32_t)g.n1, aw = s_inv[w2] < (uint32_t)g.n1;
+        if (av | aw) {
+            const int w = g.ew2 ? __ldg(g.ew2 + e) : 1;
+            if (aw) count_add(s_ic, v, w);
+            if (av && v != w2) count_add(s_ic, w2, w);
+        }
+    }
+    __syncthreads();
+    unsigned short* out = nc + (size_t)pl * ncs;
+    const unsigned short* h_cc = reinterpret_cast<const unsigned short*>(s_cc);
+    const unsigned short* h_ic = reinterpret_cast<const unsigned short*>(s_ic);
+    for (int i = threadIdx.x; i < g.n1; i += blockDim.x) out[i] = h_cc[i];
+    for (int i = threadIdx.x; i < g.n2; i += blockDim.x) out[ic_off + i] = h_ic[i];
+}
+
 // per-individual summaries of the swap-delta kernel (null = not wanted)
 struct DeltaSummary {
     int* num_improved;    // [count] (atomic)
@@ -539,14 +596,21 @@ __device__ __forceinline__ void sort_pass(const int (&key)[PER], unsigned short 
     __syncthreads();
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kSortThreads, ONA_SORT_MINBLOCKS)
+// FAST: the walk on precomputed node counts (nc, from k_node_counts on the same slots; see
+// "fast walk" in ona_device.cuh) -- same results, about a third of the list items.
+#ifndef ONA_FAST_MINBLOCKS
+#define ONA_FAST_MINBLOCKS 3
+#endif
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(kSortThreads, FAST ? ONA_FAST_MINBLOCKS : ONA_SORT_MINBLOCKS)
 k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first, int K,
                      const int* __restrict__ xy, unsigned long long seed, long long island_offset,
-                     int obj, DevDeltaOut out, DeltaSummary sum, int* __restrict__ err_flag, int grid_x0) {
+                     int obj, DevDeltaOut out, DeltaSummary sum, int* __restrict__ err_flag, int grid_x0,
+                     const unsigned short* __restrict__ nc, int ncs, int ic_off) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int2 s_xy[kSortCap];                 // proposals of this pass, original order
     __shared__ int2 s_res[kSortCap];                // (dcons, dind), original order
+    __shared__ uint2 s_plan[FAST ? kSortCap : 1];   // fast walk: the two packed walks of every candidate
     __shared__ unsigned short s_order[kSortCap];    // sorted position -> candidate
     __shared__ unsigned short s_cnt[kSortWarps * kSortPer][kSortBins];  // per (virtual) warp histogram
     __shared__ int s_nhub, s_next;
@@ -599,7 +663,23 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                 s_xy[i] = make_int2(x, y);
             }
             const SwapCtx cx = make_ctx<T>(g, s_aln, x, y);
-            key[j] = i < n ? min(make_plan(g, cx).e3, kSortBins - 1) : -1;
+            int quads;
+            if (FAST) {
+                // everything that does not depend on the walk is done here, in original order with
+                // all of its (independent) loads in flight at once: the plan, and the closed-form
+                // part of the delta (fast_delta is linear in the two walked sums)
+                const FastPlan fp = make_fast_plan(g, cx);
+                quads = fp.e1;
+                if (i < n) {
+                    int dc0, di0;
+                    fast_delta(g, cx, nc + (size_t)pl * ncs, ic_off, 0, 0, dc0, di0);
+                    s_res[i] = make_int2(dc0, di0);
+                    s_plan[i] = pack_fast_plan(fp);
+                }
+            } else {
+                quads = make_plan(g, cx).e3;
+            }
+            key[j] = i < n ? min(quads, kSortBins - 1) : -1;
         }
         sort_pass<kSortThreads, kSortPer>(key, s_cnt, s_order, &s_nhub, &s_next);
         // ---- C: walk.  Warps pull work units, longest first: a hub (walked by the whole warp)
@@ -613,16 +693,26 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                 const int i = s_order[u];
                 const int2 q = s_xy[i];
                 const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
-                const QuadPlan pl4 = make_plan(g, cx);
-                int dc, di, seen;
-                walk_plan<T>(g, s_aln, s_inv, cx, pl4, lane, 32, dc, di, seen);
-                dc = warp_sum<int>(dc);
-                di = warp_sum<int>(di);
-                seen = __reduce_or_sync(0xffffffffu, (unsigned)seen);
-                if (lane == 0) {
-                    special_terms(g, cx, seen, dc, di);
-                    s_res[i] = make_int2(dc, di);
+                int dc, di;
+                if (FAST) {
+                    const FastPlan fp = make_fast_plan(g, cx);   // hubs may exceed the packed length field
+                    int ix, iy;
+                    walk_fast<T>(g, s_aln, s_inv, cx, fp, lane, 32, ix, iy);
+                    ix = warp_sum<int>(ix);
+                    iy = warp_sum<int>(iy);
+                    const int2 base = s_res[i];
+                    dc = base.x + ix + iy;
+                    di = base.y;
+                } else {
+                    const QuadPlan pl4 = make_plan(g, cx);
+                    int seen;
+                    walk_plan<T>(g, s_aln, s_inv, cx, pl4, lane, 32, dc, di, seen);
+                    dc = warp_sum<int>(dc);
+                    di = warp_sum<int>(di);
+                    seen = __reduce_or_sync(0xffffffffu, (unsigned)seen);
+                    if (lane == 0) special_terms(g, cx, seen, dc, di);
                 }
+                if (lane == 0) s_res[i] = make_int2(dc, di);
                 continue;
             }
             const int pos = nhub + (u - nhub) * 32 + lane;
@@ -631,10 +721,20 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                 const int i = s_order[pos];
                 const int2 q = s_xy[i];
                 const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
-                const QuadPlan pl4 = make_plan(g, cx);
-                int dc, di, seen;
-                walk_plan<T>(g, s_aln, s_inv, cx, pl4, 0, 1, dc, di, seen);
-                if (seen) special_terms(g, cx, seen, dc, di);
+                int dc, di;
+                if (FAST) {
+                    const FastPlan fp = unpack_fast_plan(s_plan[i]);   // never a hub here: lengths fit
+                    int ix, iy;
+                    walk_fast<T>(g, s_aln, s_inv, cx, fp, 0, 1, ix, iy);
+                    const int2 base = s_res[i];
+                    dc = base.x + ix + iy;
+                    di = base.y;
+                } else {
+                    const QuadPlan pl4 = make_plan(g, cx);
+                    int seen;
+                    walk_plan<T>(g, s_aln, s_inv, cx, pl4, 0, 1, dc, di, seen);
+                    if (seen) special_terms(g, cx, seen, dc, di);
+                }
                 s_res[i] = make_int2(dc, di);
             }
         }

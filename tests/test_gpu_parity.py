@@ -11,6 +11,14 @@ from oracle import port
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["classic-walk", "fast-walk"])
+def swap_delta_walk(request, monkeypatch):
+    """every test runs with both walks of the swap-delta kernel: the classic one (both neighbour
+    lists of x and y) and the fast one on precomputed node counts (normally chosen from 4096
+    candidates per individual on; ONA_FAST_MIN_K is read when an engine is created)"""
+    monkeypatch.setenv("ONA_FAST_MIN_K", "-1" if request.param == "classic-walk" else "0")
+
 ALL = list(range(10))
 RTOL = 1e-9          # north_star: "S3/ICS ratios and summed bitscores agree within 1e-9 relative"
 
@@ -83,8 +91,8 @@ def test_small_golden_hill_climb_trajectories(small_golden):
 
 
 # --------------------------------------------------------------- golden: example pair
-@pytest.fixture(scope="module")
-def example_engine(example_golden):
+@pytest.fixture
+def example_engine(example_golden, swap_delta_walk):
     g = example_golden
     e = engine_for_golden(g, g["names"], (g["bit_rows"], g["bit_cols"], g["bit_vals"]))
     return e

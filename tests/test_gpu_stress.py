@@ -11,6 +11,14 @@ from oracle import port
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["classic-walk", "fast-walk"])
+def swap_delta_walk(request, monkeypatch):
+    """every test runs with both walks of the swap-delta kernel: the classic one (both neighbour
+    lists of x and y) and the fast one on precomputed node counts (normally chosen from 4096
+    candidates per individual on; ONA_FAST_MIN_K is read when an engine is created)"""
+    monkeypatch.setenv("ONA_FAST_MIN_K", "-1" if request.param == "classic-walk" else "0")
+
 ALL = list(range(10))
 
 
