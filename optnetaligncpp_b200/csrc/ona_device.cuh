@@ -169,6 +169,23 @@ __device__ __forceinline__ double table_lookup(const DevTable& t, int r, int c) 
     }
 }
 
+// Neighbourhood signatures (DevGraph::sig1 / sig2): bit (id & 31) of .x, bit ((id >> 5) & 31) of
+// .y, bit ((id >> 10) & 31) of .z and -- ONA_BLOOM4 -- bit (id * 0x9E3779B1 >> 27) of .w.  For
+// graphs of a few thousand nodes the third slice has only a handful of distinct values, so the
+// fourth, multiplicative word is what brings the false-positive rate of a degree-10 row from ~2 %
+// to ~0.5 %: every false positive is a predicated L2 probe that the whole warp waits for.
+#ifndef ONA_BLOOM4
+#define ONA_BLOOM4 1
+#endif
+__host__ __device__ __forceinline__ unsigned sig_slot4(unsigned id) { return (id * 0x9E3779B1u) >> 27; }
+__device__ __forceinline__ unsigned nbr_sig_bit(const uint4& sg, unsigned id) {
+    unsigned r = (sg.x >> (id & 31u)) & (sg.y >> ((id >> 5) & 31u)) & (sg.z >> ((id >> 10) & 31u));
+#if ONA_BLOOM4
+    r &= sg.w >> sig_slot4(id);
+#endif
+    return r & 1u;
+}
+
 __device__ __forceinline__ bool sig_has(const uint4& sg, int id) {
     const unsigned u = (unsigned)id;
     return (((sg.x >> (u & 31u)) & (sg.y >> ((u >> 5) & 31u)) & (sg.z >> ((u >> 10) & 31u))) & 1u) != 0u;
@@ -289,10 +306,10 @@ __device__ __forceinline__ void quad_item(const DevGraph& g, const QuadCtx& qc, 
     is0 |= t == qc.sp0;
     is1 |= t == qc.sp1;
     const bool plain = (t != qc.sp0) & (t != qc.sp1);
-    const unsigned it = r & MASK, h1 = it >> 5, h2 = it >> 10;  // shifts use the low 5 bits
+    const unsigned it = r & MASK, h1 = it >> 5;
     const bool live = plain & qc.cons & !(r & FLAG);
-    const bool pX = live & ((((rs.sx.x >> (it & 31u)) & (rs.sx.y >> (h1 & 31u)) & (rs.sx.z >> (h2 & 31u))) & 1u) != 0u);
-    const bool pY = live & ((((rs.sy.x >> (it & 31u)) & (rs.sy.y >> (h1 & 31u)) & (rs.sy.z >> (h2 & 31u))) & 1u) != 0u);
+    const bool pX = live & (nbr_sig_bit(rs.sx, it) != 0u);
+    const bool pY = live & (nbr_sig_bit(rs.sy, it) != 0u);
     unsigned wX = 0u, wY = 0u;
     if (pX) wX = __ldg(g.adj2 + (unsigned)(rs.rax + h1));
     if (pY) wY = __ldg(g.adj2 + (unsigned)(rs.ray + h1));
@@ -507,7 +524,7 @@ __device__ __forceinline__ int fast_item(const T* table, uint32_t lim, const uin
     const uint32_t r = table[t];
     const bool live = (t != sp0) & (t != sp1) & (r < lim);
     const unsigned it = r & MASK, s0 = it & 31u, h1 = it >> 5;
-    const bool hit = live & ((((sg.x >> s0) & (sg.y >> (h1 & 31u)) & (sg.z >> ((it >> 10) & 31u))) & 1u) != 0u);
+    const bool hit = live & (nbr_sig_bit(sg, it) != 0u);
     unsigned w = 0u;
     if (hit) w = __ldg(row + h1);
     return (int)((w >> s0) & 1u);
@@ -532,9 +549,10 @@ __device__ __forceinline__ void walk_fast(const DevGraph& g, const T* s_aln, con
         sg1 = p.side1 ? __ldg(g.sig1 + c.y) : __ldg(g.sig2 + c.ax);
         row1 = p.side1 ? g.adj1 + (size_t)c.y * (size_t)g.W1 : g.adj2 + (size_t)c.ax * (size_t)g.W;
     }
-    for (int q = first; q < p.e1; q += stride) {
-        const bool w1 = q >= p.e0;
-        const int4 t = __ldg(g.cq1 + (w1 ? p.b1 : p.b0) + q);
+#ifndef ONA_FAST_UNROLL2
+#define ONA_FAST_UNROLL2 1
+#endif
+    auto quad = [&](const int4& t, bool w1) {
         const int side = w1 ? p.side1 : p.side0;
         const T* table = side ? s_inv : s_aln;
         const uint32_t lim = side ? (uint32_t)g.n1 : FLAG;
@@ -545,7 +563,26 @@ __device__ __forceinline__ void walk_fast(const DevGraph& g, const T* s_aln, con
                       fast_item<T>(table, lim, sg, row, sp0, sp1, t.z) + fast_item<T>(table, lim, sg, row, sp0, sp1, t.w);
         if (w1) iy += n;
         else ix += n;
+    };
+#if ONA_FAST_UNROLL2
+    // two quads per trip, both requested before either is scored: the lists are short (1-3 quads),
+    // so this halves the number of dependent L2 round trips of a candidate.  A missing second quad
+    // is the padding quad (id n2: masked off in both tables, contributes nothing).
+    for (int q = first; q < p.e1; q += 2 * stride) {
+        const int q2 = q + stride;
+        const bool wa = q >= p.e0, wb = q2 >= p.e0;
+        const int4 ta = __ldg(g.cq1 + (wa ? p.b1 : p.b0) + q);
+        int4 tb = make_int4(g.n2, g.n2, g.n2, g.n2);
+        if (q2 < p.e1) tb = __ldg(g.cq1 + (wb ? p.b1 : p.b0) + q2);
+        quad(ta, wa);
+        quad(tb, wb);
     }
+#else
+    for (int q = first; q < p.e1; q += stride) {
+        const bool w1 = q >= p.e0;
+        quad(__ldg(g.cq1 + (w1 ? p.b1 : p.b0) + q), w1);
+    }
+#endif
 }
 
 __device__ __forceinline__ int bit_of(const uint32_t* bits, int i) {

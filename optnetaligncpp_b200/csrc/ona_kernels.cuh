@@ -458,45 +458,62 @@ constexpr int kCountThreads = ONA_COUNT_THREADS;
 __device__ __forceinline__ void count_add(uint32_t* words, int i, int v) {
     atomicAdd(words + (i >> 1), (uint32_t)v << ((i & 1) * 16));
 }
+// grid = (2, individuals): CTA 0 of an individual counts cc from net1's edges (needs aln only),
+// CTA 1 counts ic from net2's edges (needs alnInv only)
 template <typename T>
 __global__ void __launch_bounds__(kCountThreads)
 k_node_counts(DevGraph g, DevPop pop, int first, unsigned short* __restrict__ nc, int ncs, int ic_off) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
-    T *s_aln, *s_inv;
-    const int pl = blockIdx.x, p = first + pl;
-    const size_t state_bytes = sizeof(T) == 2 ? (size_t)2 * pop.n2p * 2 : 0;
-    uint32_t* s_cc = reinterpret_cast<uint32_t*>(smem_raw + state_bytes);
-    const int wc = (g.n1 + 1) / 2, wi = (g.n2 + 1) / 2;
-    uint32_t* s_ic = s_cc + wc;
-    for (int i = threadIdx.x; i < wc + wi; i += blockDim.x) s_cc[i] = 0u;
-    State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
-    __syncthreads();
-    for (int e = threadIdx.x; e < g.ne1; e += blockDim.x) {
-        const int u = __ldg(g.eu1 + e), v = __ldg(g.ev1 + e);
-        const uint32_t ru = s_aln[u], rv = s_aln[v];
-        const bool mu = !(ru & FLAG), mv = !(rv & FLAG);
-        if ((mu | mv) && probe(g, (int)(ru & MASK), (int)(rv & MASK))) {
-            const int w = g.ew1 ? __ldg(g.ew1 + e) : 1;
-            if (mv) count_add(s_cc, u, w);
-            if (mu && u != v) count_add(s_cc, v, w);
+    const int pl = blockIdx.y, p = first + pl;
+    const bool do_ic = blockIdx.x != 0;
+    const int n = do_ic ? g.n2 : g.n1, words = (n + 1) / 2;
+    // one packed table (uint16 ids: staged; wider ids: used in place), then the counters
+    const uint32_t* src = (do_ic ? pop.inv : pop.aln) + (size_t)p * pop.n2p;
+    const size_t table_bytes = sizeof(T) == 2 ? (size_t)pop.n2p * 2 : 0;
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw + table_bytes);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) s_cnt[i] = 0u;
+    const T* tab;
+    if (sizeof(T) == 2) {
+        T* st = reinterpret_cast<T*>(smem_raw);
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        for (int i = threadIdx.x; i < (pop.n2p >> 2); i += blockDim.x) {
+            const uint4 a = s4[i];
+            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st[4 * i + j] = (T)((av[j] & kGMask) | ((av[j] & kGFlag) ? FLAG : 0u));
         }
-    }
-    for (int e = threadIdx.x; e < g.ne2; e += blockDim.x) {
-        const int v = __ldg(g.eu2 + e), w2 = __ldg(g.ev2 + e);
-        const bool av = s_inv[v] < (uint32_t)g.n1, aw = s_inv[w2] < (uint32_t)g.n1;
-        if (av | aw) {
-            const int w = g.ew2 ? __ldg(g.ew2 + e) : 1;
-            if (aw) count_add(s_ic, v, w);
-            if (av && v != w2) count_add(s_ic, w2, w);
-        }
+        tab = st;
+    } else {
+        tab = reinterpret_cast<const T*>(src);
     }
     __syncthreads();
-    unsigned short* out = nc + (size_t)pl * ncs;
-    const unsigned short* h_cc = reinterpret_cast<const unsigned short*>(s_cc);
-    const unsigned short* h_ic = reinterpret_cast<const unsigned short*>(s_ic);
-    for (int i = threadIdx.x; i < g.n1; i += blockDim.x) out[i] = h_cc[i];
-    for (int i = threadIdx.x; i < g.n2; i += blockDim.x) out[ic_off + i] = h_ic[i];
+    if (!do_ic) {
+        for (int e = threadIdx.x; e < g.ne1; e += blockDim.x) {
+            const int u = __ldg(g.eu1 + e), v = __ldg(g.ev1 + e);
+            const uint32_t ru = tab[u], rv = tab[v];
+            const bool mu = !(ru & FLAG), mv = !(rv & FLAG);
+            if ((mu | mv) && probe(g, (int)(ru & MASK), (int)(rv & MASK))) {
+                const int w = g.ew1 ? __ldg(g.ew1 + e) : 1;
+                if (mv) count_add(s_cnt, u, w);
+                if (mu && u != v) count_add(s_cnt, v, w);
+            }
+        }
+    } else {
+        for (int e = threadIdx.x; e < g.ne2; e += blockDim.x) {
+            const int v = __ldg(g.eu2 + e), w2 = __ldg(g.ev2 + e);
+            const bool av = tab[v] < (uint32_t)g.n1, aw = tab[w2] < (uint32_t)g.n1;
+            if (av | aw) {
+                const int w = g.ew2 ? __ldg(g.ew2 + e) : 1;
+                if (aw) count_add(s_cnt, v, w);
+                if (av && v != w2) count_add(s_cnt, w2, w);
+            }
+        }
+    }
+    __syncthreads();
+    unsigned short* out = nc + (size_t)pl * ncs + (do_ic ? ic_off : 0);
+    const unsigned short* h = reinterpret_cast<const unsigned short*>(s_cnt);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = h[i];
 }
 
 // per-individual summaries of the swap-delta kernel (null = not wanted)
@@ -542,15 +559,22 @@ constexpr int kSortWarps = kSortThreads / 32;
 #endif
 constexpr int kHubQuads = ONA_HUB_QUADS;           // more quads than this: walked by a whole warp
 constexpr int kSortBins = kHubQuads + 2;           // 0..kHubQuads exact, last bin = hubs
+#ifndef ONA_FAST_HUB_QUADS
+#define ONA_FAST_HUB_QUADS 8
+#endif
+// the fast walk's lists are short (2.6 quads per candidate on the yeast-fly pair): hubs start earlier
+constexpr int kFastHubQuads = ONA_FAST_HUB_QUADS < ONA_HUB_QUADS ? ONA_FAST_HUB_QUADS : ONA_HUB_QUADS;
+constexpr int kFastBins = kFastHubQuads + 2;
 
 // Counting sort of one pass by work key (quads to walk), longest first: per-(virtual-)warp
 // histograms by ballots (no shared-memory atomics), an exclusive scan over (bin descending,
 // warp ascending) by warp 0, then the scatter.  key[j] belongs to candidate j*kSortThreads+tid
 // (-1 = beyond the pass).  On return s_order[pos] = candidate, *s_nhub = number of hubs (they
 // come first) and *s_next = 0 (the work-unit counter).  All threads of the CTA must call.
-template <int THREADS, int PER>
+template <int THREADS, int PER, int BINS = kSortBins>
 __device__ __forceinline__ void sort_pass(const int (&key)[PER], unsigned short (*s_cnt)[kSortBins],
                                           unsigned short* s_order, int* s_nhub, int* s_next) {
+    static_assert(BINS <= kSortBins, "histogram rows hold kSortBins columns");
     constexpr int WARPS = THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -560,7 +584,7 @@ __device__ __forceinline__ void sort_pass(const int (&key)[PER], unsigned short 
         const int k = key[j];
         int r = 0;
 #pragma unroll
-        for (int b = 0; b < kSortBins; ++b) {
+        for (int b = 0; b < BINS; ++b) {
             const unsigned m = __ballot_sync(0xffffffffu, k == b);
             if (k == b) r = __popc(m & lt_mask);
             if (lane == 0) s_cnt[j * WARPS + warp][b] = (unsigned short)__popc(m);
@@ -571,7 +595,7 @@ __device__ __forceinline__ void sort_pass(const int (&key)[PER], unsigned short 
     if (warp == 0) {
         int running = 0;
         constexpr int NV = WARPS * PER;
-        for (int b = kSortBins - 1; b >= 0; --b) {
+        for (int b = BINS - 1; b >= 0; --b) {
             for (int v0 = 0; v0 < NV; v0 += 32) {
                 const int v = v0 + lane;
                 const int cnt = v < NV ? (int)s_cnt[v][b] : 0;
@@ -584,7 +608,7 @@ __device__ __forceinline__ void sort_pass(const int (&key)[PER], unsigned short 
                 if (v < NV) s_cnt[v][b] = (unsigned short)(running + incl - cnt);
                 running += __shfl_sync(0xffffffffu, incl, 31);
             }
-            if (b == kSortBins - 1 && lane == 0) { *s_nhub = running; *s_next = 0; }
+            if (b == BINS - 1 && lane == 0) { *s_nhub = running; *s_next = 0; }
         }
     }
     __syncthreads();
@@ -679,9 +703,9 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             } else {
                 quads = make_plan(g, cx).e3;
             }
-            key[j] = i < n ? min(quads, kSortBins - 1) : -1;
+            key[j] = i < n ? min(quads, (FAST ? kFastBins : kSortBins) - 1) : -1;
         }
-        sort_pass<kSortThreads, kSortPer>(key, s_cnt, s_order, &s_nhub, &s_next);
+        sort_pass<kSortThreads, kSortPer, FAST ? kFastBins : kSortBins>(key, s_cnt, s_order, &s_nhub, &s_next);
         // ---- C: walk.  Warps pull work units, longest first: a hub (walked by the whole warp)
         //      or 32 consecutive sorted candidates (one per lane, equal loop lengths)
         const int nhub = s_nhub;
@@ -812,10 +836,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
 // --------------------------------------------------------------------------------
 constexpr int kRound = 32;
 
-__device__ __forceinline__ bool bloom_has(const uint4& sg, int id) {
-    const unsigned u = (unsigned)id;
-    return (((sg.x >> (u & 31u)) & (sg.y >> ((u >> 5) & 31u)) & (sg.z >> ((u >> 10) & 31u))) & 1u) != 0u;
-}
+__device__ __forceinline__ bool bloom_has(const uint4& sg, int id) { return nbr_sig_bit(sg, (unsigned)id) != 0u; }
 
 // what one proposal of the round published for the pair tests and the resolve
 struct RoundSlot {
@@ -867,7 +888,7 @@ __device__ __forceinline__ void correct_delta(const DevGraph& g, const T* s_aln,
 // u1 / u2: the unions n1x|n1y and n2x|n2y of j's signatures -- if none of i's four ids is in
 // them, none of the eight pair tests below can fire, which settles most pairs after four tests.
 __device__ __forceinline__ uint4 bloom_or(const uint4& a, const uint4& b) {
-    return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, 0u);
+    return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w);
 }
 __device__ __forceinline__ bool commit_conflicts(const DevGraph& g, const RoundSlot& j, const uint4& u1,
                                                  const uint4& u2, const RoundSlot& i) {

@@ -95,10 +95,14 @@ def main():
     if os.environ.get("ONA_AB_CHILD"):
         return child()
     for lib in sys.argv[1:]:
-        env = dict(os.environ, ONA_AB_CHILD="1", ONA_LIB_PATH=os.path.join(ROOT, lib))
+        extra = {}
+        if "@" in lib:                      # lib.so@VAR=value,VAR2=value2
+            lib, _, kv = lib.partition("@")
+            extra = dict(item.split("=", 1) for item in kv.split(","))
+        env = dict(os.environ, ONA_AB_CHILD="1", ONA_LIB_PATH=os.path.join(ROOT, lib), **extra)
         out = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True)
         line = [l for l in out.stdout.splitlines() if l.startswith("AB ")]
-        print("%-40s %s" % (lib, line[0][3:] if line else "FAILED: " + out.stderr[-600:]))
+        print("%-40s %s %s" % (lib, extra or "", line[0][3:] if line else "FAILED: " + out.stderr[-600:]))
 
 
 if __name__ == "__main__":

@@ -148,7 +148,8 @@ def test_nsgaii_driver(world):
         a = ref.Aln.load(w["n1"], w["n2"], row[0], w["B"], None)
         C_seed, I = a.counters()[0], a.counters()[1]
         E1 = w["pair"].E1
-        assert row[1] in [fmt(C / (E1 + I - C)) for C in (C_seed, C_seed + 1)], (row, C_seed, I)
+        # the loader's seed and the driver's running count may each sit one below the true count (H1)
+        assert row[1] in [fmt(C / (E1 + I - C)) for C in (C_seed - 1, C_seed, C_seed + 1)], (row, C_seed, I)
         assert row[2] == fmt(a.sum_blast())
         best = max(best, float(row[1]))
     assert best > 0.01                                         # 3 generations x 2000 climb iterations
