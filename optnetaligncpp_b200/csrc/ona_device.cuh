@@ -77,12 +77,10 @@ struct DevGraph {
     const int* ew1;
     const int* ew2;
     int dup;  // any duplicate in either network
-    // fast swap-delta walk (k_swap_deltas_sorted<T, true>): per node, quad range packed as
-    // base << 8 | min(quads, 255) (255 = look it up in rq), and self-loop bits of both networks
+    // fast swap-delta walk (k_swap_deltas_sorted<T, true>): one word per node = quad base << 8 |
+    // has-self-loop << 7 | min(quads, 127) (127 = look the count up in rq)
     const uint32_t* pk1;
     const uint32_t* pk2;
-    const uint32_t* self1;
-    const uint32_t* self2;
 };
 
 // BLASTDict / GOCDict on the device: dense fp64 matrix, or an open-addressing hash of the
@@ -186,10 +184,7 @@ __device__ __forceinline__ unsigned nbr_sig_bit(const uint4& sg, unsigned id) {
     return r & 1u;
 }
 
-__device__ __forceinline__ bool sig_has(const uint4& sg, int id) {
-    const unsigned u = (unsigned)id;
-    return (((sg.x >> (u & 31u)) & (sg.y >> ((u >> 5) & 31u)) & (sg.z >> ((u >> 10) & 31u))) & 1u) != 0u;
-}
+__device__ __forceinline__ bool sig_has(const uint4& sg, int id) { return nbr_sig_bit(sg, (unsigned)id) != 0u; }
 // the two lookups S[r][c0], S[r][c1] of one row, each gated by a flag
 __device__ __forceinline__ void row_lookup2(const DevTable& t, int r, bool want0, int c0, bool want1, int c1,
                                             double& v0, double& v1) {
@@ -463,20 +458,32 @@ struct FastPlan {
     int b0, b1;   // cq index of quad q is b0 + q (walk 0) / b1 + q (walk 1; b1 is pre-shifted by -e0)
     int side0, side1;  // 0: the net1 list is walked, 1: the net2 list
 };
-__device__ __forceinline__ void quad_range(const uint32_t* pk, const int* rq, int node, int& base, int& cnt) {
-    const uint32_t w = __ldg(pk + node);
-    base = (int)(w >> 8);     // index into the combined quad array (net1's rows, then net2's)
-    cnt = (int)(w & 255u);
-    if (cnt == 255) cnt = __ldg(rq + node + 1) - __ldg(rq + node);
+// the packed node words of the four nodes a candidate touches (0 for a dummy position)
+struct NodeWords {
+    uint32_t wx, wy, wax, way;
+};
+__device__ __forceinline__ NodeWords load_node_words(const DevGraph& g, const SwapCtx& c) {
+    NodeWords w;
+    w.wx = c.xr ? __ldg(g.pk1 + c.x) : 0u;
+    w.wy = c.yr ? __ldg(g.pk1 + c.y) : 0u;
+    w.wax = __ldg(g.pk2 + c.ax);
+    w.way = __ldg(g.pk2 + c.ay);
+    return w;
 }
-__device__ __forceinline__ FastPlan make_fast_plan(const DevGraph& g, const SwapCtx& c) {
+__device__ __forceinline__ void quad_range(uint32_t w, const int* rq, int node, int& base, int& cnt) {
+    base = (int)(w >> 8);     // index into the combined quad array (net1's rows, then net2's)
+    cnt = (int)(w & 127u);
+    if (cnt == 127) cnt = __ldg(rq + node + 1) - __ldg(rq + node);
+}
+__device__ __forceinline__ int word_self(uint32_t w) { return (int)((w >> 7) & 1u); }
+__device__ __forceinline__ FastPlan make_fast_plan(const DevGraph& g, const SwapCtx& c, const NodeWords& w) {
     FastPlan p;
     p.e0 = p.e1 = p.b0 = p.b1 = p.side0 = p.side1 = 0;
     if (c.x == c.y) return p;
     if (c.xr & (c.my != 0)) {   // I(x, a_y)
         int b1l, q1l, b2l, q2l;
-        quad_range(g.pk1, g.rq1, c.x, b1l, q1l);
-        quad_range(g.pk2, g.rq2, c.ay, b2l, q2l);
+        quad_range(w.wx, g.rq1, c.x, b1l, q1l);
+        quad_range(w.way, g.rq2, c.ay, b2l, q2l);
         p.side0 = (g.dup == 0 && q2l < q1l) ? 1 : 0;
         p.b0 = p.side0 ? b2l : b1l;
         p.e0 = p.side0 ? q2l : q1l;
@@ -484,8 +491,8 @@ __device__ __forceinline__ FastPlan make_fast_plan(const DevGraph& g, const Swap
     int len1 = 0;
     if (c.yr & (c.mx != 0)) {   // I(y, a_x)
         int b1l, q1l, b2l, q2l;
-        quad_range(g.pk1, g.rq1, c.y, b1l, q1l);
-        quad_range(g.pk2, g.rq2, c.ax, b2l, q2l);
+        quad_range(w.wy, g.rq1, c.y, b1l, q1l);
+        quad_range(w.wax, g.rq2, c.ax, b2l, q2l);
         p.side1 = (g.dup == 0 && q2l < q1l) ? 1 : 0;
         p.b1 = p.side1 ? b2l : b1l;
         len1 = p.side1 ? q2l : q1l;
@@ -585,23 +592,20 @@ __device__ __forceinline__ void walk_fast(const DevGraph& g, const T* s_aln, con
 #endif
 }
 
-__device__ __forceinline__ int bit_of(const uint32_t* bits, int i) {
-    return (int)((__ldg(bits + (i >> 5)) >> (i & 31)) & 1u);
-}
 // The closed forms around the two walked sums (see the derivation in DESIGN.md, section 4.1):
 // conservedCount before / after the exchange for x and y (Alignment.cpp:492-493, 506-507) and
 // inducedCount before / after for a_x and a_y (:494-495, 508-509), with the node counts standing
 // in for every sum that does not involve the partner node.
 //   nc: this individual's node counts, cc at [0, n1), ic at [ic_off, ic_off + n2)
-__device__ __forceinline__ void fast_delta(const DevGraph& g, const SwapCtx& c, const unsigned short* nc, int ic_off,
-                                           int ix, int iy, int& dc, int& di) {
+__device__ __forceinline__ void fast_delta(const DevGraph& g, const SwapCtx& c, const NodeWords& nw,
+                                           const unsigned short* nc, int ic_off, int ix, int iy, int& dc, int& di) {
     dc = 0;
     di = 0;
     if (c.x == c.y) return;
     // multiplicities of the entries that involve the exchanged nodes themselves
     int sxx = 0, syy = 0, mxy = 0;
-    if (c.xr) sxx = bit_of(g.self1, c.x);
-    if (c.yr) syy = bit_of(g.self1, c.y);
+    if (c.xr) sxx = word_self(nw.wx);
+    if (c.yr) syy = word_self(nw.wy);
     if (c.xr & c.yr) mxy = (int)((__ldg(g.adj1 + (size_t)c.x * (size_t)g.W1 + (c.y >> 5)) >> (c.y & 31)) & 1u);
     if (g.dup) {
         if (sxx) sxx = list_multiplicity(g.rp1, g.col1, c.x, c.x);
@@ -620,7 +624,7 @@ __device__ __forceinline__ void fast_delta(const DevGraph& g, const SwapCtx& c, 
     const int cYn = c.mx * yr * (iy + syy * c.mx * a_xx);
     dc = cXn + cYn - cX - cY;
     if (ich) {
-        int s2x = bit_of(g.self2, c.ax), s2y = bit_of(g.self2, c.ay), m2 = a_xy;
+        int s2x = word_self(nw.wax), s2y = word_self(nw.way), m2 = a_xy;
         if (g.dup) {
             if (s2x) s2x = list_multiplicity(g.rp2, g.col2, c.ax, c.ax);
             if (s2y) s2y = list_multiplicity(g.rp2, g.col2, c.ay, c.ay);

@@ -56,7 +56,7 @@ struct DevBuf {  // grow-only device scratch
 constexpr int kPipeSlices = 32;  // upper bound; the default number of slices is pipe_slices
 
 struct PipeKey {          // everything a captured ona_swap_deltas pipeline has baked in
-    const void* ptrs[19];
+    const void* ptrs[20];
     int ints[8];
 };
 struct PipeGraph {
@@ -87,7 +87,7 @@ struct ona_engine {
     bool use_graphs = true;             // replay the host-buffer pipeline of ona_swap_deltas as a CUDA graph
     std::vector<PipeGraph> graphs;
     unsigned long long graph_clock = 0;
-    DevBuf<unsigned short> t_nc;
+    DevBuf<unsigned short> t_nc, t_st16;   // node counts; 16-bit copy of the scored slots' state
     int sm_count = 148;
     size_t smem_optin = 0;
 
@@ -277,6 +277,9 @@ int build_table(ona_engine* e, const ona_score_table& t, int n1, int n2, DevTabl
         rowsig[r].x |= 1u << (c & 31);
         rowsig[r].y |= 1u << ((c >> 5) & 31);
         rowsig[r].z |= 1u << ((c >> 10) & 31);
+#if ONA_BLOOM4
+        rowsig[r].w |= 1u << sig_slot4((unsigned)c);
+#endif
     }
     int rc = upload<uint4>(e, rowsig, &out->rowsig);
     if (rc) return rc;
@@ -347,8 +350,8 @@ template <typename T>
 int prepare_counts_t(ona_engine* e, int first, int count) {
     int rc = set_smem(k_node_counts<T>, counts_smem(e));
     if (rc) return rc;
-    k_node_counts<T><<<dim3(2, count), kCountThreads, counts_smem(e), e->stream>>>(e->g, e->pop, first, e->t_nc.p,
-                                                                                  e->nc_stride, e->nc_ic_off);
+    k_node_counts<T><<<dim3(2, count), kCountThreads, counts_smem(e), e->stream>>>(
+        e->g, e->pop, first, e->t_nc.p, e->nc_stride, e->nc_ic_off, e->small_ids ? e->t_st16.p : nullptr);
     e->launches++;
     CU(cudaGetLastError());
     return ONA_OK;
@@ -357,6 +360,7 @@ int prepare_counts(ona_engine* e, int first, int count, int K, const unsigned sh
     *nc = nullptr;
     if (!e->fast_ok || K < e->fast_min_k) return ONA_OK;
     CU(e->t_nc.need((size_t)count * e->nc_stride));
+    if (e->small_ids) CU(e->t_st16.need((size_t)count * 2 * e->pop.n2p));
     const int rc = e->small_ids ? prepare_counts_t<uint16_t>(e, first, count) : prepare_counts_t<uint32_t>(e, first, count);
     if (rc) return rc;
     *nc = e->t_nc.p;
@@ -375,13 +379,14 @@ int launch_deltas_sorted(ona_engine* e, int first, int count, int K, const int* 
         if (rc) return rc;
         k_swap_deltas_sorted<T, true><<<grid, kSortThreads, smem, e->stream>>>(
             e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag,
-            grid_x0, nc, e->nc_stride, e->nc_ic_off);
+            grid_x0, nc, e->nc_stride, e->nc_ic_off,
+            e->small_ids ? e->t_st16.p + (size_t)(nc - e->t_nc.p) / e->nc_stride * 2 * e->pop.n2p : nullptr);
     } else {
         int rc = set_smem(k_swap_deltas_sorted<T, false>, smem);
         if (rc) return rc;
         k_swap_deltas_sorted<T, false><<<grid, kSortThreads, smem, e->stream>>>(
             e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag,
-            grid_x0, nullptr, 0, 0);
+            grid_x0, nullptr, 0, 0, nullptr);
     }
     e->launches++;
     CU(cudaGetLastError());
@@ -604,7 +609,9 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
                     cq.push_back(q);
                 }
                 const size_t base = off + (size_t)rq[u], cnt = cq.size() - base;
-                pk[u] = (uint32_t)((base << 8) | std::min<size_t>(cnt, 255));
+                bool self = false;
+                for (int k = rp[u]; k < rp[u + 1]; ++k) self = self || col[k] == u;
+                pk[u] = (uint32_t)((base << 8) | (self ? 128u : 0u) | std::min<size_t>(cnt, 127));
             }
             rq[n] = (int)(cq.size() - off);
             if (!net) ncq1 = cq.size();
@@ -616,16 +623,6 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
         if ((rc = upload<uint32_t>(e, pk1, &g.pk1))) return bail(rc);
         if ((rc = upload<uint32_t>(e, pk2, &g.pk2))) return bail(rc);
         e->fast_ok = cq.size() < ((size_t)1 << 24) && max_row < 65536;
-        for (int net = 0; net < 2; ++net) {  // self-loop bits
-            const int n = net ? pr->n2 : pr->n1;
-            const int* rp = net ? pr->rowptr2 : pr->rowptr1;
-            const int* col = net ? pr->col2 : pr->col1;
-            std::vector<uint32_t> bits((n + 31) / 32 + 1, 0u);
-            for (int u = 0; u < n; ++u)
-                for (int k = rp[u]; k < rp[u + 1]; ++k)
-                    if (col[k] == u) bits[u >> 5] |= 1u << (u & 31);
-            if ((rc = upload<uint32_t>(e, bits, net ? &g.self2 : &g.self1))) return bail(rc);
-        }
     }
     g.W1 = (pr->n1 + 31) / 32;
     {
@@ -704,7 +701,7 @@ void ona_engine_destroy(ona_engine* e) {
     e->t_i0.release(); e->t_i1.release(); e->t_i2.release(); e->t_xy.release();
     e->t_d0.release(); e->t_d1.release(); e->t_d2.release(); e->t_d3.release(); e->t_d4.release();
     e->t_seq.release(); e->t_u0.release(); e->t_mask.release(); e->t_l0.release();
-    e->t_part.release(); e->t_ticket.release(); e->t_claims.release(); e->t_nc.release();
+    e->t_part.release(); e->t_ticket.release(); e->t_claims.release(); e->t_nc.release(); e->t_st16.release();
     e->ns_dom.release(); e->ns_front.release(); e->ns_count.release(); e->ns_pos.release();
     e->ns_cnt.release(); e->ns_rank.release(); e->ns_order.release(); e->ns_offsets.release();
     e->ns_after.release(); e->ns_slot.release(); e->ns_old.release(); e->ns_keys.release();
@@ -1031,7 +1028,10 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
     if (fitness) { CU(e->t_d3.need(n * M)); out.fit = e->t_d3.p; }
     if (improved) { CU(e->t_u0.need(n)); out.improved = e->t_u0.p; }
     if (snd) { CU(e->t_d2.need(n)); out.snd = e->t_d2.p; }
-    if (e->fast_ok && K >= e->fast_min_k) CU(e->t_nc.need((size_t)count * e->nc_stride));
+    if (e->fast_ok && K >= e->fast_min_k) {
+        CU(e->t_nc.need((size_t)count * e->nc_stride));
+        if (e->small_ids) CU(e->t_st16.need((size_t)count * 2 * e->pop.n2p));
+    }
     const int slices = std::min(count, e->pipe_slices);
     // Repeated calls with the same (pinned) host buffers -- a driver's steady state -- replay a CUDA
     // graph of the whole pipeline: one launch instead of ~10 API calls per slice, whose CPU-side
@@ -1046,7 +1046,7 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
     }
     PipeKey key{};
     const void* ptrs[] = {xy, cons, ind, bits, goc, fitness, improved, snd, e->t_xy.p, out.cons, out.ind,
-                          out.bits, out.goc, out.fit, out.improved, out.snd, e->t_nc.p, e->pop.aln, e->stream};
+                          out.bits, out.goc, out.fit, out.improved, out.snd, e->t_nc.p, e->pop.aln, e->stream, e->t_st16.p};
     static_assert(sizeof(ptrs) / sizeof(ptrs[0]) == sizeof(key.ptrs) / sizeof(key.ptrs[0]), "key layout");
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) key.ptrs[i] = ptrs[i];
     key.ints[0] = first; key.ints[1] = count; key.ints[2] = K; key.ints[3] = obj; key.ints[4] = slices;

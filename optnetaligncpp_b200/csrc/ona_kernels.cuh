@@ -462,7 +462,8 @@ __device__ __forceinline__ void count_add(uint32_t* words, int i, int v) {
 // CTA 1 counts ic from net2's edges (needs alnInv only)
 template <typename T>
 __global__ void __launch_bounds__(kCountThreads)
-k_node_counts(DevGraph g, DevPop pop, int first, unsigned short* __restrict__ nc, int ncs, int ic_off) {
+k_node_counts(DevGraph g, DevPop pop, int first, unsigned short* __restrict__ nc, int ncs, int ic_off,
+              unsigned short* __restrict__ st16) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
     const int pl = blockIdx.y, p = first + pl;
@@ -482,6 +483,13 @@ k_node_counts(DevGraph g, DevPop pop, int first, unsigned short* __restrict__ nc
             const uint32_t av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) st[4 * i + j] = (T)((av[j] & kGMask) | ((av[j] & kGFlag) ? FLAG : 0u));
+            // the 16-bit form of this table, for the swap-delta CTAs of this individual to stage from
+            // (half the bytes of the packed 32-bit rows and no conversion): [aln | alnInv], n2p each
+            if (st16) {
+                const uint2 h = make_uint2((uint32_t)st[4 * i] | ((uint32_t)st[4 * i + 1] << 16),
+                                           (uint32_t)st[4 * i + 2] | ((uint32_t)st[4 * i + 3] << 16));
+                reinterpret_cast<uint2*>(st16 + ((size_t)pl * 2 + (do_ic ? 1 : 0)) * pop.n2p)[i] = h;
+            }
         }
         tab = st;
     } else {
@@ -630,7 +638,8 @@ __global__ void __launch_bounds__(kSortThreads, FAST ? ONA_FAST_MINBLOCKS : ONA_
 k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first, int K,
                      const int* __restrict__ xy, unsigned long long seed, long long island_offset,
                      int obj, DevDeltaOut out, DeltaSummary sum, int* __restrict__ err_flag, int grid_x0,
-                     const unsigned short* __restrict__ nc, int ncs, int ic_off) {
+                     const unsigned short* __restrict__ nc, int ncs, int ic_off,
+                     const unsigned short* __restrict__ st16) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int2 s_xy[kSortCap];                 // proposals of this pass, original order
     __shared__ int2 s_res[kSortCap];                // (dcons, dind), original order
@@ -643,7 +652,16 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     __shared__ long long s_besti[kSortWarps];
     T *s_aln, *s_inv;
     const int pl = blockIdx.y, p = first + pl;
-    State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
+    if (FAST && sizeof(T) == 2 && st16) {
+        // k_node_counts left this individual's state in 16-bit form: plain 16-byte copies
+        s_aln = reinterpret_cast<T*>(smem_raw);
+        s_inv = s_aln + pop.n2p;
+        const uint4* src = reinterpret_cast<const uint4*>(st16 + (size_t)pl * 2 * pop.n2p);
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+        for (int i = threadIdx.x; i < (pop.n2p >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+    } else {
+        State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
+    }
 
     Scalars cur;
     cur.C = pop.cons[p]; cur.I = pop.ind[p]; cur.size = pop.size[p];
@@ -692,11 +710,12 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                 // everything that does not depend on the walk is done here, in original order with
                 // all of its (independent) loads in flight at once: the plan, and the closed-form
                 // part of the delta (fast_delta is linear in the two walked sums)
-                const FastPlan fp = make_fast_plan(g, cx);
+                const NodeWords nw = load_node_words(g, cx);
+                const FastPlan fp = make_fast_plan(g, cx, nw);
                 quads = fp.e1;
                 if (i < n) {
                     int dc0, di0;
-                    fast_delta(g, cx, nc + (size_t)pl * ncs, ic_off, 0, 0, dc0, di0);
+                    fast_delta(g, cx, nw, nc + (size_t)pl * ncs, ic_off, 0, 0, dc0, di0);
                     s_res[i] = make_int2(dc0, di0);
                     s_plan[i] = pack_fast_plan(fp);
                 }
@@ -719,7 +738,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                 const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
                 int dc, di;
                 if (FAST) {
-                    const FastPlan fp = make_fast_plan(g, cx);   // hubs may exceed the packed length field
+                    const FastPlan fp = make_fast_plan(g, cx, load_node_words(g, cx));   // hubs may exceed the packed length field
                     int ix, iy;
                     walk_fast<T>(g, s_aln, s_inv, cx, fp, lane, 32, ix, iy);
                     ix = warp_sum<int>(ix);
