@@ -15,6 +15,8 @@
 
 using namespace ona;
 
+#define TRY_RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
 namespace {
 
 thread_local std::string g_err;
@@ -83,11 +85,17 @@ struct ona_engine {
     int pipe_slices = 8;     // host-buffer pipeline depth of ona_swap_deltas
     bool fast_ok = false;    // the fast swap-delta walk (node counts) is usable on this problem
     int fast_min_k = 4096;   // ... and pays from this many candidates per individual on
+    int split_min_count = 32;  // full fitness: from this many individuals on, one CTA per network
     int nc_ic_off = 0, nc_stride = 0;   // layout of one individual's node counts
     bool use_graphs = true;             // replay the host-buffer pipeline of ona_swap_deltas as a CUDA graph
     std::vector<PipeGraph> graphs;
     unsigned long long graph_clock = 0;
-    DevBuf<unsigned short> t_nc, t_st16;   // node counts; 16-bit copy of the scored slots' state
+    // per-slot node counts and 16-bit state copy for the fast swap-delta walk: a pure function of a
+    // slot's (aln, mask), produced by ona_full_fitness* (k_full_fitness_split) or k_node_counts and
+    // dropped whenever the slot's alignment is changed (upload, hill climb, applied swaps / edits)
+    unsigned short* pop_nc = nullptr;
+    unsigned short* pop_st16 = nullptr;
+    std::vector<unsigned char> nc_valid;
     int sm_count = 148;
     size_t smem_optin = 0;
 
@@ -311,8 +319,49 @@ int set_smem(K kernel, size_t bytes) {
     return ONA_OK;
 }
 
+size_t counts_smem(const ona_engine* e) {   // one staged table + the larger of the two counter arrays
+    return state_smem(e) / 2 + ((size_t)(e->g.n2 + 1) / 2) * 4;
+}
+
+// storage of the per-slot node counts / 16-bit state (lazy: only engines that score swap deltas need it)
+int ensure_count_store(ona_engine* e) {
+    if (e->pop_nc || !e->fast_ok || e->P == 0) return ONA_OK;
+    CU(cudaMalloc(&e->pop_nc, (size_t)e->P * e->nc_stride * sizeof(unsigned short)));
+    if (e->small_ids) CU(cudaMalloc(&e->pop_st16, (size_t)e->P * 2 * e->pop.n2p * sizeof(unsigned short)));
+    e->nc_valid.assign((size_t)e->P, 0);
+    return ONA_OK;
+}
+void invalidate_counts(ona_engine* e, int first, int count) {
+    if (e->nc_valid.empty()) return;
+    std::fill(e->nc_valid.begin() + first, e->nc_valid.begin() + first + count, (unsigned char)0);
+}
+
 template <typename T>
 int launch_full(ona_engine* e, int first, int count, int seed_mode, int sequential, FullOut out) {
+    if (e->fast_ok && count >= e->split_min_count) {
+        // two CTAs per individual (one per network); node counts and 16-bit state as a by-product
+        TRY_RC(ensure_count_store(e));
+        double* seq = nullptr;
+        if (sequential) {
+            CU(e->t_seq.need((size_t)count * 2 * e->g.n1));
+            seq = e->t_seq.p;
+        }
+        CU(e->t_part.need((size_t)count * 2));
+        if (e->t_ticket.cap < (size_t)count) {
+            CU(e->t_ticket.need((size_t)count));
+            CU(cudaMemsetAsync(e->t_ticket.p, 0, e->t_ticket.cap * sizeof(unsigned int), e->stream));
+        }
+        int rc = set_smem(k_full_fitness_split<T>, counts_smem(e));
+        if (rc) return rc;
+        k_full_fitness_split<T><<<dim3(2, count), kFullSplitThreads, counts_smem(e), e->stream>>>(
+            e->g, e->S, e->G, e->ob, e->pop, first, seed_mode, sequential, seq, e->t_part.p, e->t_ticket.p, out,
+            e->pop_nc + (size_t)first * e->nc_stride, e->nc_stride, e->nc_ic_off,
+            e->pop_st16 ? e->pop_st16 + (size_t)first * 2 * e->pop.n2p : nullptr);
+        e->launches++;
+        CU(cudaGetLastError());
+        std::fill(e->nc_valid.begin() + first, e->nc_valid.begin() + first + count, (unsigned char)1);
+        return ONA_OK;
+    }
     const size_t smem = state_smem(e);
     int rc = set_smem(k_full_fitness<T>, smem);
     if (rc) return rc;
@@ -339,31 +388,37 @@ int launch_full(ona_engine* e, int first, int count, int seed_mode, int sequenti
     return ONA_OK;
 }
 
-size_t counts_smem(const ona_engine* e) {   // one staged table + the larger of the two counter arrays
-    return state_smem(e) / 2 + ((size_t)(e->g.n2 + 1) / 2) * 4;
-}
-
-// Node counts of slots first..first+count in their CURRENT state (recomputed by every swap-delta
-// call: nothing is cached across calls) for the fast walk; *nc = nullptr when the classic walk is
-// to be used (problem too large for the 16-bit counters, or too few candidates to pay for it).
+// Node counts of slots first..first+count for the fast walk: taken from the slots' last evaluation
+// when their alignments have not changed since, else counted now (k_node_counts).  *nc = nullptr
+// when the classic walk is to be used (problem too large for the 16-bit counters, or too few
+// candidates to pay for the counting).
 template <typename T>
 int prepare_counts_t(ona_engine* e, int first, int count) {
     int rc = set_smem(k_node_counts<T>, counts_smem(e));
     if (rc) return rc;
     k_node_counts<T><<<dim3(2, count), kCountThreads, counts_smem(e), e->stream>>>(
-        e->g, e->pop, first, e->t_nc.p, e->nc_stride, e->nc_ic_off, e->small_ids ? e->t_st16.p : nullptr);
+        e->g, e->pop, first, e->pop_nc + (size_t)first * e->nc_stride, e->nc_stride, e->nc_ic_off,
+        e->pop_st16 ? e->pop_st16 + (size_t)first * 2 * e->pop.n2p : nullptr);
     e->launches++;
     CU(cudaGetLastError());
     return ONA_OK;
 }
+bool counts_ready(const ona_engine* e, int first, int count) {
+    if (e->nc_valid.empty()) return false;
+    for (int i = first; i < first + count; ++i)
+        if (!e->nc_valid[i]) return false;
+    return true;
+}
 int prepare_counts(ona_engine* e, int first, int count, int K, const unsigned short** nc) {
     *nc = nullptr;
     if (!e->fast_ok || K < e->fast_min_k) return ONA_OK;
-    CU(e->t_nc.need((size_t)count * e->nc_stride));
-    if (e->small_ids) CU(e->t_st16.need((size_t)count * 2 * e->pop.n2p));
-    const int rc = e->small_ids ? prepare_counts_t<uint16_t>(e, first, count) : prepare_counts_t<uint32_t>(e, first, count);
-    if (rc) return rc;
-    *nc = e->t_nc.p;
+    TRY_RC(ensure_count_store(e));
+    if (!counts_ready(e, first, count)) {
+        const int rc = e->small_ids ? prepare_counts_t<uint16_t>(e, first, count) : prepare_counts_t<uint32_t>(e, first, count);
+        if (rc) return rc;
+        std::fill(e->nc_valid.begin() + first, e->nc_valid.begin() + first + count, (unsigned char)1);
+    }
+    *nc = e->pop_nc + (size_t)first * e->nc_stride;
     return ONA_OK;
 }
 
@@ -380,7 +435,7 @@ int launch_deltas_sorted(ona_engine* e, int first, int count, int K, const int* 
         k_swap_deltas_sorted<T, true><<<grid, kSortThreads, smem, e->stream>>>(
             e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag,
             grid_x0, nc, e->nc_stride, e->nc_ic_off,
-            e->small_ids ? e->t_st16.p + (size_t)(nc - e->t_nc.p) / e->nc_stride * 2 * e->pop.n2p : nullptr);
+            e->pop_st16 ? e->pop_st16 + (size_t)(nc - e->pop_nc) / e->nc_stride * 2 * e->pop.n2p : nullptr);
     } else {
         int rc = set_smem(k_swap_deltas_sorted<T, false>, smem);
         if (rc) return rc;
@@ -474,6 +529,10 @@ void free_pop(ona_engine* e) {
     drop_graphs(e);   // captured pipelines hold the population's pointers
     cudaFree(e->pop.aln); cudaFree(e->pop.inv); cudaFree(e->pop.cons); cudaFree(e->pop.ind);
     cudaFree(e->pop.size); cudaFree(e->pop.bits); cudaFree(e->pop.goc); cudaFree(e->pop.fit);
+    cudaFree(e->pop_nc); cudaFree(e->pop_st16);
+    e->pop_nc = nullptr;
+    e->pop_st16 = nullptr;
+    e->nc_valid.clear();
     const int n2p = e->pop.n2p;
     e->pop = DevPop{};
     e->pop.n2p = n2p;
@@ -673,6 +732,7 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
     e->nc_stride = e->nc_ic_off + (pr->n2 + 7) / 8 * 8;
     e->fast_ok = e->fast_ok && counts_smem(e) + 1024 <= e->smem_optin;
     if (const char* gr = getenv("ONA_E2E_GRAPH")) e->use_graphs = atoi(gr) != 0;
+    if (const char* sm = getenv("ONA_FF_SPLIT_MIN")) e->split_min_count = std::max(1, atoi(sm));
     if (const char* fk = getenv("ONA_FAST_MIN_K")) {   // 0 = always, negative = never (tests, A/B runs)
         const int v = atoi(fk);
         if (v < 0) e->fast_ok = false;
@@ -701,7 +761,7 @@ void ona_engine_destroy(ona_engine* e) {
     e->t_i0.release(); e->t_i1.release(); e->t_i2.release(); e->t_xy.release();
     e->t_d0.release(); e->t_d1.release(); e->t_d2.release(); e->t_d3.release(); e->t_d4.release();
     e->t_seq.release(); e->t_u0.release(); e->t_mask.release(); e->t_l0.release();
-    e->t_part.release(); e->t_ticket.release(); e->t_claims.release(); e->t_nc.release(); e->t_st16.release();
+    e->t_part.release(); e->t_ticket.release(); e->t_claims.release();
     e->ns_dom.release(); e->ns_front.release(); e->ns_count.release(); e->ns_pos.release();
     e->ns_cnt.release(); e->ns_rank.release(); e->ns_order.release(); e->ns_offsets.release();
     e->ns_after.release(); e->ns_slot.release(); e->ns_old.release(); e->ns_keys.release();
@@ -839,6 +899,7 @@ int ona_pop_upload(ona_engine* e, int first, int count, const int* aln, const un
     CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
     dim3 grid((e->pop.n2p + 255) / 256, count);
     k_pack_state<<<grid, 256, 0, e->stream>>>(e->pop, first, count, n2, e->t_xy.p, dmask);
+    invalidate_counts(e, first, count);
     k_check_state<<<grid, 256, 0, e->stream>>>(e->pop, first, count, n2, e->d_flag);
     k_recount_size<<<count, 256, 0, e->stream>>>(e->g, e->pop, first, count);
     e->launches += 3;
@@ -1028,10 +1089,7 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
     if (fitness) { CU(e->t_d3.need(n * M)); out.fit = e->t_d3.p; }
     if (improved) { CU(e->t_u0.need(n)); out.improved = e->t_u0.p; }
     if (snd) { CU(e->t_d2.need(n)); out.snd = e->t_d2.p; }
-    if (e->fast_ok && K >= e->fast_min_k) {
-        CU(e->t_nc.need((size_t)count * e->nc_stride));
-        if (e->small_ids) CU(e->t_st16.need((size_t)count * 2 * e->pop.n2p));
-    }
+    if (e->fast_ok && K >= e->fast_min_k) TRY(ensure_count_store(e));
     const int slices = std::min(count, e->pipe_slices);
     // Repeated calls with the same (pinned) host buffers -- a driver's steady state -- replay a CUDA
     // graph of the whole pipeline: one launch instead of ~10 API calls per slice, whose CPU-side
@@ -1046,11 +1104,12 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
     }
     PipeKey key{};
     const void* ptrs[] = {xy, cons, ind, bits, goc, fitness, improved, snd, e->t_xy.p, out.cons, out.ind,
-                          out.bits, out.goc, out.fit, out.improved, out.snd, e->t_nc.p, e->pop.aln, e->stream, e->t_st16.p};
+                          out.bits, out.goc, out.fit, out.improved, out.snd, e->pop_nc, e->pop.aln, e->stream, e->pop_st16};
     static_assert(sizeof(ptrs) / sizeof(ptrs[0]) == sizeof(key.ptrs) / sizeof(key.ptrs[0]), "key layout");
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) key.ptrs[i] = ptrs[i];
     key.ints[0] = first; key.ints[1] = count; key.ints[2] = K; key.ints[3] = obj; key.ints[4] = slices;
-    key.ints[5] = M; key.ints[6] = e->fast_min_k; key.ints[7] = (int)e->island_offset;
+    key.ints[5] = M; key.ints[6] = e->fast_min_k;
+    key.ints[7] = counts_ready(e, first, count) ? 1 : 0;   // whether the counting kernel is part of the graph
     PipeGraph* hit = nullptr;
     for (auto& gph : e->graphs)
         if (std::memcmp(&gph.key, &key, sizeof(key)) == 0) hit = &gph;
@@ -1252,6 +1311,7 @@ int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const i
     }
     CU(e->t_l0.need((size_t)count));
     TRY(launch_climb(e, first, count, iters, xy_dev, seed, objs_dev, -3, acc_dev, e->t_l0.p));
+    invalidate_counts(e, first, count);
     TRY(d2h(e, accepted, acc_dev, n));
     TRY(d2h(e, num_accepted, e->t_l0.p, (size_t)count));
     return finish_checked(e, "proposal outside [0,n2)");
@@ -1285,6 +1345,7 @@ int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters,
     }
     CU(e->t_l0.need((size_t)count));
     // claim arrays (4 x n2 x u16) live in shared memory next to the staged state when they fit
+    invalidate_counts(e, first, count);
     const size_t claim_bytes = (size_t)4 * e->g.n2 * 2;
     size_t smem = state_smem(e) + claim_bytes;
     unsigned short* claims_global = nullptr;
@@ -1320,6 +1381,7 @@ int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* 
     CU(e->t_xy.need(2 * n));
     TRY(h2d(e, e->t_xy.p, xy, 2 * n));
     TRY(launch_climb(e, first, count, nswaps, e->t_xy.p, 0ull, nullptr, -2, nullptr, nullptr));
+    invalidate_counts(e, first, count);
     return finish_checked(e, "swap outside [0,n2)");
 }
 
@@ -1334,6 +1396,7 @@ int ona_apply_edits(ona_engine* e, int first, int count, int nops, const int* op
     TRY(h2d(e, e->t_xy.p, ops, 4 * n));
     k_apply_edits<<<count, 32, 0, e->stream>>>(e->g, e->S, e->G, e->pop, first, nops,
                                                reinterpret_cast<const int4*>(e->t_xy.p), e->d_flag);
+    invalidate_counts(e, first, count);
     k_recount_size<<<count, 256, 0, e->stream>>>(e->g, e->pop, first, count);
     k_refresh_fitness<<<(count + 127) / 128, 128, 0, e->stream>>>(e->g, e->ob, e->pop, first, count);
     e->launches += 3;

@@ -81,6 +81,12 @@ __global__ void k_build_jaccard(int n1, int n2, const int* __restrict__ rp1, con
     out[(size_t)u * n2 + v] = val;
 }
 
+// 16-bit shared-memory counters, two per 32-bit word (no carry between them: a count never
+// exceeds a degree, < 65536 -- checked at engine creation)
+__device__ __forceinline__ void count_add(uint32_t* words, int i, int v) {
+    atomicAdd(words + (i >> 1), (uint32_t)v << ((i & 1) * 16));
+}
+
 // --------------------------------------------------------------------------------
 // Block reductions
 // --------------------------------------------------------------------------------
@@ -252,6 +258,178 @@ k_full_fitness(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop
         const double denom = (double)ind;
         const double ics = iset == 0 ? 0.0 : __ddiv_rn((double)cset, (double)iset);
         const int cref = __double2int_rz(__dmul_rn(ics, denom));
+        Scalars s;
+        s.C = (seed_mode == 2) ? cref : c;
+        s.I = ind;
+        s.size = sz;
+        s.bits = sb;
+        s.goc = sg;
+        if (seed_mode != 0) {
+            pop.cons[p] = s.C;
+            pop.ind[p] = s.I;
+            pop.size[p] = s.size;
+            pop.bits[p] = s.bits;
+            pop.goc[p] = s.goc;
+        }
+        for (int j = 0; j < ob.M; ++j) {
+            const double f = objective(ob.names[j], s, g.E1);
+            if (seed_mode != 0) pop.fit[(size_t)p * ob.M + j] = f;
+            if (out.fit) out.fit[(size_t)pl * ob.M + j] = f;
+        }
+        if (out.cons_true) out.cons_true[pl] = c;
+        if (out.cons_ref) out.cons_ref[pl] = cref;
+        if (out.ind) out.ind[pl] = ind;
+        if (out.bits) out.bits[pl] = sb;
+        if (out.goc) out.goc[pl] = sg;
+        if (out.size) out.size[pl] = (double)sz;
+        if (out.ics) out.ics[pl] = ics;
+    }
+}
+
+// --------------------------------------------------------------------------------
+// The same evaluation split by NETWORK instead of by edge slices: grid = (2, individuals).
+//   CTA 0  stages aln only:    net1's unique edges (conserved counts), the score sums and the size
+//   CTA 1  stages alnInv only: net2's unique edges (induced counts)
+// Each CTA moves half the state of a k_full_fitness part, and the two edge loops are exactly the
+// ones k_node_counts runs, so the per-node counts cc / ic and the 16-bit copy of the state that the
+// fast swap-delta walk needs fall out as a by-product (nc / st16, both nullable): a swap-delta call
+// on slots whose state has not changed since their last evaluation starts walking at once.
+// --------------------------------------------------------------------------------
+constexpr int kFullSplitThreads = 512;
+template <typename T>
+__global__ void __launch_bounds__(kFullSplitThreads)
+k_full_fitness_split(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first,
+                     int seed_mode, int sequential, double* __restrict__ seq_scratch,
+                     FullPartial* __restrict__ partials, unsigned int* __restrict__ tickets, FullOut out,
+                     unsigned short* __restrict__ nc, int ncs, int ic_off, unsigned short* __restrict__ st16) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red_d[32];
+    __shared__ int red_i[32];
+    __shared__ bool s_last;
+    constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
+    const int pl = blockIdx.y, p = first + pl;
+    const bool net2 = blockIdx.x != 0;
+    const int n = net2 ? g.n2 : g.n1, words = (n + 1) / 2;
+    const uint32_t* src = (net2 ? pop.inv : pop.aln) + (size_t)p * pop.n2p;
+    const size_t table_bytes = sizeof(T) == 2 ? (size_t)pop.n2p * 2 : 0;
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw + table_bytes);
+    if (nc)
+        for (int i = threadIdx.x; i < words; i += blockDim.x) s_cnt[i] = 0u;
+    const T* tab;
+    if (sizeof(T) == 2) {
+        T* st = reinterpret_cast<T*>(smem_raw);
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        for (int i = threadIdx.x; i < (pop.n2p >> 2); i += blockDim.x) {
+            const uint4 a = s4[i];
+            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st[4 * i + j] = (T)((av[j] & kGMask) | ((av[j] & kGFlag) ? FLAG : 0u));
+            if (st16) {
+                const uint2 h = make_uint2((uint32_t)st[4 * i] | ((uint32_t)st[4 * i + 1] << 16),
+                                           (uint32_t)st[4 * i + 2] | ((uint32_t)st[4 * i + 3] << 16));
+                reinterpret_cast<uint2*>(st16 + ((size_t)pl * 2 + (net2 ? 1 : 0)) * pop.n2p)[i] = h;
+            }
+        }
+        tab = st;
+    } else {
+        tab = reinterpret_cast<const T*>(src);
+    }
+    __syncthreads();
+
+    int c = 0, ind = 0, sz = 0, cset = 0, iset = 0;
+    double sb = 0.0, sg = 0.0;
+    double* seq_b = seq_scratch ? seq_scratch + (size_t)pl * 2 * g.n1 : nullptr;
+    double* seq_g = seq_b ? seq_b + g.n1 : nullptr;
+    if (!net2) {
+#pragma unroll 4
+        for (int e = threadIdx.x; e < g.ne1; e += blockDim.x) {
+            const int u = __ldg(g.eu1 + e), v = __ldg(g.ev1 + e);
+            const uint32_t ru = tab[u], rv = tab[v];
+            const bool mu = !(ru & FLAG), mv = !(rv & FLAG);
+            if ((nc ? (mu | mv) : (mu & mv)) && probe(g, (int)(ru & MASK), (int)(rv & MASK))) {
+                const int w = g.ew1 ? __ldg(g.ew1 + e) : 1;
+                if (mu & mv) { cset += 1; c += w; }
+                if (nc) {
+                    if (mv) count_add(s_cnt, u, w);
+                    if (mu && u != v) count_add(s_cnt, v, w);
+                }
+            }
+        }
+#pragma unroll 2
+        for (int i = threadIdx.x; i < g.n1; i += blockDim.x) {
+            const uint32_t r = tab[i];
+            const bool m = !(r & FLAG);
+            sz += m ? 1 : 0;
+            double vb = 0.0, vg = 0.0;
+            if (m) {
+                if (S.kind) vb = table_lookup(S, i, (int)(r & MASK));
+                if (Gt.kind) vg = table_lookup(Gt, i, (int)(r & MASK));
+            }
+            if (sequential) {
+                seq_b[i] = vb;
+                seq_g[i] = vg;
+            } else {
+                sb += vb;
+                sg += vg;
+            }
+        }
+    } else {
+#pragma unroll 4
+        for (int e = threadIdx.x; e < g.ne2; e += blockDim.x) {
+            const int v = __ldg(g.eu2 + e), w2 = __ldg(g.ev2 + e);
+            const bool av = tab[v] < (uint32_t)g.n1, aw = tab[w2] < (uint32_t)g.n1;
+            if (av | aw) {
+                const int w = g.ew2 ? __ldg(g.ew2 + e) : 1;
+                if (av & aw) { iset += 1; ind += w; }
+                if (nc) {
+                    if (aw) count_add(s_cnt, v, w);
+                    if (av && v != w2) count_add(s_cnt, w2, w);
+                }
+            }
+        }
+    }
+    c = block_sum<int>(c, red_i);
+    ind = block_sum<int>(ind, red_i);
+    sz = block_sum<int>(sz, red_i);
+    cset = block_sum<int>(cset, red_i);
+    iset = block_sum<int>(iset, red_i);
+    sb = block_sum<double>(sb, red_d);
+    sg = block_sum<double>(sg, red_d);
+    if (nc) {   // (the block sums above synchronised the counters)
+        unsigned short* o = nc + (size_t)pl * ncs + (net2 ? ic_off : 0);
+        const unsigned short* h = reinterpret_cast<const unsigned short*>(s_cnt);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = h[i];
+    }
+    if (threadIdx.x == 0) {
+        FullPartial fp;
+        fp.c = c; fp.ind = ind; fp.sz = sz; fp.cset = cset; fp.iset = iset; fp.pad = 0; fp.sb = sb; fp.sg = sg;
+        partials[(size_t)pl * 2 + (net2 ? 1 : 0)] = fp;
+        __threadfence();
+        s_last = atomicAdd(tickets + pl, 1u) == 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ double s_seq[2];
+    if (sequential) {
+        if (threadIdx.x == 0 || threadIdx.x == 32) {
+            const volatile double* sq = threadIdx.x == 0 ? seq_b : seq_g;
+            double acc = 0.0;
+            if ((threadIdx.x == 0 && S.kind) || (threadIdx.x == 32 && Gt.kind))
+                for (int i = 0; i < g.n1; ++i) acc += sq[i];
+            s_seq[threadIdx.x == 0 ? 0 : 1] = acc;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        tickets[pl] = 0;
+        const volatile FullPartial* fp = partials + (size_t)pl * 2;
+        c = fp[0].c; cset = fp[0].cset; sz = fp[0].sz; sb = fp[0].sb; sg = fp[0].sg;
+        ind = fp[1].ind; iset = fp[1].iset;
+        if (sequential) { sb = s_seq[0]; sg = s_seq[1]; }
+        const double denom = (double)ind;
+        const double ics = iset == 0 ? 0.0 : __ddiv_rn((double)cset, (double)iset);
+        const int cref = __double2int_rz(__dmul_rn(ics, denom));   // :445, truncated (H1)
         Scalars s;
         s.C = (seed_mode == 2) ? cref : c;
         s.I = ind;
@@ -455,9 +633,6 @@ k_apply_edits(DevGraph g, DevTable S, DevTable Gt, DevPop pop, int first, int no
 #define ONA_COUNT_THREADS 512
 #endif
 constexpr int kCountThreads = ONA_COUNT_THREADS;
-__device__ __forceinline__ void count_add(uint32_t* words, int i, int v) {
-    atomicAdd(words + (i >> 1), (uint32_t)v << ((i & 1) * 16));
-}
 // grid = (2, individuals): CTA 0 of an individual counts cc from net1's edges (needs aln only),
 // CTA 1 counts ic from net2's edges (needs alnInv only)
 template <typename T>
