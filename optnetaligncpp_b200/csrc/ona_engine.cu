@@ -411,9 +411,13 @@ bool counts_ready(const ona_engine* e, int first, int count) {
 }
 int prepare_counts(ona_engine* e, int first, int count, int K, const unsigned short** nc) {
     *nc = nullptr;
-    if (!e->fast_ok || K < e->fast_min_k) return ONA_OK;
+    if (!e->fast_ok) return ONA_OK;
+    // counting costs about as much as 1000-2000 candidates per individual; when the slots' counts
+    // are still valid from their last evaluation the fast walk pays from a few hundred candidates on
+    const bool ready = counts_ready(e, first, count);
+    if (K < (ready ? std::min(e->fast_min_k, 512) : e->fast_min_k)) return ONA_OK;
     TRY_RC(ensure_count_store(e));
-    if (!counts_ready(e, first, count)) {
+    if (!ready) {
         const int rc = e->small_ids ? prepare_counts_t<uint16_t>(e, first, count) : prepare_counts_t<uint32_t>(e, first, count);
         if (rc) return rc;
         std::fill(e->nc_valid.begin() + first, e->nc_valid.begin() + first + count, (unsigned char)1);
@@ -1017,6 +1021,18 @@ static int enqueue_swap_deltas(ona_engine* e, int first, int count, int K, const
                                const DevDeltaOut& out, int* cons, int* ind, double* bits, double* goc,
                                double* fitness, unsigned char* improved, double* snd, int slices) {
     const int M = e->ob.M;
+    // ONA_E2E_TRACE=1 (with ONA_E2E_GRAPH=0): timestamps of every stage of every slice, printed
+    // after the call -- the tool behind the pipeline notes in profiles/README.md
+    static const bool trace = getenv("ONA_E2E_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto stamp = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        tev.push_back(ev);
+    };
+    stamp(e->stream);
     DeltaSummary sum{};
     CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
     const unsigned short* nc = nullptr;
@@ -1028,7 +1044,9 @@ static int enqueue_swap_deltas(ona_engine* e, int first, int count, int K, const
         const int cnt = l - f;
         if (cnt == 0) continue;
         const size_t off = (size_t)f * K, m = (size_t)cnt * K;
+        stamp(e->s_in);
         CU(cudaMemcpyAsync(e->t_xy.p + 2 * off, xy + 2 * off, 2 * m * sizeof(int), cudaMemcpyHostToDevice, e->s_in));
+        stamp(e->s_in);
         CU(cudaEventRecord(e->ev_in[sidx], e->s_in));
         CU(cudaStreamWaitEvent(e->stream, e->ev_in[sidx], 0));
         DevDeltaOut o = out;
@@ -1039,14 +1057,17 @@ static int enqueue_swap_deltas(ona_engine* e, int first, int count, int K, const
         if (o.fit) o.fit += off * M;
         if (o.improved) o.improved += off;
         if (o.snd) o.snd += off;
+        stamp(e->stream);
         TRY(launch_deltas(e, first + f, cnt, K, e->t_xy.p + 2 * off, 0ull, obj, o, sum, pick_chunks(e, cnt, K),
                           nc ? nc + (size_t)f * e->nc_stride : nullptr));
+        stamp(e->stream);
         CU(cudaEventRecord(e->ev_k[sidx], e->stream));
         CU(cudaStreamWaitEvent(e->s_out, e->ev_k[sidx], 0));
         auto back = [&](void* host, const void* dev, size_t bytes) -> cudaError_t {
             if (!host) return cudaSuccess;
             return cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, e->s_out);
         };
+        stamp(e->s_out);
         CU(back(cons ? cons + off : nullptr, o.cons, m * 4));
         CU(back(ind ? ind + off : nullptr, o.ind, m * 4));
         CU(back(bits ? bits + off : nullptr, o.bits, m * 8));
@@ -1054,9 +1075,21 @@ static int enqueue_swap_deltas(ona_engine* e, int first, int count, int K, const
         CU(back(fitness ? fitness + off * M : nullptr, o.fit, m * M * 8));
         CU(back(improved ? improved + off : nullptr, o.improved, m));
         CU(back(snd ? snd + off : nullptr, o.snd, m * 8));
+        stamp(e->s_out);
     }
     CU(cudaEventRecord(e->ev_out, e->s_out));
     CU(cudaStreamWaitEvent(e->stream, e->ev_out, 0));
+    if (trace) {
+        cudaStreamSynchronize(e->stream);
+        fprintf(stderr, "slice   h2d[start end]   kernel[start end]   d2h[start end]  (us)\n");
+        for (size_t i = 1; i + 5 < tev.size() + 1; i += 6) {
+            float t[6];
+            for (int j = 0; j < 6; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[i + j]);
+            fprintf(stderr, "%5zu   %7.1f %7.1f   %7.1f %7.1f   %7.1f %7.1f\n", (i - 1) / 6, t[0] * 1e3, t[1] * 1e3,
+                    t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3);
+        }
+        for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+    }
     return ONA_OK;
 }
 
@@ -1089,7 +1122,7 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
     if (fitness) { CU(e->t_d3.need(n * M)); out.fit = e->t_d3.p; }
     if (improved) { CU(e->t_u0.need(n)); out.improved = e->t_u0.p; }
     if (snd) { CU(e->t_d2.need(n)); out.snd = e->t_d2.p; }
-    if (e->fast_ok && K >= e->fast_min_k) TRY(ensure_count_store(e));
+    if (e->fast_ok && K >= std::min(e->fast_min_k, 512)) TRY(ensure_count_store(e));
     const int slices = std::min(count, e->pipe_slices);
     // Repeated calls with the same (pinned) host buffers -- a driver's steady state -- replay a CUDA
     // graph of the whole pipeline: one launch instead of ~10 API calls per slice, whose CPU-side

@@ -36,4 +36,5 @@ for P in (256, 1024, 4096, 16384):
         ms = ev[0].elapsed_time(ev[1]) / reps
         rows.append(dict(P=P, K=K, ms=ms, swap_deltas_per_sec=P * K / (ms * 1e-3)))
         print("P=%6d K=%6d  %8.3f ms  %.3e swap-deltas/s" % (P, K, ms, P * K / (ms * 1e-3)), flush=True)
-json.dump(rows, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "r1_sweep_1gpu.json"), "w"), indent=1)
+out = sys.argv[1] if len(sys.argv) > 1 else "sweep_1gpu.json"
+json.dump(rows, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), out), "w"), indent=1)
