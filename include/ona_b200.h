@@ -101,6 +101,13 @@ typedef struct ona_engine ona_engine;
 int ona_device_count(void);
 int ona_engine_create(int device, const ona_problem* problem, ona_engine** out);
 void ona_engine_destroy(ona_engine* e);
+/* A second command queue on the same problem: the fork shares the parent's immutable device data
+ * (graph layouts, score tables -- nothing is copied or rebuilt) and has its own population slots,
+ * scratch, stream and lock.  Replaces nothing in the reference; it is what lets the short
+ * per-alignment calls of one host thread (a child's crossover / mutation / evaluation,
+ * steadystate.cpp:211-232) run beside a long batched hill-climb launch of other threads instead of
+ * queueing behind it.  Destroy parent and forks in any order. */
+int ona_engine_fork(ona_engine* parent, ona_engine** out);
 const char* ona_last_error(void);
 /* run on an existing stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream */
 int ona_set_stream(ona_engine* e, void* cuda_stream);
@@ -211,6 +218,12 @@ int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long 
 int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const int* xy,
                    unsigned long long seed, const int* objs, unsigned char* accepted,
                    long long* num_accepted);
+
+/* Same, the proposals of individual i read from its own host array xy_lists[i] ([iters][2]): the
+ * form in which the reference's callers have them, one correctHillClimb call = one PRNG = one
+ * list per alignment (localSearch.cpp:18-28), without gathering them into one array first. */
+int ona_hill_climb_lists(ona_engine* e, int first, int count, long long iters, const int* const* xy_lists,
+                         const int* objs, unsigned char* accepted, long long* num_accepted);
 
 /* Throughput form of the hill climb (north_star item 3: "thousands of candidates per individual
  * at once; accepted swaps are applied in-kernel").  Per individual, rounds of 1024 proposals

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -37,13 +38,18 @@ template <typename V>
 struct DevBuf {  // grow-only device scratch
     V* p = nullptr;
     size_t cap = 0;
+    // Regrowth frees the old block, and cudaFree waits for EVERY stream of the device -- including
+    // another queue's hill-climb launch that runs for a second -- so blocks grow geometrically and
+    // start at a useful size: a queue reaches its steady state after a handful of calls.
     cudaError_t need(size_t n) {
         if (n <= cap) return cudaSuccess;
+        size_t want = std::max<size_t>(n, std::max<size_t>(2 * cap, (size_t)16384 / sizeof(V)));
+        if (want * sizeof(V) > ((size_t)1 << 30)) want = n;   // no doubling for gigabyte blocks
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(V));
-        if (e == cudaSuccess) cap = n;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(want, 1) * sizeof(V));
+        if (e == cudaSuccess) cap = want;
         return e;
     }
     void release() {
@@ -66,6 +72,17 @@ struct PipeGraph {
     cudaGraphExec_t exec;
     unsigned long long stamp;
     long long launches;   // kernel launches one replay stands for
+};
+
+// the immutable device data of one problem (graph layouts, score tables): shared by an engine and
+// its forks, freed with the last of them
+struct DeviceBlock {
+    int device = 0;
+    std::vector<void*> ptrs;
+    ~DeviceBlock() {
+        cudaSetDevice(device);
+        for (void* p : ptrs) cudaFree(p);
+    }
 };
 
 struct ona_engine {
@@ -99,7 +116,7 @@ struct ona_engine {
     int sm_count = 148;
     size_t smem_optin = 0;
 
-    std::vector<void*> owned;  // immutable device allocations (graph, tables)
+    std::shared_ptr<DeviceBlock> owned;  // immutable device allocations (graph, tables)
 
     int P = 0;
     DevPop pop{};
@@ -129,7 +146,7 @@ template <typename V>
 int upload(ona_engine* e, const std::vector<V>& h, const V** out) {
     V* d = nullptr;
     CU(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(V)));
-    e->owned.push_back(d);
+    e->owned->ptrs.push_back(d);
     if (!h.empty()) CU(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     *out = d;
@@ -211,7 +228,7 @@ int build_table(ona_engine* e, const ona_score_table& t, int n1, int n2, DevTabl
         if (t.ann_present2 && (rc = upload<unsigned char>(e, std::vector<unsigned char>(t.ann_present2, t.ann_present2 + n2), &d_p2))) return rc;
         double* d = nullptr;
         CU(cudaMalloc(&d, (size_t)n1 * (size_t)n2 * sizeof(double)));
-        e->owned.push_back(d);
+        e->owned->ptrs.push_back(d);
         dim3 grid((n2 + 255) / 256, n1);
         k_build_jaccard<<<grid, 256, 0, e->stream>>>(n1, n2, d_rp1, d_t1, d_rp2, d_t2, d_p1, d_p2, d);
         e->launches++;
@@ -245,7 +262,7 @@ int build_table(ona_engine* e, const ona_score_table& t, int n1, int n2, DevTabl
         }
         double* d = nullptr;
         CU(cudaMalloc(&d, cells * sizeof(double)));
-        e->owned.push_back(d);
+        e->owned->ptrs.push_back(d);
         CU(cudaMemcpy(d, src, cells * sizeof(double), cudaMemcpyHostToDevice));
         out->kind = 1;
         out->dense = d;
@@ -518,6 +535,11 @@ int h2d(ona_engine* e, V* dev, const V* host, size_t n) {
 // drain the stream and turn the device-side validation flag into an error code
 int finish_checked(ona_engine* e, const char* what) {
     int bad = 0;
+    // wait FIRST, copy after: a device-to-host copy into pageable memory that is enqueued behind a
+    // long kernel keeps the driver's staging path busy until that kernel ends, and every other
+    // queue's small pageable copy (a fork scoring one alignment beside a one-second hill-climb
+    // launch) would wait with it
+    CU(cudaStreamSynchronize(e->stream));
     CU(cudaMemcpyAsync(&bad, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     if (bad) return fail(ONA_ERR_INVALID, what);
@@ -550,6 +572,27 @@ void free_pop(ona_engine* e) {
 // objective count) runs under the lock, so resize / set_objectives from other threads cannot race it
 #define ENTER(e) if (!(e)) return fail(ONA_ERR_INVALID, "null engine"); LOCK(e)
 #define TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+// per-engine runtime objects: the validation flag now, the copy streams and events of the
+// host-buffer pipeline on first use (an engine that never runs ona_swap_deltas should not hold
+// stream slots: streams beyond the device's hardware connections alias onto shared work queues,
+// where a short kernel can end up behind another engine's long-running launch)
+static int init_runtime(ona_engine* e) {
+    if (cudaMalloc(&e->d_flag, sizeof(int)) != cudaSuccess) return fail(ONA_ERR_CUDA, "cudaMalloc");
+    return ONA_OK;
+}
+static int init_pipeline(ona_engine* e) {
+    if (e->s_in) return ONA_OK;
+    if (cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess)
+        return fail(ONA_ERR_CUDA, "stream/event creation failed");
+    for (int i = 0; i < kPipeSlices; ++i)
+        if (cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming) != cudaSuccess)
+            return fail(ONA_ERR_CUDA, "event creation failed");
+    return ONA_OK;
+}
 
 extern "C" {
 
@@ -593,6 +636,8 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
     CU(cudaSetDevice(device));
     ona_engine* e = new ona_engine();
     e->device = device;
+    e->owned = std::make_shared<DeviceBlock>();
+    e->owned->device = device;
     auto bail = [&](int rc) {
         ona_engine_destroy(e);
         return rc;
@@ -742,15 +787,39 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
         if (v < 0) e->fast_ok = false;
         else e->fast_min_k = v;
     }
-    if (cudaMalloc(&e->d_flag, sizeof(int)) != cudaSuccess) return bail(fail(ONA_ERR_CUDA, "cudaMalloc"));
-    if (cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess)
-        return bail(fail(ONA_ERR_CUDA, "stream/event creation failed"));
-    for (int i = 0; i < kPipeSlices; ++i)
-        if (cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming) != cudaSuccess)
-            return bail(fail(ONA_ERR_CUDA, "event creation failed"));
+    if ((rc = init_runtime(e))) return bail(rc);
+    *out = e;
+    return ONA_OK;
+}
+
+int ona_engine_fork(ona_engine* parent, ona_engine** out) {
+    if (!parent || !out) return fail(ONA_ERR_INVALID, "null argument");
+    *out = nullptr;
+    LOCK(parent);
+    ona_engine* e = new ona_engine();
+    e->device = parent->device;
+    e->owned = parent->owned;                 // graph layouts and score tables are shared, never copied
+    e->g = parent->g; e->S = parent->S; e->G = parent->G; e->ob = parent->ob;
+    e->small_ids = parent->small_ids; e->group = parent->group; e->group_forced = parent->group_forced;
+    e->pipe_slices = parent->pipe_slices; e->fast_ok = parent->fast_ok; e->fast_min_k = parent->fast_min_k;
+    e->split_min_count = parent->split_min_count; e->nc_ic_off = parent->nc_ic_off; e->nc_stride = parent->nc_stride;
+    e->use_graphs = parent->use_graphs; e->sm_count = parent->sm_count; e->smem_optin = parent->smem_optin;
+    e->island_offset = parent->island_offset;
+    e->pop.n2p = parent->pop.n2p;
+    int rc = ONA_OK;
+    // a fork's work is meant to run beside its parent's long launches: highest stream priority
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess)
+        rc = fail(ONA_ERR_CUDA, "cudaStreamCreate failed");
+    else {
+        e->own_stream = true;
+        rc = init_runtime(e);
+    }
+    if (rc) {
+        ona_engine_destroy(e);
+        return rc;
+    }
     *out = e;
     return ONA_OK;
 }
@@ -760,7 +829,7 @@ void ona_engine_destroy(ona_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     drop_graphs(e);
-    for (void* p : e->owned) cudaFree(p);
+    e->owned.reset();
     free_pop(e);
     e->t_i0.release(); e->t_i1.release(); e->t_i2.release(); e->t_xy.release();
     e->t_d0.release(); e->t_d1.release(); e->t_d2.release(); e->t_d3.release(); e->t_d4.release();
@@ -1113,6 +1182,7 @@ int ona_swap_deltas(ona_engine* e, int first, int count, int K, const int* xy, i
     if (count == 0 || K == 0) return ONA_OK;
     const size_t n = (size_t)count * K;
     const int M = e->ob.M;
+    TRY(init_pipeline(e));
     CU(e->t_xy.need(2 * n));
     DevDeltaOut out{};
     if (cons) { CU(e->t_i0.need(n)); out.cons = e->t_i0.p; }
@@ -1310,10 +1380,10 @@ int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long 
     return ONA_OK;
 }
 
-int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const int* xy,
-                   unsigned long long seed, const int* objs, unsigned char* accepted,
-                   long long* num_accepted) {
-    ENTER(e);
+// xy: one flat [count][iters][2] host array, or lists: `count` host pointers to [iters][2] arrays, or neither
+static int hill_climb_impl(ona_engine* e, int first, int count, long long iters, const int* xy,
+                           const int* const* lists, unsigned long long seed, const int* objs,
+                           unsigned char* accepted, long long* num_accepted) {
     TRY(check_range(e, first, count));
     if (iters < 0) return fail(ONA_ERR_INVALID, "iters < 0");
     if (count == 0 || iters == 0) {
@@ -1326,9 +1396,14 @@ int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const i
     const size_t n = (size_t)count * (size_t)iters;
     CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
     const int* xy_dev = nullptr;
-    if (xy) {
+    if (xy || lists) {
         CU(e->t_xy.need(2 * n));
-        TRY(h2d(e, e->t_xy.p, xy, 2 * n));
+        if (xy) TRY(h2d(e, e->t_xy.p, xy, 2 * n));
+        else
+            for (int i = 0; i < count; ++i) {
+                if (!lists[i]) return fail(ONA_ERR_INVALID, "null proposal list");
+                TRY(h2d(e, e->t_xy.p + 2 * (size_t)i * (size_t)iters, lists[i], 2 * (size_t)iters));
+            }
         xy_dev = e->t_xy.p;
     }
     const int* objs_dev = nullptr;
@@ -1345,9 +1420,24 @@ int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const i
     CU(e->t_l0.need((size_t)count));
     TRY(launch_climb(e, first, count, iters, xy_dev, seed, objs_dev, -3, acc_dev, e->t_l0.p));
     invalidate_counts(e, first, count);
+    CU(cudaStreamSynchronize(e->stream));   // before any pageable read-back, see finish_checked
     TRY(d2h(e, accepted, acc_dev, n));
     TRY(d2h(e, num_accepted, e->t_l0.p, (size_t)count));
     return finish_checked(e, "proposal outside [0,n2)");
+}
+
+int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const int* xy,
+                   unsigned long long seed, const int* objs, unsigned char* accepted,
+                   long long* num_accepted) {
+    ENTER(e);
+    return hill_climb_impl(e, first, count, iters, xy, nullptr, seed, objs, accepted, num_accepted);
+}
+
+int ona_hill_climb_lists(ona_engine* e, int first, int count, long long iters, const int* const* xy_lists,
+                         const int* objs, unsigned char* accepted, long long* num_accepted) {
+    ENTER(e);
+    if (!xy_lists) return fail(ONA_ERR_INVALID, "null proposal lists");
+    return hill_climb_impl(e, first, count, iters, nullptr, xy_lists, 0ull, objs, accepted, num_accepted);
 }
 
 int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters, const int* xy,
@@ -1400,6 +1490,7 @@ int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters,
     }
     e->launches++;
     CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));   // before any pageable read-back, see finish_checked
     TRY(d2h(e, num_applied, e->t_l0.p, (size_t)count));
     return finish_checked(e, "proposal outside [0,n2)");
 }

@@ -112,6 +112,35 @@ __device__ __forceinline__ V block_sum(V v, V* scratch) {
     return r;
 }
 
+// The reference's index-order fp64 sums (sumBLAST / sumGOC, Alignment.cpp:701-722) of the per-position
+// terms another CTA left in global memory (masked-off terms were skipped there; adding their +0.0
+// here leaves every partial sum unchanged).  The additions have to stay in index order, so one
+// thread per table adds -- but from shared-memory tiles that the whole CTA fetches with coalesced
+// loads (a lone thread walking global memory pays a full L2 round trip per term: 2 ms for 6 000).
+// Returns the two sums in s_out[0] (bit scores) and s_out[1] (GOC); all threads must call.
+constexpr int kSeqTile = 512;
+__device__ __forceinline__ void sequential_sums(const double* seq_b, const double* seq_g, int n, bool has_b,
+                                                bool has_g, double* s_out) {
+    __shared__ double s_tile[2][kSeqTile];
+    double acc = 0.0;
+    for (int t0 = 0; t0 < n; t0 += kSeqTile) {
+        const int m = min(kSeqTile, n - t0);
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            s_tile[0][i] = has_b ? __ldcg(seq_b + t0 + i) : 0.0;
+            s_tile[1][i] = has_g ? __ldcg(seq_g + t0 + i) : 0.0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 || threadIdx.x == 32) {
+            const double* src = s_tile[threadIdx.x == 0 ? 0 : 1];
+            for (int i = 0; i < m; ++i) acc += src[i];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s_out[0] = acc;
+    if (threadIdx.x == 32) s_out[1] = acc;
+    __syncthreads();
+}
+
 // --------------------------------------------------------------------------------
 // F1-F4: population-batched from-scratch scoring, one CTA per individual.
 //   conserved  = |{(u,v) in E1 : mask[u], mask[v], (aln[u],aln[v]) in E2}|   ics() numerator :629-658
@@ -232,18 +261,7 @@ k_full_fitness(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop
     if (!s_last) return;
     __threadfence();
     __shared__ double s_seq[2];
-    if (sequential) {
-        // the reference's index-order fp64 sums (masked-off terms were skipped there; adding
-        // their +0.0 here leaves every partial sum unchanged)
-        if (threadIdx.x == 0 || threadIdx.x == 32) {
-            const volatile double* src = threadIdx.x == 0 ? seq_b : seq_g;
-            double acc = 0.0;
-            if ((threadIdx.x == 0 && S.kind) || (threadIdx.x == 32 && Gt.kind))
-                for (int i = 0; i < g.n1; ++i) acc += src[i];
-            s_seq[threadIdx.x == 0 ? 0 : 1] = acc;
-        }
-        __syncthreads();
-    }
+    if (sequential) sequential_sums(seq_b, seq_g, g.n1, S.kind != 0, Gt.kind != 0, s_seq);
     if (threadIdx.x == 0) {
         tickets[pl] = 0;  // ready for the next launch
         c = 0; ind = 0; sz = 0; cset = 0; iset = 0; sb = 0.0; sg = 0.0;
@@ -411,16 +429,7 @@ k_full_fitness_split(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     if (!s_last) return;
     __threadfence();
     __shared__ double s_seq[2];
-    if (sequential) {
-        if (threadIdx.x == 0 || threadIdx.x == 32) {
-            const volatile double* sq = threadIdx.x == 0 ? seq_b : seq_g;
-            double acc = 0.0;
-            if ((threadIdx.x == 0 && S.kind) || (threadIdx.x == 32 && Gt.kind))
-                for (int i = 0; i < g.n1; ++i) acc += sq[i];
-            s_seq[threadIdx.x == 0 ? 0 : 1] = acc;
-        }
-        __syncthreads();
-    }
+    if (sequential) sequential_sums(seq_b, seq_g, g.n1, S.kind != 0, Gt.kind != 0, s_seq);
     if (threadIdx.x == 0) {
         tickets[pl] = 0;
         const volatile FullPartial* fp = partials + (size_t)pl * 2;

@@ -19,11 +19,11 @@ OBJECTIVE_NAMES = ["ICS", "EC", "BitscoreSum", "EvalsSum", "Size", "GOC", "S3", 
 SEED_NONE, SEED_TRUE, SEED_REFCOMPAT, SUM_SEQUENTIAL = 0, 1, 2, 16
 
 EXPORTS = [
-    "ona_device_count", "ona_engine_create", "ona_engine_destroy", "ona_last_error",
+    "ona_device_count", "ona_engine_create", "ona_engine_fork", "ona_engine_destroy", "ona_last_error",
     "ona_set_stream", "ona_synchronize", "ona_host_alloc", "ona_host_free", "ona_kernel_launches",
     "ona_set_island_offset", "ona_set_objectives", "ona_pop_resize", "ona_pop_upload", "ona_pop_download",
     "ona_pop_set_counters", "ona_pop_get_counters", "ona_full_fitness", "ona_full_fitness_dev",
-    "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_steepest_step", "ona_rng_proposals", "ona_hill_climb", "ona_hill_climb_batched",
+    "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_steepest_step", "ona_rng_proposals", "ona_hill_climb", "ona_hill_climb_lists", "ona_hill_climb_batched",
     "ona_apply_swaps", "ona_apply_edits", "ona_export_fitness_dev", "ona_nsga2_rank", "ona_nsga2_rank_dev",
 ]
 
@@ -70,6 +70,8 @@ def load_library(build_if_missing=True):
     vp, ci, ll = C.c_void_p, C.c_int, C.c_longlong
     L.ona_last_error.restype = C.c_char_p
     L.ona_engine_create.argtypes = [ci, C.POINTER(_Problem), C.POINTER(vp)]
+    L.ona_engine_fork.argtypes = [vp, C.POINTER(vp)]
+    L.ona_hill_climb_lists.argtypes = [vp, ci, ci, ll, vp, vp, vp, vp]
     L.ona_engine_destroy.argtypes = [vp]
     L.ona_engine_destroy.restype = None
     L.ona_set_stream.argtypes = [vp, vp]
@@ -173,6 +175,16 @@ class Engine:
         goc = goc_dense if use_goc else None
         return cls(pair.n1, pair.n2, pair.E1, pair.rp1, pair.col1, pair.rp2, pair.col2, objectives,
                    bits=bits, goc=goc, device=device)
+
+    def fork(self):
+        """ona_engine_fork: a second queue (own slots, stream, lock) on the same device data."""
+        f = object.__new__(Engine)
+        f.L, f.n1, f.n2, f.M, f.objectives, f.P = self.L, self.n1, self.n2, self.M, self.objectives, 0
+        f.device = self.device
+        h = C.c_void_p()
+        self._check(self.L.ona_engine_fork(self.h, C.byref(h)))
+        f.h = h
+        return f
 
     def _check(self, rc):
         if rc != 0:
@@ -324,6 +336,16 @@ class Engine:
         self._check(self.L.ona_hill_climb(self.h, first, count, int(iters), _ptr(xy), int(seed),
                                           _ptr(o), _ptr(acc), _ptr(nacc)))
         return acc, nacc
+
+    def hill_climb_lists(self, lists, objs=None, first=0):
+        """ona_hill_climb_lists: one [iters,2] host array per individual."""
+        arrs = [_i32(a) for a in lists]
+        count, iters = len(arrs), arrs[0].shape[0]
+        ptrs = (C.c_void_p * count)(*[a.ctypes.data for a in arrs])
+        o = None if objs is None else _i32(np.broadcast_to(np.asarray(objs), (count,)))
+        nacc = np.empty(count, np.int64)
+        self._check(self.L.ona_hill_climb_lists(self.h, first, count, int(iters), ptrs, _ptr(o), None, _ptr(nacc)))
+        return nacc
 
     def hill_climb_batched(self, iters=None, xy=None, seed=0, objs=None, first=0, count=None):
         """throughput hill climb: rounds of 1024 proposals scored at once, a conflict-free accepted

@@ -19,10 +19,33 @@ namespace {
 // agree on (engine, objective list, iteration count) are combined into ONE batched GPU climb,
 // one CTA per alignment: the first caller becomes the leader, waits a moment for company,
 // runs the batch and wakes the others.
+// Per-thread pinned buffer for the proposal list of the thread's current correctHillClimb call
+// (pinned: the batched launch copies every caller's list with a true asynchronous DMA instead of a
+// staged pageable copy, 55 GB/s instead of ~5).  Grown on demand, released with the thread.
+struct PinnedList {
+    int* p = nullptr;
+    size_t cap = 0;
+    int* need(size_t n) {
+        if (n > cap) {
+            if (p) ona_host_free(p);
+            cap = max<size_t>(n, 1 << 16);
+            p = static_cast<int*>(ona_host_alloc((long long)(cap * sizeof(int))));
+            if (!p) {
+                cap = 0;
+                throw runtime_error("ona_b200: pinned host allocation failed");
+            }
+        }
+        return p;
+    }
+    ~PinnedList() {
+        if (p) ona_host_free(p);
+    }
+};
+
 struct Request {
     Alignment* aln;
     const vector<fitnessName>* names;
-    vector<int> xy;
+    int* xy = nullptr;   // [iters][2], in the calling thread's pinned buffer
     int obj;
     long long iters;
     bool done = false;
@@ -40,11 +63,22 @@ public:
                 continue;
             }
             leader_ = true;
-            cv_.wait_for(lk, chrono::microseconds(200));  // give concurrent callers a moment to join
+            // Give concurrent callers time to join.  A launch takes as long as its slowest climb
+            // whatever the batch size (one CTA per alignment, up to ~300 of them run at once), so
+            // the leader waits until as many callers are queued as were around at the previous
+            // launch (those it climbed plus those left waiting), for at most ~5 % of the launch's
+            // expected duration (200 us for a 500-iteration climb, 50 ms for a 10^6-iteration one).
+            {
+                const long long cap_us = min<long long>(100000, max<long long>(200, r.iters / 20));
+                const auto t_end = chrono::steady_clock::now() + chrono::microseconds(cap_us);
+                while (chrono::steady_clock::now() < t_end && queue_.size() < callers_)
+                    cv_.wait_for(lk, chrono::microseconds(100));
+            }
             vector<Request*> batch;
             for (Request* q : queue_)
                 if (q->iters == queue_.front()->iters && *q->names == *queue_.front()->names) batch.push_back(q);
             for (Request* q : batch) queue_.erase(find(queue_.begin(), queue_.end(), q));
+            callers_ = batch.size() + queue_.size();
             lk.unlock();
             run(ctx, batch);
             lk.lock();
@@ -58,19 +92,21 @@ public:
 
 private:
     static void run(ona_host::Context& ctx, vector<Request*>& batch) {
+        ona_host::StatTimer st(ona_host::kStatClimb, (long long)batch.size());
         try {
             lock_guard<mutex> lk(ctx.lock());
             ctx.use_objectives(*batch[0]->names);
             vector<Alignment*> alns;
-            vector<int> objs, xy;
+            vector<int> objs;
+            vector<const int*> lists;       // every caller's own proposal list, uploaded where it lies
             for (Request* q : batch) {
                 alns.push_back(q->aln);
                 objs.push_back(q->obj);
-                xy.insert(xy.end(), q->xy.begin(), q->xy.end());
+                lists.push_back(q->xy);
             }
             ctx.upload(alns);
-            ona_host::check(ona_hill_climb(ctx.engine(), 0, (int)alns.size(), batch[0]->iters, xy.data(), 0ull,
-                                           objs.data(), nullptr, nullptr));
+            ona_host::check(ona_hill_climb_lists(ctx.engine(), 0, (int)alns.size(), batch[0]->iters, lists.data(),
+                                                 objs.data(), nullptr, nullptr));
             ctx.download(alns);
             for (Request* q : batch) q->aln->computeFitness(*q->names);
         } catch (const exception& ex) {
@@ -81,6 +117,7 @@ private:
     condition_variable cv_;
     vector<Request*> queue_;
     bool leader_ = false;
+    size_t callers_ = 1;   // callers around at the previous launch
 };
 
 Batcher& batcher_for(ona_host::Context& ctx) {
@@ -109,7 +146,8 @@ void correctHillClimb(RandGenT& prng, Alignment* aln, bool total, int maxIters,
     r.names = &fitnessNames;
     r.obj = obj;
     r.iters = maxIters;
-    r.xy.resize(2 * (size_t)maxIters);
+    thread_local PinnedList pinned;
+    r.xy = pinned.need(2 * (size_t)maxIters);
     for (int i = 0; i < maxIters; i++) {
         node x = randNonDummyIndex(prng);
         node y = randIndex(prng);
@@ -118,6 +156,7 @@ void correctHillClimb(RandGenT& prng, Alignment* aln, bool total, int maxIters,
         r.xy[2 * i + 1] = y;
     }
     ona_host::Context& ctx = ona_host::context_for(*aln);
+    ona_host::StatTimer st(ona_host::kStatClimbWait, maxIters);
     batcher_for(ctx).submit(ctx, r);
 }
 

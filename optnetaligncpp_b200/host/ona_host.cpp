@@ -7,9 +7,35 @@
 #include <memory>
 #include <tuple>
 
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+
 namespace ona_host {
 
 namespace {
+const char* kStatNames[kStatSlots] = {"engine creation", "from-scratch evaluations", "swap lists", "edit lists",
+                                      "hill-climb launches (individuals)", "correctHillClimb calls (caller wait)",
+                                      "steepest scans", "NSGA-II rankings", "  (of the short calls: waiting for their queue)"};
+std::atomic<long long> g_stat_ns[kStatSlots], g_stat_calls[kStatSlots], g_stat_units[kStatSlots];
+bool stats_on() {
+    static const bool on = [] {
+        const bool v = std::getenv("ONA_HOST_STATS") != nullptr;
+        if (v)
+            std::atexit([] {
+                std::fprintf(stderr, "ona_host stats (wall time inside the mirror's GPU round trips)\n");
+                for (int i = 0; i < kStatSlots; ++i)
+                    if (g_stat_calls[i].load())
+                        std::fprintf(stderr, "  %-40s calls %8lld  units %10lld  %9.3f s\n", kStatNames[i],
+                                     g_stat_calls[i].load(), g_stat_units[i].load(), g_stat_ns[i].load() * 1e-9);
+            });
+        return v;
+    }();
+    return on;
+}
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 std::mutex g_mu;
 std::map<std::tuple<const Network*, const Network*, const BLASTDict*, const GOCDict*>,
          std::unique_ptr<Context>> g_ctx;
@@ -25,7 +51,18 @@ void to_csr(const Network* n, std::vector<int>& rp, std::vector<int>& col) {
 }
 }  // namespace
 
+}  // namespace ona_host
+ona_host::StatTimer::StatTimer(int s, long long u) : slot(s), units(u), t0(stats_on() ? now_s() : 0.0) {}
+ona_host::StatTimer::~StatTimer() {
+    if (!stats_on()) return;
+    g_stat_ns[slot] += (long long)((now_s() - t0) * 1e9);
+    g_stat_calls[slot] += 1;
+    g_stat_units[slot] += units;
+}
+namespace ona_host {
+
 Context::Context(const Network* net1, const Network* net2, const BLASTDict* bit, const GOCDict* goc) {
+    StatTimer st(kStatCreate);
     n1_ = (int)net1->nodeToNodeName.size();
     n2_ = (int)net2->nodeToNodeName.size();
     std::vector<int> rp1, c1, rp2, c2;
@@ -45,19 +82,50 @@ Context::Context(const Network* net1, const Network* net2, const BLASTDict* bit,
     pr.num_objectives = 1;
     int device = 0;
     if (const char* d = std::getenv("ONA_DEVICE")) device = std::atoi(d);
-    check(ona_engine_create(device, &pr, &e_));
+    // one stream per queue: ask for enough hardware connections that none of them shares a work
+    // queue with the main queue's long launches (read by the driver when CUDA initialises, i.e.
+    // here in a drop-in binary; the default is 8)
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    check(ona_engine_create(device, &pr, &main_.e_));
+    main_.n2_ = n2_;
+    int nq = 8;
+    if (const char* q = std::getenv("ONA_HOST_QUEUES")) nq = std::max(1, std::min(64, std::atoi(q)));
+    for (int i = 0; i < nq; ++i) {
+        small_.emplace_back(new Queue());
+        check(ona_engine_fork(main_.e_, &small_.back()->e_));
+        small_.back()->n2_ = n2_;
+    }
 }
 
-Context::~Context() { ona_engine_destroy(e_); }
+Context::~Context() {
+    for (auto& q : small_) ona_engine_destroy(q->e_);
+    ona_engine_destroy(main_.e_);
+}
+
+std::unique_lock<std::mutex> Context::acquire_small(Queue*& q) {
+    static std::atomic<unsigned> next{0};
+    thread_local unsigned home = next++;
+    const size_t n = small_.size();
+    for (size_t k = 0; k < n; ++k) {
+        Queue* cand = small_[(home + k) % n].get();
+        std::unique_lock<std::mutex> lk(cand->mu_, std::try_to_lock);
+        if (lk.owns_lock()) {
+            q = cand;
+            return lk;
+        }
+    }
+    q = small_[home % n].get();
+    return std::unique_lock<std::mutex>(q->mu_);
+}
 
 void Context::use_objectives(const std::vector<fitnessName>& names) {
     std::vector<int> v(names.begin(), names.end());
     if (v == names_ || v.empty()) return;
-    check(ona_set_objectives(e_, v.data(), (int)v.size()));
+    check(ona_set_objectives(main_.e_, v.data(), (int)v.size()));
     names_ = v;
 }
 
-void Context::ensure_slots(int count) {
+void Queue::ensure_slots(int count) {
     if (count <= slots_) return;
     int want = slots_ ? slots_ : 16;
     while (want < count) want *= 2;
@@ -65,7 +133,7 @@ void Context::ensure_slots(int count) {
     slots_ = want;
 }
 
-void Context::upload(const std::vector<Alignment*>& alns) {
+void Queue::upload(const std::vector<Alignment*>& alns) {
     const int n = (int)alns.size();
     ensure_slots(n);
     h_aln_.resize((size_t)n * n2_);
@@ -90,7 +158,7 @@ void Context::upload(const std::vector<Alignment*>& alns) {
     check(ona_pop_set_counters(e_, 0, n, cons.data(), ind.data(), bits.data(), goc.data()));
 }
 
-void Context::download(const std::vector<Alignment*>& alns) {
+void Queue::download(const std::vector<Alignment*>& alns) {
     const int n = (int)alns.size();
     h_aln_.resize((size_t)n * n2_);
     h_inv_.resize((size_t)n * n2_);
@@ -123,8 +191,12 @@ Context& context_for(const Network* n1, const Network* n2, const BLASTDict* bit,
 Context& context_for(const Alignment& a) { return context_for(a.net1, a.net2, a.bitscores, a.gocs); }
 
 Scratch score_from_scratch(const Alignment& a) {
-    Context& c = context_for(a);
-    std::lock_guard<std::mutex> lk(c.lock());
+    StatTimer st(kStatScratch);
+    StatTimer* wait = new StatTimer(kStatSmallLockWait);
+    Queue* qp = nullptr;
+    std::unique_lock<std::mutex> lk = context_for(a).acquire_small(qp);
+    Queue& c = *qp;
+    delete wait;
     std::vector<Alignment*> one{const_cast<Alignment*>(&a)};
     c.ensure_slots(1);
     // only the permutation and mask matter here; the cached counters are left alone
@@ -154,8 +226,12 @@ void seed_counters(Alignment& a) {
 
 void apply_swaps(Alignment& a, const std::vector<int>& xy) {
     if (xy.empty()) return;
-    Context& c = context_for(a);
-    std::lock_guard<std::mutex> lk(c.lock());
+    StatTimer st(kStatSwaps, (long long)xy.size() / 2);
+    StatTimer* wait = new StatTimer(kStatSmallLockWait);
+    Queue* qp = nullptr;
+    std::unique_lock<std::mutex> lk = context_for(a).acquire_small(qp);
+    Queue& c = *qp;
+    delete wait;
     std::vector<Alignment*> one{&a};
     c.upload(one);
     check(ona_apply_swaps(c.engine(), 0, 1, (int)(xy.size() / 2), xy.data()));
@@ -164,8 +240,12 @@ void apply_swaps(Alignment& a, const std::vector<int>& xy) {
 
 void apply_edits(Alignment& a, const std::vector<int>& ops) {
     if (ops.empty()) return;
-    Context& c = context_for(a);
-    std::lock_guard<std::mutex> lk(c.lock());
+    StatTimer st(kStatEdits, (long long)ops.size() / 4);
+    StatTimer* wait = new StatTimer(kStatSmallLockWait);
+    Queue* qp = nullptr;
+    std::unique_lock<std::mutex> lk = context_for(a).acquire_small(qp);
+    Queue& c = *qp;
+    delete wait;
     std::vector<Alignment*> one{&a};
     c.upload(one);
     check(ona_apply_edits(c.engine(), 0, 1, (int)(ops.size() / 4), ops.data()));

@@ -15,6 +15,7 @@
 #pragma once
 #include <condition_variable>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -25,36 +26,71 @@
 
 namespace ona_host {
 
+// ONA_HOST_STATS=1: wall time and call counts of the mirror's GPU round trips, printed at exit
+// (where a drop-in driver's time goes: engine creation, evaluations, swap / edit lists, climbs)
+struct StatTimer {
+    StatTimer(int slot, long long units = 1);
+    ~StatTimer();
+    int slot;
+    long long units;
+    double t0;
+};
+enum { kStatCreate = 0, kStatScratch, kStatSwaps, kStatEdits, kStatClimb, kStatClimbWait, kStatSteepest, kStatRank, kStatSmallLockWait, kStatSlots };
+
 // non-zero C-ABI codes become exceptions again (the reference reports errors by throwing)
 inline void check(int rc) {
     if (rc != ONA_OK) throw std::runtime_error(std::string("ona_b200: ") + ona_last_error());
 }
 
-class Context {
+// One command queue of the engine: scratch population slots, a lock, host staging buffers.
+class Queue {
 public:
-    Context(const Network* n1, const Network* n2, const BLASTDict* bit, const GOCDict* goc);
-    ~Context();
     ona_engine* engine() { return e_; }
-    int n1() const { return n1_; }
-    int n2() const { return n2_; }
-    // make `names` the engine's objective list (no-op when unchanged); caller holds lock()
-    void use_objectives(const std::vector<fitnessName>& names);
+    std::mutex& lock() { return mu_; }
     // scratch slots [0, count) of the engine, grown on demand; caller holds lock()
     void ensure_slots(int count);
-    std::mutex& lock() { return mu_; }
-
-    // upload `alns` into slots 0..n-1 (permutation, mask, cached counters)
+    // upload `alns` into slots 0..n-1 (permutation, mask, cached counters); caller holds lock()
     void upload(const std::vector<Alignment*>& alns);
     // copy slots 0..n-1 back into the objects (permutation, inverse, mask, counters)
     void download(const std::vector<Alignment*>& alns);
 
 private:
+    friend class Context;
     ona_engine* e_ = nullptr;
-    int n1_ = 0, n2_ = 0, slots_ = 0;
-    std::vector<int> names_;
+    int n2_ = 0, slots_ = 0;
     std::mutex mu_;
     std::vector<int> h_aln_, h_inv_;
     std::vector<unsigned char> h_mask_;
+};
+
+// The engine of one (net1, net2, bitscores, gocs) tuple with TWO queues on it: the batched hill
+// climbs of the drivers' worker threads run on the main queue, the short per-alignment calls
+// (seeding a new alignment's counters, a child's crossover / mutation swap list) on a few forks of
+// it (ona_engine_fork: same device data, own slots / stream / lock), so that a worker preparing
+// its next child neither queues behind a climb that runs for a second nor behind every other
+// worker doing the same.
+class Context {
+public:
+    Context(const Network* n1, const Network* n2, const BLASTDict* bit, const GOCDict* goc);
+    ~Context();
+    ona_engine* engine() { return main_.e_; }
+    std::mutex& lock() { return main_.mu_; }
+    Queue& main() { return main_; }
+    // one of the side queues, locked: a free one if there is any, else the caller's home queue
+    std::unique_lock<std::mutex> acquire_small(Queue*& q);
+    int n1() const { return n1_; }
+    int n2() const { return n2_; }
+    // make `names` the main queue's objective list (no-op when unchanged); caller holds lock()
+    void use_objectives(const std::vector<fitnessName>& names);
+    void ensure_slots(int count) { main_.ensure_slots(count); }
+    void upload(const std::vector<Alignment*>& alns) { main_.upload(alns); }
+    void download(const std::vector<Alignment*>& alns) { main_.download(alns); }
+
+private:
+    Queue main_;
+    std::vector<std::unique_ptr<Queue> > small_;   // kSmallQueues forks of the main engine
+    int n1_ = 0, n2_ = 0;
+    std::vector<int> names_;
 };
 
 // the engine of the networks / score tables an Alignment borrows (created on first use)

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Wall-clock of the reference's own optnetalign driver (steadystate.cpp, unmodified) on the C2
+pair: the all-reference CPU build at the host's thread count vs the GPU-engine build at several
+--nthreads (thread count = batch size of the combined hill-climb launches).  Same CLI, same flags;
+prints generated alignments per second and correctHillClimb iterations per second.
+    python profiles/driver_walltime.py out.json"""
+import json, os, subprocess, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+from optnetaligncpp_b200 import synth
+
+pair = bench.make_workload()
+d = tempfile.mkdtemp()
+p = synth.write_text(pair, os.path.join(d, "c2"))
+popsize, gens, hci = 200, 1, int(os.environ.get("HCI", "2000"))   # 200 children x 2 climbs x 500*hci iterations
+iters_total = popsize * gens * 2 * 500 * hci
+base = ["--net1", p["net1"], "--net2", p["net2"], "--total", "--s3", "--bitscores", p["sim"], "--blastsum",
+        "--popsize", str(popsize), "--generations", str(gens), "--hillclimbiters", str(hci), "--nooutput", "--randseed", "1"]
+ncpu = os.cpu_count() or 1
+res = {}
+def run(tag, binary, nthreads, args=None):
+    t0 = time.perf_counter()
+    out = subprocess.run([binary] + (args or base) + ["--nthreads", str(nthreads)], capture_output=True, text=True, timeout=3000)
+    dt = time.perf_counter() - t0
+    assert out.returncode == 0, out.stderr[-500:]
+    res[tag] = dict(nthreads=nthreads, wall_s=dt)
+    print("%-28s nthreads %4d  wall %7.2f s" % (tag, nthreads, dt), flush=True)
+# fixed cost of a run (process start, loaders incl. the 384 MB dense BLAST matrix, for the GPU build
+# also CUDA context + engine creation): one child, no hill climbing
+fixed = [a for a in base]
+fixed[fixed.index("--popsize") + 1] = "1"
+fixed[fixed.index("--hillclimbiters") + 1] = "0"
+REF, GPU = os.path.join(ROOT, "oracle/_ref/optnetalign_ref"), os.path.join(ROOT, "optnetaligncpp_b200/host/_build/optnetalign")
+run("reference_cpu_fixed_cost", REF, 1, fixed)
+run("gpu_engine_fixed_cost", GPU, 1, fixed)
+run("reference_cpu", REF, ncpu)
+for nt in (ncpu, 64, 256):
+    run("gpu_engine_nthreads_%d" % nt, GPU, nt)
+for k, v in res.items():
+    if k.endswith("fixed_cost"):
+        continue
+    f = res["gpu_engine_fixed_cost" if k.startswith("gpu") else "reference_cpu_fixed_cost"]["wall_s"]
+    v["climb_iterations"] = iters_total
+    v["iterations_per_s_net_of_fixed_cost"] = iters_total / max(v["wall_s"] - f, 1e-9)
+json.dump(dict(host_threads=ncpu, popsize=popsize, generations=gens, hillclimbiters=hci, runs=res),
+          open(os.path.join(ROOT, "profiles", sys.argv[1] if len(sys.argv) > 1 else "driver_walltime.json"), "w"), indent=1)

@@ -348,6 +348,52 @@ def test_error_behaviour():
     e.swap_deltas(np.empty((2, 0, 2), np.int32))
 
 
+def test_forked_queue_and_per_individual_lists(mid):
+    """ona_engine_fork: a second queue on the same device data (own slots / stream / lock) gives the
+    same results as its parent, concurrently with it; ona_hill_climb_lists == ona_hill_climb on the
+    gathered lists."""
+    import threading
+    pair, S, G, prob = mid
+    names = [engine.S3, engine.BITSCORE_SUM, engine.GOC]
+    P, iters = 6, 4000
+    aln, mask = synth.random_population(pair, P, seed=31, total=False)
+    e = engine.Engine.from_pair(pair, names, use_goc=True, goc_dense=G)
+    f = e.fork()
+    hxy = synth.random_candidates(pair, P, iters, seed=32)
+    out = {}
+
+    def climb(tag, q, how):
+        q.upload(aln, mask)
+        q.full_fitness(seed_mode=engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL)
+        if how == "lists":
+            nacc = q.hill_climb_lists([hxy[p].copy() for p in range(P)])
+        else:
+            _, nacc = q.hill_climb(xy=hxy)
+        out[tag] = (q.download(), q.counters(), nacc)
+
+    ts = [threading.Thread(target=climb, args=("parent", e, "flat")), threading.Thread(target=climb, args=("fork", f, "lists"))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    (sa, ca, na), (sb, cb, nb) = out["parent"], out["fork"]
+    assert all(np.array_equal(x, y) for x, y in zip(sa, sb)) and np.array_equal(na, nb)
+    for k in ca:
+        assert np.array_equal(ca[k], cb[k], equal_nan=True), k
+    for p in range(P):
+        o = port.Aln(prob, aln[p], mask[p])
+        o.hill_climb_replay(hxy[p], names)
+        assert np.array_equal(sb[0][p], o.state()[0])
+        assert (cb["cons"][p], cb["ind"][p], cb["bits"][p], cb["goc"][p]) == o.counters()
+    f.close()
+    # the parent keeps working after its fork is gone (and the other way round)
+    e.full_fitness(seed_mode=engine.SEED_NONE)
+    g = e.fork()
+    e.close()
+    g.upload(aln, mask)
+    r = g.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
+    assert r["ind"][0] == port.Aln(prob, aln[0], mask[0]).counters()[1]
+    g.close()
+
+
 def test_resize_keeps_uploaded_slots():
     """growing the population (explicitly or through upload(first=...)) keeps earlier slots:
     permutation, mask, counters and objective rows."""
