@@ -448,11 +448,12 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": bench_config(world),
             # achieved = ALGORITHMIC bytes (SURVEY 8d B_min, summed over the evaluated candidates) per
-            # second of the swap-delta launch (k_node_counts + k_swap_deltas_sorted, CUDA events),
+            # second of the swap-delta launch (k_swap_deltas_sorted, fast walk; its node counts come
+            # from the step's k_full_fitness_split, whose time is in full_fitness.kernel_ms; CUDA events),
             # against the measured HBM copy peak as the contract asks.  It is NOT the kernel's DRAM
             # throughput: the graph, bit matrix and population are L2-resident by design, so DRAM is
             # ~2 % busy and the limiter is instruction issue / L2 latency (profiles/README.md).
-            "roofline": {"kernel": "k_swap_deltas_sorted (+ k_node_counts of the same launch)", "bound": "hbm",
+            "roofline": {"kernel": "k_swap_deltas_sorted<fast walk> (node counts: by-product of the step's k_full_fitness_split)", "bound": "hbm",
                          "achieved": achieved, "peak": peak,
                          "peak_kind": "of " + peak_kind, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,

@@ -3,6 +3,7 @@
 #include "../../include/ona_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -616,6 +617,15 @@ void ona_host_free(void* p) {
 int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
     if (!pr || !out) return fail(ONA_ERR_INVALID, "null argument");
     *out = nullptr;
+    // ONA_TRACE_CREATE=1: where engine creation spends its time (stderr)
+    const bool trace = getenv("ONA_TRACE_CREATE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "ona_engine_create: %-34s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0)
@@ -632,8 +642,11 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
     bool dups1 = false, dups2 = false;
     TRY(check_csr("net1", pr->n1, pr->rowptr1, pr->col1, pr->n1, &dups1));
     TRY(check_csr("net2", pr->n2, pr->rowptr2, pr->col2, pr->n2, &dups2));
+    lap("device count + CSR checks");
 
     CU(cudaSetDevice(device));
+    CU(cudaFree(0));
+    lap("CUDA context");
     ona_engine* e = new ona_engine();
     e->device = device;
     e->owned = std::make_shared<DeviceBlock>();
@@ -765,8 +778,11 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
     }
     if ((size_t)pr->n2 * (size_t)g.W >= ((size_t)1 << 32))
         return bail(fail(ONA_ERR_INVALID, "net2 bit matrix exceeds 2^32 words"));
+    lap("graph layouts");
     if ((rc = build_table(e, pr->bitscores, pr->n1, pr->n2, &e->S))) return bail(rc);
+    lap("bit-score table");
     if ((rc = build_table(e, pr->gocs, pr->n1, pr->n2, &e->G))) return bail(rc);
+    lap("GOC table");
     e->ob.M = pr->num_objectives;
     for (int j = 0; j < pr->num_objectives; ++j) e->ob.names[j] = pr->objectives[j];
 

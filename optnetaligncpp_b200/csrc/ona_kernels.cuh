@@ -119,7 +119,7 @@ __device__ __forceinline__ V block_sum(V v, V* scratch) {
 // loads (a lone thread walking global memory pays a full L2 round trip per term: 2 ms for 6 000).
 // Returns the two sums in s_out[0] (bit scores) and s_out[1] (GOC); all threads must call.
 constexpr int kSeqTile = 512;
-__device__ __forceinline__ void sequential_sums(const double* seq_b, const double* seq_g, int n, bool has_b,
+__device__ __noinline__ void sequential_sums(const double* seq_b, const double* seq_g, int n, bool has_b,
                                                 bool has_g, double* s_out) {
     __shared__ double s_tile[2][kSeqTile];
     double acc = 0.0;
@@ -315,7 +315,7 @@ k_full_fitness(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop
 // --------------------------------------------------------------------------------
 constexpr int kFullSplitThreads = 512;
 template <typename T>
-__global__ void __launch_bounds__(kFullSplitThreads)
+__global__ void __launch_bounds__(kFullSplitThreads, 3)   // 3 CTAs/SM: all 2 x 200 CTAs of the bench resident at once
 k_full_fitness_split(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first,
                      int seed_mode, int sequential, double* __restrict__ seq_scratch,
                      FullPartial* __restrict__ partials, unsigned int* __restrict__ tickets, FullOut out,

@@ -12,6 +12,8 @@
 // mutated children, once by the reference's own nsga-ii.cpp (linked unchanged) and once by
 // ona_host::rankGeneration on copies; prints whether the two agree member by member.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -45,6 +47,45 @@ int main(int argc, char** argv) {
         if (bit) names.push_back(BitscoreSumFit);
         if (goc) names.push_back(GOCFit);
 
+        if (argc > 10 && string(argv[10]) == "smallops") {
+            // throughput of the short per-alignment calls (mutate = one swap list, shuf = two
+            // from-scratch evaluations) from `nthreads` threads, with and without a long batched
+            // climb running beside them: the situation of steadystate.cpp's workers
+            for (int with_climb = 0; with_climb < 2; with_climb++) {
+                atomic<bool> stop(false);
+                atomic<long long> nmut(0), nshuf(0);
+                vector<thread> ts;
+                for (int t = 0; t < nthreads; t++)
+                    ts.push_back(thread([&, t]() {
+                        RandGenT g(seed + t);
+                        Alignment a(net1, net2, bit, goc);
+                        a.shuf(g, false, false, true);
+                        while (!stop) {
+                            a.mutate(g, 0.05f, true);
+                            nmut++;
+                            a.shuf(g, false, false, true);
+                            nshuf++;
+                        }
+                    }));
+                thread climber;
+                if (with_climb)
+                    climber = thread([&]() {
+                        vector<Alignment*> pop;
+                        RandGenT g(seed + 999);
+                        Alignment a(net1, net2, bit, goc);
+                        a.shuf(g, false, false, true);
+                        a.computeFitness(names);
+                        while (!stop) correctHillClimb(g, &a, true, iters, names);
+                    });
+                this_thread::sleep_for(chrono::milliseconds(3000));
+                stop = true;
+                for (auto& th : ts) th.join();
+                if (with_climb) climber.join();
+                printf("smallops threads %d climb_beside %d: %.0f swap lists/s, %.0f evaluations/s\n", nthreads, with_climb,
+                       nmut / 3.0, 2.0 * nshuf / 3.0);
+            }
+            return 0;
+        }
         if (argc > 10 && string(argv[10]) == "steepest") {
             // the threaded exhaustive search (localSearch.cpp:122-203): every scan of the n1 x n2
             // grid is one pass of the swap-delta kernel here
