@@ -817,6 +817,16 @@ __device__ __forceinline__ void sort_pass(const int (&key)[PER], unsigned short 
 #ifndef ONA_FAST_MINBLOCKS
 #define ONA_FAST_MINBLOCKS 3
 #endif
+template <typename T> struct XyStore {           // wide ids: two ints
+    int2 v;
+    __device__ __forceinline__ void set(int x, int y) { v = make_int2(x, y); }
+    __device__ __forceinline__ int2 get() const { return v; }
+};
+template <> struct XyStore<uint16_t> {           // ids < 32768: two 16-bit halves
+    uint32_t v;
+    __device__ __forceinline__ void set(int x, int y) { v = (uint32_t)x | ((uint32_t)y << 16); }
+    __device__ __forceinline__ int2 get() const { return make_int2((int)(v & 0xffffu), (int)(v >> 16)); }
+};
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(kSortThreads, FAST ? ONA_FAST_MINBLOCKS : ONA_SORT_MINBLOCKS)
 k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first, int K,
@@ -825,7 +835,9 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                      const unsigned short* __restrict__ nc, int ncs, int ic_off,
                      const unsigned short* __restrict__ st16) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int2 s_xy[kSortCap];                 // proposals of this pass, original order
+    // proposals of this pass, original order: packed to 2 x 16 bits with 16-bit ids (4 KB instead
+    // of 8 KB, which the L1 gets)
+    __shared__ XyStore<T> s_xy[kSortCap];
     __shared__ int2 s_res[kSortCap];                // (dcons, dind), original order
     __shared__ uint2 s_plan[FAST ? kSortCap : 1];   // fast walk: the two packed walks of every candidate
     __shared__ unsigned short s_order[kSortCap];    // sorted position -> candidate
@@ -886,7 +898,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                 } else {
                     rng_proposal(ikey, (unsigned long long)c, g.n1, g.n2, x, y);
                 }
-                s_xy[i] = make_int2(x, y);
+                s_xy[i].set(x, y);
             }
             const SwapCtx cx = make_ctx<T>(g, s_aln, x, y);
             int quads;
@@ -918,7 +930,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             u = __shfl_sync(0xffffffffu, u, 0);
             if (u < nhub) {
                 const int i = s_order[u];
-                const int2 q = s_xy[i];
+                const int2 q = s_xy[i].get();
                 const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
                 int dc, di;
                 if (FAST) {
@@ -946,7 +958,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             if (pos - lane >= n) break;
             if (pos < n) {
                 const int i = s_order[pos];
-                const int2 q = s_xy[i];
+                const int2 q = s_xy[i].get();
                 const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
                 int dc, di;
                 if (FAST) {
@@ -972,7 +984,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             const int i = j * kSortThreads + threadIdx.x;
             if (i >= n) continue;
             const int c = pass + i;
-            const int2 q = s_xy[i];
+            const int2 q = s_xy[i].get();
             const int2 r = s_res[i];
             const ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, q.x, q.y);
             const Scalars nw = apply_delta(cur, r.x, r.y, sd);
