@@ -225,6 +225,24 @@ int ona_hill_climb(ona_engine* e, int first, int count, long long iters, const i
 int ona_hill_climb_lists(ona_engine* e, int first, int count, long long iters, const int* const* xy_lists,
                          const int* objs, unsigned char* accepted, long long* num_accepted);
 
+/* Same, the proposals generated ON THE DEVICE as the reference's own stream (localSearch.cpp:21-28):
+ *     x = uniform_int_distribution<int>(0, n1 - 1)(prng);  y = uniform_int_distribution<int>(0, n2 - 2)(prng);
+ *     if (y >= x) y++;
+ * for prng a std::mt19937 (RandGenT, Network.h:10) and GNU libstdc++'s distributions (GCC >= 11:
+ * Lemire's multiply-shift with rejection, bits/uniform_int_dist.h) -- so neither 2*iters host draws nor
+ * an 8-byte-per-iteration upload happen per call.
+ *   mt_states  [count][625] in/out: per individual the generator's 624 state words followed by its
+ *              position (0..624), exactly the numbers operator<<(ostream&, mt19937) prints; on return
+ *              the state the caller's generator is in after the 2*iters (+ redrawn) draws, to be read
+ *              back with operator>>.
+ * Trajectory, counters and accumulators are those of ona_hill_climb fed with the host-drawn list. */
+int ona_hill_climb_mt(ona_engine* e, int first, int count, long long iters, unsigned int* mt_states,
+                      const int* objs, unsigned char* accepted, long long* num_accepted);
+/* the proposals alone ([count][iters][2] out) for explicit ranges n1 >= 1, n2 >= 2, states advanced as
+ * above -- for checking the stream against the host's libstdc++ */
+int ona_mt_proposals(ona_engine* e, int n1, int n2, int count, long long iters, unsigned int* mt_states,
+                     int* xy);
+
 /* Throughput form of the hill climb (north_star item 3: "thousands of candidates per individual
  * at once; accepted swaps are applied in-kernel").  Per individual, rounds of 1024 proposals
  * are scored against the round's base state; each is accepted or rejected against the base

@@ -123,6 +123,7 @@ struct ona_engine {
     DevPop pop{};
 
     DevBuf<int> t_i0, t_i1, t_i2, t_xy;
+    DevBuf<uint32_t> t_mt;   // mt19937 states of the callers of ona_hill_climb_mt
     DevBuf<double> t_d0, t_d1, t_d2, t_d3, t_d4, t_seq;
     DevBuf<unsigned char> t_u0, t_mask;
     DevBuf<long long> t_l0;
@@ -847,7 +848,7 @@ void ona_engine_destroy(ona_engine* e) {
     drop_graphs(e);
     e->owned.reset();
     free_pop(e);
-    e->t_i0.release(); e->t_i1.release(); e->t_i2.release(); e->t_xy.release();
+    e->t_i0.release(); e->t_i1.release(); e->t_i2.release(); e->t_xy.release(); e->t_mt.release();
     e->t_d0.release(); e->t_d1.release(); e->t_d2.release(); e->t_d3.release(); e->t_d4.release();
     e->t_seq.release(); e->t_u0.release(); e->t_mask.release(); e->t_l0.release();
     e->t_part.release(); e->t_ticket.release(); e->t_claims.release();
@@ -1396,10 +1397,27 @@ int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long 
     return ONA_OK;
 }
 
+// upload `count` mt19937 states ([624 words, position] each), validate them, and enqueue the
+// generation of iters proposals per state into xy_dev; the advanced states stay in e->t_mt
+static int mt_proposals_dev(ona_engine* e, int n1, int n2, int count, long long iters,
+                            const unsigned int* states, int* xy_dev) {
+    if (n1 < 1 || n2 < 2) return fail(ONA_ERR_INVALID, "proposal ranges are empty");
+    for (int i = 0; i < count; ++i)
+        if (states[(size_t)i * (kMtN + 1) + kMtN] > (unsigned)kMtN)
+            return fail(ONA_ERR_INVALID, "mt19937 state position outside [0,624]");
+    CU(e->t_mt.need((size_t)count * (kMtN + 1)));
+    TRY(h2d(e, e->t_mt.p, states, (size_t)count * (kMtN + 1)));
+    k_mt_proposals<<<count, 32, 0, e->stream>>>(n1, n2, iters, e->t_mt.p, xy_dev);
+    e->launches++;
+    CU(cudaGetLastError());
+    return ONA_OK;
+}
+
 // xy: one flat [count][iters][2] host array, or lists: `count` host pointers to [iters][2] arrays, or neither
+// or mt: [count][625] mt19937 states from which the reference's own proposal stream is generated on the device
 static int hill_climb_impl(ona_engine* e, int first, int count, long long iters, const int* xy,
                            const int* const* lists, unsigned long long seed, const int* objs,
-                           unsigned char* accepted, long long* num_accepted) {
+                           unsigned char* accepted, long long* num_accepted, unsigned int* mt = nullptr) {
     TRY(check_range(e, first, count));
     if (iters < 0) return fail(ONA_ERR_INVALID, "iters < 0");
     if (count == 0 || iters == 0) {
@@ -1421,6 +1439,10 @@ static int hill_climb_impl(ona_engine* e, int first, int count, long long iters,
                 TRY(h2d(e, e->t_xy.p + 2 * (size_t)i * (size_t)iters, lists[i], 2 * (size_t)iters));
             }
         xy_dev = e->t_xy.p;
+    } else if (mt) {
+        CU(e->t_xy.need(2 * n));
+        TRY(mt_proposals_dev(e, e->g.n1, e->g.n2, count, iters, mt, e->t_xy.p));
+        xy_dev = e->t_xy.p;
     }
     const int* objs_dev = nullptr;
     if (objs) {
@@ -1439,6 +1461,7 @@ static int hill_climb_impl(ona_engine* e, int first, int count, long long iters,
     CU(cudaStreamSynchronize(e->stream));   // before any pageable read-back, see finish_checked
     TRY(d2h(e, accepted, acc_dev, n));
     TRY(d2h(e, num_accepted, e->t_l0.p, (size_t)count));
+    if (mt) TRY(d2h(e, mt, e->t_mt.p, (size_t)count * (kMtN + 1)));
     return finish_checked(e, "proposal outside [0,n2)");
 }
 
@@ -1454,6 +1477,28 @@ int ona_hill_climb_lists(ona_engine* e, int first, int count, long long iters, c
     ENTER(e);
     if (!xy_lists) return fail(ONA_ERR_INVALID, "null proposal lists");
     return hill_climb_impl(e, first, count, iters, nullptr, xy_lists, 0ull, objs, accepted, num_accepted);
+}
+
+int ona_hill_climb_mt(ona_engine* e, int first, int count, long long iters, unsigned int* mt_states,
+                      const int* objs, unsigned char* accepted, long long* num_accepted) {
+    ENTER(e);
+    if (!mt_states) return fail(ONA_ERR_INVALID, "null mt19937 states");
+    return hill_climb_impl(e, first, count, iters, nullptr, nullptr, 0ull, objs, accepted, num_accepted, mt_states);
+}
+
+int ona_mt_proposals(ona_engine* e, int n1, int n2, int count, long long iters, unsigned int* mt_states,
+                     int* xy) {
+    ENTER(e);
+    if (!mt_states || !xy || count < 0 || iters < 0) return fail(ONA_ERR_INVALID, "bad argument");
+    if (count == 0 || iters == 0) return ONA_OK;
+    const size_t n = (size_t)count * (size_t)iters;
+    CU(e->t_xy.need(2 * n));
+    TRY(mt_proposals_dev(e, n1, n2, count, iters, mt_states, e->t_xy.p));
+    CU(cudaStreamSynchronize(e->stream));
+    TRY(d2h(e, xy, e->t_xy.p, 2 * n));
+    TRY(d2h(e, mt_states, e->t_mt.p, (size_t)count * (kMtN + 1)));
+    CU(cudaStreamSynchronize(e->stream));
+    return ONA_OK;
 }
 
 int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters, const int* xy,

@@ -1670,6 +1670,144 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     (void)warp;
 }
 
+// --------------------------------------------------------------------------------
+// The reference's own proposal stream, generated on the device (localSearch.cpp:21-28):
+//     x = uniform_int_distribution<int>(0, n1 - 1)(prng);  y = uniform_int_distribution<int>(0, n2 - 2)(prng);
+//     if (y >= x) y++;
+// with prng a std::mt19937 (Network.h:10) and the distributions as GNU libstdc++ (GCC >= 11)
+// implements them for a 32-bit engine: Lemire's multiply-shift, v = (u * range) >> 32, redrawing
+// while the low word is below 2^32 mod range (bits/uniform_int_dist.h:257-280).  One warp per
+// individual keeps the 624-word state in shared memory: the twist is done in three parallel phases
+// (words [0,227) read only old words, [227,454) and [454,623) read words of the phase before, 623
+// last), the 624 tempered draws of a state are mapped two per lane.  A redraw shifts which draw
+// belongs to x and which to y, so a block of draws is first checked for redraws under the role each
+// draw would have; the (one in a thousand) blocks that have one are replayed by a single lane.
+//   states  [count][625] in/out: the 624 state words and the position, as operator<< prints them
+//   xy      [count][iters][2] out
+// --------------------------------------------------------------------------------
+constexpr int kMtN = 624, kMtM = 397;
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+__device__ __forceinline__ uint32_t mt_mix(uint32_t cur, uint32_t nxt, uint32_t far) {
+    const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+// one draw of uniform_int_distribution(0, range - 1) from tempered word u: value, and whether the
+// reference would throw u away and draw again
+__device__ __forceinline__ bool mt_map(uint32_t u, uint32_t range, uint32_t threshold, int& v) {
+    const unsigned long long prod = (unsigned long long)u * (unsigned long long)range;
+    v = (int)(prod >> 32);
+    return (uint32_t)prod < threshold;
+}
+
+__global__ void __launch_bounds__(32)
+k_mt_proposals(int n1, int n2, long long iters, uint32_t* __restrict__ states, int* __restrict__ xy) {
+    __shared__ uint32_t s_x[kMtN];
+    const int pl = blockIdx.x, lane = threadIdx.x;
+    uint32_t* st = states + (size_t)pl * (kMtN + 1);
+    for (int i = lane; i < kMtN; i += 32) s_x[i] = st[i];
+    int p = (int)st[kMtN];
+    __syncwarp();
+    const uint32_t rx = (uint32_t)n1, ry = (uint32_t)(n2 - 1);
+    const uint32_t tx = (0u - rx) % rx, ty = (0u - ry) % ry;   // 2^32 mod range
+    int2* out = reinterpret_cast<int2*>(xy) + (size_t)pl * (size_t)iters;
+    long long it = 0;      // proposals written so far
+    int phase = 0;         // 1: the x of the next proposal has been drawn already (pend_x)
+    int pend_x = 0;
+    while (it < iters) {
+        if (p >= kMtN) {   // _M_gen_rand: every group of 32 words loads, synchronises, then stores
+            auto phase_of = [&](int lo, int hi, int far_off) {
+                for (int k0 = lo; k0 < hi; k0 += 32) {
+                    const int k = k0 + lane;
+                    uint32_t v = 0u;
+                    if (k < hi) v = mt_mix(s_x[k], s_x[k + 1], s_x[k + far_off]);
+                    __syncwarp();
+                    if (k < hi) s_x[k] = v;
+                    __syncwarp();
+                }
+            };
+            phase_of(0, kMtN - kMtM, kMtM);                              // [0,227): old words only
+            phase_of(kMtN - kMtM, 2 * (kMtN - kMtM), -(kMtN - kMtM));    // [227,454): new words of [0,227)
+            phase_of(2 * (kMtN - kMtM), kMtN - 1, -(kMtN - kMtM));       // [454,623): new words of [227,396)
+            if (lane == 0) s_x[kMtN - 1] = mt_mix(s_x[kMtN - 1], s_x[0], s_x[kMtM - 1]);
+            __syncwarp();
+            p = 0;
+        }
+        // draws p .. p + n of this state, as many as the remaining proposals can use
+        const long long want = 2 * (iters - it) - phase;
+        const int n = (int)min((long long)(kMtN - p), want);
+        // role of draw r (relative to p): (r + phase) odd = y.  Any redraw under these roles?
+        bool redraw = false;
+        for (int r = lane; r < n; r += 32) {
+            int v;
+            const bool is_y = ((r + phase) & 1) != 0;
+            redraw |= mt_map(mt_temper(s_x[p + r]), is_y ? ry : rx, is_y ? ty : tx, v);
+        }
+        if (__any_sync(0xffffffffu, redraw)) {
+            // replay this block draw by draw (lane 0); the block ends where the state does or
+            // with the last proposal's y, whichever comes first
+            if (lane == 0) {
+                int r = 0;
+                while (r < kMtN - p && it < iters) {
+                    int v;
+                    const bool is_y = phase != 0;
+                    const bool again = mt_map(mt_temper(s_x[p + r]), is_y ? ry : rx, is_y ? ty : tx, v);
+                    ++r;
+                    if (again) continue;
+                    if (!is_y) {
+                        pend_x = v;
+                        phase = 1;
+                    } else {
+                        out[it++] = make_int2(pend_x, v >= pend_x ? v + 1 : v);
+                        phase = 0;
+                    }
+                }
+                p += r;
+            }
+            p = __shfl_sync(0xffffffffu, p, 0);
+            it = __shfl_sync(0xffffffffu, it, 0);
+            phase = __shfl_sync(0xffffffffu, phase, 0);
+            pend_x = __shfl_sync(0xffffffffu, pend_x, 0);
+            continue;
+        }
+        // no redraw: draw 0 completes a pending x, then pairs, then possibly a lone x at the end
+        int r0 = 0;
+        if (phase) {
+            if (lane == 0) {
+                int v;
+                mt_map(mt_temper(s_x[p]), ry, ty, v);
+                out[it] = make_int2(pend_x, v >= pend_x ? v + 1 : v);
+            }
+            it += 1;
+            r0 = 1;
+        }
+        const int pairs = (n - r0) / 2;
+        for (int k = lane; k < pairs; k += 32) {
+            int vx, vy;
+            mt_map(mt_temper(s_x[p + r0 + 2 * k]), rx, tx, vx);
+            mt_map(mt_temper(s_x[p + r0 + 2 * k + 1]), ry, ty, vy);
+            out[it + k] = make_int2(vx, vy >= vx ? vy + 1 : vy);
+        }
+        it += pairs;
+        phase = 0;
+        if ((n - r0) & 1) {   // the last draw of the block is an x without its y yet
+            int v;
+            mt_map(mt_temper(s_x[p + n - 1]), rx, tx, v);
+            pend_x = v;
+            phase = 1;
+        }
+        p += n;
+    }
+    __syncwarp();
+    for (int i = lane; i < kMtN; i += 32) st[i] = s_x[i];
+    if (lane == 0) st[kMtN] = (uint32_t)p;
+}
+
 // proposals of the device RNG, for host-side checking / replay
 __global__ void k_rng_proposals(int n1, int n2, int count, int K, unsigned long long seed,
                                 long long island_offset, int first, long long start,

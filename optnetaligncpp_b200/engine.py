@@ -24,6 +24,7 @@ EXPORTS = [
     "ona_set_island_offset", "ona_set_objectives", "ona_pop_resize", "ona_pop_upload", "ona_pop_download",
     "ona_pop_set_counters", "ona_pop_get_counters", "ona_full_fitness", "ona_full_fitness_dev",
     "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_steepest_step", "ona_rng_proposals", "ona_hill_climb", "ona_hill_climb_lists", "ona_hill_climb_batched",
+    "ona_hill_climb_mt", "ona_mt_proposals",
     "ona_apply_swaps", "ona_apply_edits", "ona_export_fitness_dev", "ona_nsga2_rank", "ona_nsga2_rank_dev",
 ]
 
@@ -98,6 +99,8 @@ def load_library(build_if_missing=True):
     L.ona_rng_proposals.argtypes = [vp, ci, ci, ci, C.c_ulonglong, ll, vp]
     L.ona_hill_climb.argtypes = [vp, ci, ci, ll, vp, C.c_ulonglong, vp, vp, vp]
     L.ona_hill_climb_batched.argtypes = [vp, ci, ci, ll, vp, C.c_ulonglong, vp, vp]
+    L.ona_hill_climb_mt.argtypes = [vp, ci, ci, ll, vp, vp, vp, vp]
+    L.ona_mt_proposals.argtypes = [vp, ci, ci, ci, ll, vp, vp]
     L.ona_apply_swaps.argtypes = [vp, ci, ci, ci, vp]
     L.ona_export_fitness_dev.argtypes = [vp, ci, ci, vp]
     L.ona_apply_edits.argtypes = [vp, ci, ci, ci, vp]
@@ -346,6 +349,27 @@ class Engine:
         nacc = np.empty(count, np.int64)
         self._check(self.L.ona_hill_climb_lists(self.h, first, count, int(iters), ptrs, _ptr(o), None, _ptr(nacc)))
         return nacc
+
+    def hill_climb_mt(self, iters, states, objs=None, first=0, want_accepted=False):
+        """ona_hill_climb_mt: the reference's own proposal stream generated on the device from
+        `states` ([count,625] uint32: mt19937 words + position); returns (accepted, num_accepted,
+        states after the draws)."""
+        st = np.ascontiguousarray(states, np.uint32).copy()
+        count = st.shape[0]
+        o = None if objs is None else _i32(np.broadcast_to(np.asarray(objs), (count,)))
+        acc = np.empty((count, iters), np.uint8) if want_accepted else None
+        nacc = np.empty(count, np.int64)
+        self._check(self.L.ona_hill_climb_mt(self.h, first, count, int(iters), _ptr(st), _ptr(o), _ptr(acc),
+                                             _ptr(nacc)))
+        return acc, nacc, st
+
+    def mt_proposals(self, n1, n2, iters, states):
+        """ona_mt_proposals: (xy [count,iters,2], states after)."""
+        st = np.ascontiguousarray(states, np.uint32).copy()
+        count = st.shape[0]
+        xy = np.empty((count, iters, 2), np.int32)
+        self._check(self.L.ona_mt_proposals(self.h, int(n1), int(n2), count, int(iters), _ptr(st), _ptr(xy)))
+        return xy, st
 
     def hill_climb_batched(self, iters=None, xy=None, seed=0, objs=None, first=0, count=None):
         """throughput hill climb: rounds of 1024 proposals scored at once, a conflict-free accepted

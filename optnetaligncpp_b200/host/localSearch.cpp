@@ -5,7 +5,9 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <iostream>
+#include <sstream>
 
 #include "nsga-ii.h"
 #include "ona_host.hpp"
@@ -42,10 +44,24 @@ struct PinnedList {
     }
 };
 
+constexpr size_t kMtWords = 625;   // what operator<< of std::mt19937 prints: 624 state words, position
+
+// From this many iterations on the proposals are drawn on the device (ona_hill_climb_mt): the
+// generator's state travels instead of the list.  Below it (proportionalSearch's 500-iteration
+// climbs) printing and parsing 625 numbers costs more than the draws.  ONA_HOST_MT_MIN overrides.
+long long mt_threshold() {
+    static const long long v = [] {
+        const char* s = getenv("ONA_HOST_MT_MIN");
+        return s ? atoll(s) : 8192ll;
+    }();
+    return v;
+}
+
 struct Request {
     Alignment* aln;
     const vector<fitnessName>* names;
-    int* xy = nullptr;   // [iters][2], in the calling thread's pinned buffer
+    int* xy = nullptr;   // [iters][2], in the calling thread's pinned buffer; or
+    unsigned int* mt = nullptr;   // the caller's mt19937 state (625 numbers): proposals drawn on the device
     int obj;
     long long iters;
     bool done = false;
@@ -76,7 +92,9 @@ public:
             }
             vector<Request*> batch;
             for (Request* q : queue_)
-                if (q->iters == queue_.front()->iters && *q->names == *queue_.front()->names) batch.push_back(q);
+                if (q->iters == queue_.front()->iters && *q->names == *queue_.front()->names &&
+                    !q->mt == !queue_.front()->mt)
+                    batch.push_back(q);
             for (Request* q : batch) queue_.erase(find(queue_.begin(), queue_.end(), q));
             callers_ = batch.size() + queue_.size();
             lk.unlock();
@@ -105,8 +123,17 @@ private:
                 lists.push_back(q->xy);
             }
             ctx.upload(alns);
-            ona_host::check(ona_hill_climb_lists(ctx.engine(), 0, (int)alns.size(), batch[0]->iters, lists.data(),
-                                                 objs.data(), nullptr, nullptr));
+            if (batch[0]->mt) {   // generator states in, advanced states out
+                vector<unsigned int> states(batch.size() * kMtWords);
+                for (size_t i = 0; i < batch.size(); ++i)
+                    copy(batch[i]->mt, batch[i]->mt + kMtWords, states.begin() + i * kMtWords);
+                ona_host::check(ona_hill_climb_mt(ctx.engine(), 0, (int)alns.size(), batch[0]->iters, states.data(),
+                                                  objs.data(), nullptr, nullptr));
+                for (size_t i = 0; i < batch.size(); ++i)
+                    copy(states.begin() + i * kMtWords, states.begin() + (i + 1) * kMtWords, batch[i]->mt);
+            } else
+                ona_host::check(ona_hill_climb_lists(ctx.engine(), 0, (int)alns.size(), batch[0]->iters,
+                                                     lists.data(), objs.data(), nullptr, nullptr));
             ctx.download(alns);
             for (Request* q : batch) q->aln->computeFitness(*q->names);
         } catch (const exception& ex) {
@@ -146,6 +173,31 @@ void correctHillClimb(RandGenT& prng, Alignment* aln, bool total, int maxIters,
     r.names = &fitnessNames;
     r.obj = obj;
     r.iters = maxIters;
+    ona_host::Context& ctx = ona_host::context_for(*aln);
+    if (maxIters >= mt_threshold() && aln->actualSize >= 1 && aln->aln.size() >= 2) {
+        // the stream of :21-28 is generated on the device from the generator's state (operator<<
+        // gives the 624 words and the position, operator>> puts the advanced state back), so the
+        // caller's prng ends exactly where the reference's loop leaves it
+        unsigned int state[kMtWords];
+        {
+            stringstream ss;
+            ss << prng;
+            for (size_t i = 0; i < kMtWords; ++i) {
+                unsigned long v;
+                ss >> v;
+                state[i] = (unsigned int)v;
+            }
+        }
+        r.mt = state;
+        {
+            ona_host::StatTimer st(ona_host::kStatClimbWait, maxIters);
+            batcher_for(ctx).submit(ctx, r);
+        }
+        stringstream ss;
+        for (size_t i = 0; i < kMtWords; ++i) ss << state[i] << ' ';
+        ss >> prng;
+        return;
+    }
     thread_local PinnedList pinned;
     r.xy = pinned.need(2 * (size_t)maxIters);
     for (int i = 0; i < maxIters; i++) {
@@ -155,7 +207,6 @@ void correctHillClimb(RandGenT& prng, Alignment* aln, bool total, int maxIters,
         r.xy[2 * i] = x;
         r.xy[2 * i + 1] = y;
     }
-    ona_host::Context& ctx = ona_host::context_for(*aln);
     ona_host::StatTimer st(ona_host::kStatClimbWait, maxIters);
     batcher_for(ctx).submit(ctx, r);
 }

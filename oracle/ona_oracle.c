@@ -409,6 +409,60 @@ void orc_hill_climb_replay(OrcAln* a, const int* xy, long iters, const int* name
     }
 }
 
+/* The proposal stream of localSearch.cpp:21-28 restated in plain C:
+ *     x = uniform_int_distribution<int>(0, n1 - 1)(prng);  y = uniform_int_distribution<int>(0, n2 - 2)(prng);
+ *     if (y >= x) y++;
+ * prng = std::mt19937 (Network.h:10): MT19937 of Matsumoto & Nishimura (n = 624, m = 397, r = 31,
+ * a = 0x9908b0df, tempering (11, 0xffffffff), (7, 0x9d2c5680), (15, 0xefc60000), 18), state regenerated
+ * when all 624 words have been used.  The distributions are GNU libstdc++'s (GCC >= 11,
+ * bits/uniform_int_dist.h:_S_nd): for a 32-bit generator and a range of R values, Lemire's
+ * multiply-shift  v = (u * R) >> 32  with the draw repeated while  (uint32)(u * R) < 2^32 mod R.
+ * state = the 625 numbers operator<< of std::mt19937 prints (624 words, then the position 0..624);
+ * it is advanced in place.  Pinned against the compiled reference shim (libstdc++ itself) in
+ * tests/test_oracle_vs_reference.py. */
+static uint32_t orc_mt_next(uint32_t* st) {
+    uint32_t* x = st;
+    if (st[624] >= 624u) {
+        for (int k = 0; k < 624; ++k) {
+            uint32_t y = (x[k] & 0x80000000u) | (x[(k + 1) % 624] & 0x7fffffffu);
+            x[k] = x[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        st[624] = 0;
+    }
+    uint32_t z = x[st[624]++];
+    z ^= z >> 11;
+    z ^= (z << 7) & 0x9d2c5680u;
+    z ^= (z << 15) & 0xefc60000u;
+    z ^= z >> 18;
+    return z;
+}
+static int orc_mt_uniform(uint32_t* st, uint32_t range) {
+    uint64_t prod = (uint64_t)orc_mt_next(st) * (uint64_t)range;
+    uint32_t low = (uint32_t)prod;
+    if (low < range) {
+        uint32_t threshold = (0u - range) % range;
+        while (low < threshold) {
+            prod = (uint64_t)orc_mt_next(st) * (uint64_t)range;
+            low = (uint32_t)prod;
+        }
+    }
+    return (int)(prod >> 32);
+}
+void orc_mt_seed(uint32_t seed, uint32_t* state) {   /* mersenne_twister_engine::seed(value) */
+    state[0] = seed;
+    for (uint32_t i = 1; i < 624; ++i) state[i] = 1812433253u * (state[i - 1] ^ (state[i - 1] >> 30)) + i;
+    state[624] = 624;
+}
+void orc_mt_xy_stream(uint32_t* state, int n1, int n2, long iters, int* xy) {
+    for (long i = 0; i < iters; ++i) {
+        int x = orc_mt_uniform(state, (uint32_t)n1);
+        int y = orc_mt_uniform(state, (uint32_t)(n2 - 1));
+        if (y >= x) y++;
+        xy[2 * i] = x;
+        xy[2 * i + 1] = y;
+    }
+}
+
 /* localSearch.cpp:88-120 */
 double orc_swap_normalized_delta(OrcAln* a, const int* names, int M, int x, int y) {
     double currFit[ORC_MAX_OBJ], newFit[ORC_MAX_OBJ], pct[ORC_MAX_OBJ];

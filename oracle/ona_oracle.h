@@ -83,6 +83,11 @@ double orc_time_hill_climb(OrcAln** alns, int nalns, const int* xy, long iters, 
 double orc_time_full_fitness(OrcAln** alns, int nalns, const int* names, int M, long reps,
                              int nthreads, double* sink);
 
+/* the proposal stream of localSearch.cpp:21-28 (std::mt19937 + libstdc++'s uniform_int_distribution);
+ * state = 624 words + position, advanced in place */
+void orc_mt_seed(uint32_t seed, uint32_t* state);
+void orc_mt_xy_stream(uint32_t* state, int n1, int n2, long iters, int* xy);
+
 /* NSGA-II ranking of the objective rows (ona_oracle_nsga2.c; nsga-ii.cpp:14-134).
  * fitness [P][M]; has_norm [P] or NULL; norm_io [P][M] in/out; dom_rank, front_order,
  * order_after, crowd_dist [P]; front_offsets [P+1].  See oracle/ref_shim.cpp:ref_nsga2. */

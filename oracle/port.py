@@ -69,6 +69,8 @@ def lib():
     L.orc_time_full_fitness.restype = C.c_double
     L.orc_time_full_fitness.argtypes = [vp, C.c_int, I32P, C.c_int, C.c_long, C.c_int, vp]
     L.orc_apply_edits.argtypes = [vp, I32P, C.c_int]
+    L.orc_mt_seed.argtypes = [C.c_uint32, vp]
+    L.orc_mt_xy_stream.argtypes = [vp, C.c_int, C.c_int, C.c_long, I32P]
     L.orc_nsga2.restype = C.c_int
     L.orc_nsga2.argtypes = [C.c_int, C.c_int] + [vp] * 9
     L.orc_dominates.restype = C.c_int
@@ -242,3 +244,19 @@ def gnu_sort_by_key(keys, idx, heap=False):
     (lib().orc_gnu_heap_sort_by_key if heap else lib().orc_gnu_sort_by_key)(len(i), k.ctypes.data,
                                                                             i.ctypes.data)
     return i
+
+
+def mt_state(seed):
+    """std::mt19937(seed) as its operator<< prints it: 624 state words and the position (624)."""
+    st = np.empty(625, np.uint32)
+    lib().orc_mt_seed(seed, st.ctypes.data_as(C.c_void_p))
+    return st
+
+
+def mt_xy_stream(state, n1, n2, iters):
+    """the proposals correctHillClimb draws (localSearch.cpp:21-28) from an mt19937 in `state`;
+    returns (xy [iters,2], state after the draws)."""
+    st = np.ascontiguousarray(state, np.uint32).copy()
+    xy = np.empty(2 * iters, np.int32)
+    lib().orc_mt_xy_stream(st.ctypes.data_as(C.c_void_p), n1, n2, iters, xy)
+    return xy.reshape(-1, 2), st

@@ -359,6 +359,22 @@ def gen_xy_stream(seed, n1, n2, iters):
     return xy.reshape(-1, 2)
 
 
+def mt_state(seed):
+    """std::mt19937(seed) as operator<< prints it: 624 state words and the position."""
+    st = np.empty(625, np.uint32)
+    lib().ref_mt_state(C.c_uint32(seed), st.ctypes.data_as(C.c_void_p))
+    return st
+
+
+def gen_xy_stream_state(state, n1, n2, iters):
+    """proposals of localSearch.cpp:21-28 from an explicit mt19937 state; returns (xy, state after)."""
+    st = np.ascontiguousarray(state, np.uint32).copy()
+    xy = np.empty(2 * iters, np.int32)
+    lib().ref_gen_xy_stream_state(st.ctypes.data_as(C.c_void_p), C.c_int(n1), C.c_int(n2), C.c_long(iters),
+                                  xy.ctypes.data_as(C.c_void_p))
+    return xy.reshape(-1, 2), st
+
+
 def _handles(alns):
     return (C.c_void_p * len(alns))(*[a.h for a in alns])
 

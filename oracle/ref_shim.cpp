@@ -33,6 +33,7 @@
 #include <random>
 #include <string>
 #include <thread>
+#include <sstream>
 #include <vector>
 
 #include "Alignment.h"
@@ -313,6 +314,42 @@ void ref_gen_xy_stream(uint32_t seed, int n1, int n2, long iters, int* xy) {
         if (y >= x) y++;
         xy[2 * i] = x;
         xy[2 * i + 1] = y;
+    }
+}
+
+// same, starting from an explicit generator state and returning the state the draws leave behind:
+// state = the 625 numbers operator<< / operator>> of std::mt19937 exchange (624 words, position)
+void ref_gen_xy_stream_state(uint32_t* state, int n1, int n2, long iters, int* xy) {
+    std::stringstream ss;
+    for (int i = 0; i < 625; ++i) ss << state[i] << ' ';
+    RandGenT prng;
+    ss >> prng;
+    auto randNonDummyIndex = std::uniform_int_distribution<int>(0, n1 - 1);
+    auto randIndex = std::uniform_int_distribution<int>(0, n2 - 2);
+    for (long i = 0; i < iters; ++i) {
+        node x = randNonDummyIndex(prng);
+        node y = randIndex(prng);
+        if (y >= x) y++;
+        xy[2 * i] = x;
+        xy[2 * i + 1] = y;
+    }
+    std::stringstream out;
+    out << prng;
+    for (int i = 0; i < 625; ++i) {
+        unsigned long v;
+        out >> v;
+        state[i] = (uint32_t)v;
+    }
+}
+// the state of mt19937(seed) in the same form
+void ref_mt_state(uint32_t seed, uint32_t* state) {
+    RandGenT prng(seed);
+    std::stringstream out;
+    out << prng;
+    for (int i = 0; i < 625; ++i) {
+        unsigned long v;
+        out >> v;
+        state[i] = (uint32_t)v;
     }
 }
 

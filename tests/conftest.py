@@ -35,6 +35,11 @@ def edits_golden():
     return dict(np.load(os.path.join(GOLDEN, "edits.npz")))
 
 
+@pytest.fixture(scope="session")
+def mt_golden():
+    return dict(np.load(os.path.join(GOLDEN, "mt_stream.npz")))
+
+
 def dense_from_coo(n1, n2, r, c, v):
     S = np.zeros((n1, n2), np.float64)
     S[r, c] = v

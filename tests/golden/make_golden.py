@@ -232,8 +232,29 @@ def nsga2():
           "ka2 crowd", out["ka2_crowd_dist"])
 
 
+MT_CASES = [(7, 6000, 8000, 3000), (42, 5499, 9633, 2000), (1, 3, 5, 1000),
+            (9, 1_500_000_000, 2_000_000_000, 1500)]
+
+
+def mt_stream():
+    """the (x, y) proposals of localSearch.cpp:21-28 drawn by the compiled reference toolchain's own
+    std::mt19937 / uniform_int_distribution<int>, and the generator state they leave behind"""
+    out = {"cases": np.array(MT_CASES, np.int64)}
+    for i, (seed, n1, n2, iters) in enumerate(MT_CASES):
+        st = ref.mt_state(seed)
+        xy, after = ref.gen_xy_stream_state(st, n1, n2, iters)
+        assert np.array_equal(xy, ref.gen_xy_stream(seed, n1, n2, iters))
+        out["c%d_state" % i], out["c%d_xy" % i], out["c%d_after" % i] = st, xy, after
+    np.savez_compressed(os.path.join(OUT, "mt_stream.npz"), **out)
+    print("mt_stream.npz written;", [out["c%d_xy" % i][0].tolist() for i in range(len(MT_CASES))])
+
+
 if __name__ == "__main__":
     assert ref.available(), "build oracle/_ref first (make -C oracle)"
+    if sys.argv[1:] == ["mt_stream"]:
+        mt_stream()
+        sys.exit(0)
+    mt_stream()
     nsga2()
     edits()
     small_pair()

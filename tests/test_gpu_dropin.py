@@ -36,8 +36,12 @@ def test_dropin_matches_reference(with_goc, lines):
     seed, iters, nthreads = 77, 4000, 3
     a1 = paths.get("annos1", "-") if with_goc else "-"
     a2 = paths.get("annos2", "-") if with_goc else "-"
+    # with GOC: correctHillClimb's proposals come from the device (the caller's mt19937 state travels,
+    # ona_hill_climb_mt) whatever the iteration count; without: drawn on the host below 8192 iterations
+    env = dict(os.environ, ONA_HOST_MT_MIN="0") if with_goc else dict(os.environ)
     out = subprocess.run([DEMO, paths["net1"], paths["net2"], paths["sim"], a1, a2, str(seed), str(iters),
-                          str(nthreads), os.path.join(d, "out")], capture_output=True, text=True, timeout=300)
+                          str(nthreads), os.path.join(d, "out")], capture_output=True, text=True, timeout=300,
+                         env=env)
     assert out.returncode == 0, out.stderr
     lines = [l.split() for l in out.stdout.strip().splitlines()]
 

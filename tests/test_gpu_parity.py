@@ -785,3 +785,56 @@ def test_hill_climb_every_group_size(monkeypatch, group, total):
         st = o.state()
         assert np.array_equal(a[p], st[0]) and np.array_equal(inv[p], st[1]) and np.array_equal(m[p], st[2])
         assert (int(c["cons"][p]), int(c["ind"][p]), float(c["bits"][p]), float(c["goc"][p])) == o.counters()
+
+
+# ------------------------------------------------- the reference's own proposal stream on the device
+def test_mt_proposal_stream_on_device(mid, mt_golden, swap_delta_walk):
+    """ona_mt_proposals / ona_hill_climb_mt: std::mt19937 + libstdc++'s uniform_int_distribution
+    (localSearch.cpp:21-28) generated on the device -- proposals and the generator state left behind,
+    against golden vectors recorded from the real ones and the oracle's restatement; the climb they
+    drive equals the climb on the host-drawn list."""
+    if swap_delta_walk != "classic-walk":
+        pytest.skip("independent of the swap-delta walk")
+    pair, S, G, prob = mid
+    names = [engine.S3, engine.BITSCORE_SUM]
+    e = engine.Engine.from_pair(pair, names)
+    g = mt_golden
+    for i, (seed, n1, n2, iters) in enumerate(g["cases"].tolist()):
+        xy, after = e.mt_proposals(n1, n2, iters, g["c%d_state" % i][None])
+        assert np.array_equal(xy[0], g["c%d_xy" % i]), i
+        assert np.array_equal(after[0], g["c%d_after" % i]), i
+    # many generators at once, odd lengths (an x left pending across a state refill), states that start
+    # in the middle of a block, ranges where every third draw is rejected and drawn again
+    rng = np.random.default_rng(3)
+    for n1, n2, iters in [(600, 800, 1), (600, 800, 311), (600, 800, 312), (600, 800, 313), (600, 800, 2501),
+                          (1, 2, 700), (1, 3, 700), (1_500_000_000, 2_000_000_000, 1999),
+                          (2_147_483_647, 2_147_483_647, 1000), (1_073_741_825, 1_073_741_826, 1777)]:
+        states = np.stack([port.mt_state(int(s)) for s in rng.integers(0, 2**32, 9)])
+        for p in range(9):          # advance each by a different amount first
+            states[p] = port.mt_xy_stream(states[p], 77, 99, int(rng.integers(0, 700)))[1]
+        xy, after = e.mt_proposals(n1, n2, iters, states)
+        for p in range(9):
+            xo, so = port.mt_xy_stream(states[p], n1, n2, iters)
+            assert np.array_equal(xy[p], xo), (n1, n2, iters, p)
+            assert np.array_equal(after[p], so), (n1, n2, iters, p)
+        xy2, after2 = e.mt_proposals(n1, n2, 5, after)      # and the states are resumable
+        for p in range(9):
+            assert np.array_equal(xy2[p], port.mt_xy_stream(after[p], n1, n2, 5)[0])
+    # the climb
+    P, iters = 5, 7001
+    aln, _ = synth.random_population(pair, P, seed=11)
+    states = np.stack([port.mt_state(1000 + p) for p in range(P)])
+    e.upload(aln)
+    e.full_fitness(seed_mode=engine.SEED_REFCOMPAT | engine.SUM_SEQUENTIAL)
+    acc, nacc, after = e.hill_climb_mt(iters, states, objs=[-1, 0, 1, -1, 0], want_accepted=True)
+    a, _, _ = e.download()
+    c = e.counters()
+    for p in range(P):
+        xy, so = port.mt_xy_stream(states[p], pair.n1, pair.n2, iters)
+        assert np.array_equal(after[p], so)
+        o = port.Aln(prob, aln[p])
+        o.compute_fitness(names)
+        oacc = o.hill_climb_replay(xy, names, obj=[-1, 0, 1, -1, 0][p], want_accepted=True)
+        assert np.array_equal(acc[p], oacc) and nacc[p] == oacc.sum()
+        assert np.array_equal(a[p], o.state()[0])
+        assert (c["cons"][p], c["ind"][p], c["bits"][p]) == o.counters()[:3]

@@ -164,3 +164,20 @@ def test_nsga2_reference_suite_known_answers(nsga_golden):
     assert np.allclose(r["crowd_dist"][1:4], [1.0, 2.0 / 3.0, 1.0], rtol=1e-12)
     assert r["crowd_dist"][0] == r["crowd_dist"][4] == np.finfo(np.float64).max
     nsga_cases.assert_same(r, {k: g["ka2_" + k] for k in NSGA_KEYS}, "ka2")
+
+
+# ------------------------------------------------------------------ proposal stream (localSearch.cpp:21-28)
+def test_mt_proposal_stream_golden(mt_golden):
+    """the C restatement of std::mt19937 + libstdc++'s uniform_int_distribution against proposals and
+    end states recorded from the real ones (make_golden.py:mt_stream)"""
+    g = mt_golden
+    for i, (seed, n1, n2, iters) in enumerate(g["cases"].tolist()):
+        st = port.mt_state(seed)
+        assert np.array_equal(st, g["c%d_state" % i])
+        xy, after = port.mt_xy_stream(st, n1, n2, iters)
+        assert np.array_equal(xy, g["c%d_xy" % i]) and np.array_equal(after, g["c%d_after" % i]), i
+        # resumable: the stream drawn in two calls equals the stream drawn in one
+        h = iters // 3
+        xa, sa = port.mt_xy_stream(st, n1, n2, h)
+        xb, sb = port.mt_xy_stream(sa, n1, n2, iters - h)
+        assert np.array_equal(np.concatenate([xa, xb]), xy) and np.array_equal(sb, after)

@@ -220,3 +220,25 @@ def test_nsga2_edge_shapes_match_reference():
              nsga_cases.make_case("single_front", 257, 4, 2), np.zeros((20, 2)), -rng.random((50, 2))]
     for i, f in enumerate(cases):
         nsga_cases.assert_same(port.nsga2(f), ref.nsga2(f), i)
+
+
+MT_RANGES = [(6000, 8000), (5499, 9633), (20000, 20000), (1, 2), (3, 5), (1, 3),
+             (1_500_000_000, 2_000_000_000),      # about every third draw is thrown away and repeated
+             (2_147_483_647, 2_147_483_647), (1_073_741_825, 1_073_741_826)]
+
+
+def test_mt_proposal_stream_matches_libstdcxx():
+    """orc_mt_seed / orc_mt_xy_stream (MT19937 + Lemire's mapping as libstdc++ does it) against the
+    real std::mt19937 and uniform_int_distribution<int> in the compiled shim: proposals AND the
+    generator state left behind, from fresh seeds and from states in the middle of a block."""
+    for seed in (0, 1, 7, 42, 5489, 0xFFFFFFFF):
+        assert np.array_equal(port.mt_state(seed), ref.mt_state(seed)), seed
+    for t, (n1, n2) in enumerate(MT_RANGES):
+        st = ref.mt_state(100 + t)
+        for iters in (1, 311, 312, 313, 5000, 1):      # odd totals leave an x pending across blocks
+            xr, sr = ref.gen_xy_stream_state(st, n1, n2, iters)
+            xo, so = port.mt_xy_stream(st, n1, n2, iters)
+            assert np.array_equal(xr, xo), (n1, n2, iters)
+            assert np.array_equal(sr, so), (n1, n2, iters)
+            st = sr
+    assert np.array_equal(ref.gen_xy_stream(7, 600, 800, 4000), port.mt_xy_stream(port.mt_state(7), 600, 800, 4000)[0])
