@@ -2,7 +2,7 @@
 """Aggregate a .ncu-rep's source page by CUDA source line: warp-level instructions executed and
 stall samples per file:line (needs -lineinfo and --import-source on).
 
-    python profiles/ncu_by_line.py gpurun_out/prof.ncu-rep [top_n]
+    python profiles/ncu_by_line.py gpurun_out/prof.ncu-rep [top_n] [kernel-name substring]
 """
 import csv
 import io
@@ -14,11 +14,13 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    want = sys.argv[3] if len(sys.argv) > 3 else None
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     path, h, agg, text = None, None, {}, {}
     seen_kernel = None
+    skipping = False
     for r in rows:
         if not r:
             continue
@@ -26,16 +28,23 @@ def main():
             path = os.path.basename(r[1])
             continue
         if r[0] == "Function Name":
+            if want is not None and seen_kernel is None and want not in r[1]:
+                h = None
+                skipping = True
+                continue
+            skipping = False
             if seen_kernel is None:
                 seen_kernel = r[1]
             elif r[1] != seen_kernel:
-                break                       # first kernel only
+                break                       # one kernel only (the first, or the first whose name matches)
             continue
         if r[0] == "Line No":
+            if skipping:
+                continue
             h = r
             ie, si = h.index("Instructions Executed"), h.index("# Samples")
             continue
-        if h is None or len(r) != len(h) or not r[0].isdigit():
+        if skipping or h is None or len(r) != len(h) or not r[0].isdigit():
             continue
         key = (path, int(r[0]))
         a = agg.setdefault(key, [0, 0])

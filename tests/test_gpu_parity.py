@@ -21,6 +21,7 @@ def swap_delta_walk(request, monkeypatch):
     # ... and with both from-scratch kernels: edge slices over several CTAs (small batches) and one
     # CTA per network (from 32 individuals on), which also leaves the node counts behind
     monkeypatch.setenv("ONA_FF_SPLIT_MIN", "1000000" if request.param == "classic-walk" else "1")
+    return request.param
 
 ALL = list(range(10))
 RTOL = 1e-9          # north_star: "S3/ICS ratios and summed bitscores agree within 1e-9 relative"
