@@ -769,6 +769,38 @@ __device__ __forceinline__ void unstage_state(const DevPop& pop, int p, const T*
     }
 }
 
+// One individual's 16-bit state mirror (aln then alnInv, contiguous) into shared memory with ONE bulk
+// copy of the TMA engine (cp.async.bulk, 1-D: no tensor map) completing on an mbarrier: no thread
+// issues loads or stores for the staging, and the CTA's prologue runs beside it.
+__device__ __forceinline__ void bulk_stage_begin(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b)
+            : "memory");
+    }
+}
+// every thread that reads the staged bytes waits for phase 0 of the barrier (after a __syncthreads
+// that makes thread 0's mbarrier.init visible)
+__device__ __forceinline__ void bulk_stage_wait(uint64_t* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(b)
+            : "memory");
+    }
+}
+
 // Where one individual's packed state lives while a CTA works on it:
 //   uint16_t : staged into shared memory (n2 < 32768; 4*n2 bytes), written back on release
 //   uint32_t : used in place in HBM/L2 (any n2); same flag layout as the global arrays

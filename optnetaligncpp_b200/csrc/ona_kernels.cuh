@@ -817,6 +817,12 @@ __device__ __forceinline__ void sort_pass(const int (&key)[PER], unsigned short 
 #ifndef ONA_FAST_MINBLOCKS
 #define ONA_FAST_MINBLOCKS 3
 #endif
+#ifndef ONA_STAGE_BULK
+#define ONA_STAGE_BULK 1     // stage the 16-bit state mirror with one cp.async.bulk instead of per-thread copies
+#endif
+#ifndef ONA_SD_SMEM_NAMES
+#define ONA_SD_SMEM_NAMES 1  // phase D reads the objective list from shared memory, not the parameter bank
+#endif
 template <typename T> struct XyStore {           // wide ids: two ints
     int2 v;
     __device__ __forceinline__ void set(int x, int y) { v = make_int2(x, y); }
@@ -846,15 +852,24 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     __shared__ double s_curfit[kMaxObj];
     __shared__ double s_bestv[kSortWarps];
     __shared__ long long s_besti[kSortWarps];
+    __shared__ int s_names[kMaxObj];
+    __shared__ __align__(8) uint64_t s_bar;
     T *s_aln, *s_inv;
     const int pl = blockIdx.y, p = first + pl;
+    bool bulk = false;
     if (FAST && sizeof(T) == 2 && st16) {
-        // k_node_counts left this individual's state in 16-bit form: plain 16-byte copies
+        // the evaluation (or k_node_counts) left this individual's state in 16-bit form, aln then
+        // alnInv in one contiguous run of 4 * n2p bytes (a multiple of 16, 16-byte aligned)
         s_aln = reinterpret_cast<T*>(smem_raw);
         s_inv = s_aln + pop.n2p;
+#if ONA_STAGE_BULK
+        bulk = true;
+        bulk_stage_begin(smem_raw, st16 + (size_t)pl * 2 * pop.n2p, (uint32_t)pop.n2p * 4u, &s_bar);
+#else
         const uint4* src = reinterpret_cast<const uint4*>(st16 + (size_t)pl * 2 * pop.n2p);
         uint4* dst = reinterpret_cast<uint4*>(smem_raw);
         for (int i = threadIdx.x; i < (pop.n2p >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+#endif
     } else {
         State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
     }
@@ -862,8 +877,12 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     Scalars cur;
     cur.C = pop.cons[p]; cur.I = pop.ind[p]; cur.size = pop.size[p];
     cur.bits = pop.bits[p]; cur.goc = pop.goc[p];
-    if (threadIdx.x < ob.M) s_curfit[threadIdx.x] = objective(ob.names[threadIdx.x], cur, g.E1);
+    if (threadIdx.x < ob.M) {
+        s_curfit[threadIdx.x] = objective(ob.names[threadIdx.x], cur, g.E1);
+        s_names[threadIdx.x] = ob.names[threadIdx.x];
+    }
     __syncthreads();
+    if (bulk) bulk_stage_wait(&s_bar);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = (K + gridDim.x - 1) / gridDim.x;
@@ -992,7 +1011,8 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             const bool want_snd = out.snd || sum.block_best;
             double v;
             const bool imp = judge_move(ob, obj, cur, s_curfit, nw, g.E1,
-                                        out.fit ? out.fit + o * ob.M : nullptr, want_snd, v);
+                                        out.fit ? out.fit + o * ob.M : nullptr, want_snd, v,
+                                        ONA_SD_SMEM_NAMES ? s_names : nullptr);
             if (out.cons) out.cons[o] = nw.C;
             if (out.ind) out.ind[o] = nw.I;
             if (out.bits) out.bits[o] = nw.bits;
