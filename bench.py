@@ -442,6 +442,19 @@ def run_ours(args):
             pass
         ff_ms = float(np.mean(full_ms))
         ff_bytes = full_fitness_bytes(pair, 1, M)
+        # second ceiling, the one the gathers actually run into: scattered 32-byte-sector reads per
+        # second from an L2-resident table, measured live (ona_probe_gather_rate, 32 MiB table), against
+        # the L2 read sectors the kernel requests per launch (offline ncu count of the same launch)
+        l2g = None
+        try:
+            g_peak, _ = e.probe_gather_rate(32 << 20)
+            sect = tj.get("k_swap_deltas", {}).get("l2_read_sectors_per_launch")
+            if sect:
+                l2g = {"peak_sectors_per_s": g_peak, "peak_kind": "measured live: scattered 4-byte reads, 8 in flight per thread, 32 MiB table",
+                       "l2_read_sectors_per_launch": sect, "sectors_source": traffic_src,
+                       "achieved_sectors_per_s": sect / (k_ms * 1e-3), "frac": sect / (k_ms * 1e-3) / g_peak}
+        except Exception as ex:      # the probe is an aid, never a reason to lose the bench line
+            l2g = {"error": str(ex)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -460,7 +473,7 @@ def run_ours(args):
                          "limiter": "instruction issue / L2 latency; inputs L2-resident, DRAM ~2 % busy "
                                     "(achieved is algorithmic bytes / time, not DRAM throughput)",
                          "algorithmic_bytes_per_swap_delta": bytes_per_delta,
-                         "units_per_launch": P * K, "kernel_ms": k_ms},
+                         "units_per_launch": P * K, "kernel_ms": k_ms, "l2_gather": l2g},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "call": "ona_swap_deltas: pinned host proposals [P,K,2] int32 -> accept bit (u8) + swapNormalizedDelta (f64) per candidate, pinned host"},

@@ -279,6 +279,15 @@ int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* 
 #define ONA_EDIT_CROSS 3
 int ona_apply_edits(ona_engine* e, int first, int count, int nops, const int* ops);
 
+/* ------------------------------------------------------------ measurement aid
+ * Replaces nothing in the reference.  Measures, on the engine's GPU and stream, how many scattered
+ * 4-byte reads per second (one 32-byte sector each, 8 independent loads in flight per thread, all SMs)
+ * the memory system serves from a table of table_bytes (rounded down to a power of two; sized like the
+ * engine's L2-resident structures it stays in L2).  This is the request pattern of the engine's gathers
+ * -- adjacency words, node words, signatures, hash slots -- and so the ceiling bench.py sets the
+ * swap-delta kernel's L2 sector rate against.  Best of 4 timed launches after 2 warm-up ones. */
+int ona_probe_gather_rate(ona_engine* e, long long table_bytes, double* sectors_per_s, double* ms);
+
 /* -------------------------------------------------------------- device access */
 /* copy the [count][M] objective rows of slots first..first+count into a device buffer
  * (e.g. a torch tensor's data_ptr) on the engine's stream -- the send buffer of the

@@ -1380,6 +1380,42 @@ int ona_steepest_step(ona_engine* e, int slot, double* best_delta, int* best_x, 
     return ONA_OK;
 }
 
+int ona_probe_gather_rate(ona_engine* e, long long table_bytes, double* sectors_per_s, double* ms_out) {
+    ENTER(e);
+    if (!sectors_per_s || table_bytes < 4096 || table_bytes > (1ll << 31)) return fail(ONA_ERR_INVALID, "bad argument");
+    size_t words = 1024;
+    while (words * 2 * 4 <= (size_t)table_bytes) words *= 2;        // power of two, <= table_bytes
+    uint32_t* table = nullptr;
+    uint32_t* sink = nullptr;
+    CU(cudaMalloc(&table, words * 4));
+    if (cudaMalloc(&sink, 4) != cudaSuccess) { cudaFree(table); return fail(ONA_ERR_CUDA, "cudaMalloc"); }
+    cudaMemsetAsync(table, 0x5a, words * 4, e->stream);
+    const int ctas = e->sm_count * 8, trips = 64;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {      // the first launches also pull the table into L2
+        cudaEventRecord(a, e->stream);
+        k_probe_gather<<<ctas, 256, 0, e->stream>>>(table, (uint32_t)(words - 1), trips, sink);
+        cudaEventRecord(b, e->stream);
+        cudaStreamSynchronize(e->stream);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep >= 2) best = std::min(best, ms);
+        e->launches++;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    const cudaError_t err = cudaGetLastError();
+    cudaFree(table);
+    cudaFree(sink);
+    if (err != cudaSuccess) return fail(ONA_ERR_CUDA, cudaGetErrorString(err));
+    *sectors_per_s = (double)ctas * 256.0 * trips * 8.0 / ((double)best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return ONA_OK;
+}
+
 int ona_rng_proposals(ona_engine* e, int first, int count, int K, unsigned long long seed,
                       long long start, int* xy) {
     ENTER(e);

@@ -1828,6 +1828,34 @@ k_mt_proposals(int n1, int n2, long long iters, uint32_t* __restrict__ states, i
     if (lane == 0) st[kMtN] = (uint32_t)p;
 }
 
+// --------------------------------------------------------------------------------
+// Measurement aid: the rate at which the memory system serves scattered 4-byte reads -- one 32-byte
+// sector each -- from a table that lives in L2, i.e. the request pattern of this engine's gathers
+// (adjacency words, node words, signatures, hash slots).  Every thread keeps 8 independent loads
+// in flight per trip; addresses come from a counter hash, so consecutive lanes hit unrelated sectors.
+// --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_probe_gather(const uint32_t* __restrict__ table, uint32_t word_mask, int trips, uint32_t* __restrict__ sink) {
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t acc = 0u;
+    for (int t = 0; t < trips; ++t) {
+        const unsigned long long r0 = mix64(tid * 0x10001ull + (unsigned long long)t * 4ull);
+        const unsigned long long r1 = mix64(r0), r2 = mix64(r1), r3 = mix64(r2);
+        uint32_t v[8];
+        v[0] = __ldg(table + ((uint32_t)r0 & word_mask));
+        v[1] = __ldg(table + ((uint32_t)(r0 >> 32) & word_mask));
+        v[2] = __ldg(table + ((uint32_t)r1 & word_mask));
+        v[3] = __ldg(table + ((uint32_t)(r1 >> 32) & word_mask));
+        v[4] = __ldg(table + ((uint32_t)r2 & word_mask));
+        v[5] = __ldg(table + ((uint32_t)(r2 >> 32) & word_mask));
+        v[6] = __ldg(table + ((uint32_t)r3 & word_mask));
+        v[7] = __ldg(table + ((uint32_t)(r3 >> 32) & word_mask));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc ^= v[k];
+    }
+    if (acc == 0x9e3779b9u) sink[0] = acc;   // keeps the loads alive
+}
+
 // proposals of the device RNG, for host-side checking / replay
 __global__ void k_rng_proposals(int n1, int n2, int count, int K, unsigned long long seed,
                                 long long island_offset, int first, long long start,

@@ -24,7 +24,7 @@ EXPORTS = [
     "ona_set_island_offset", "ona_set_objectives", "ona_pop_resize", "ona_pop_upload", "ona_pop_download",
     "ona_pop_set_counters", "ona_pop_get_counters", "ona_full_fitness", "ona_full_fitness_dev",
     "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_steepest_step", "ona_rng_proposals", "ona_hill_climb", "ona_hill_climb_lists", "ona_hill_climb_batched",
-    "ona_hill_climb_mt", "ona_mt_proposals",
+    "ona_hill_climb_mt", "ona_mt_proposals", "ona_probe_gather_rate",
     "ona_apply_swaps", "ona_apply_edits", "ona_export_fitness_dev", "ona_nsga2_rank", "ona_nsga2_rank_dev",
 ]
 
@@ -101,6 +101,7 @@ def load_library(build_if_missing=True):
     L.ona_hill_climb_batched.argtypes = [vp, ci, ci, ll, vp, C.c_ulonglong, vp, vp]
     L.ona_hill_climb_mt.argtypes = [vp, ci, ci, ll, vp, vp, vp, vp]
     L.ona_mt_proposals.argtypes = [vp, ci, ci, ci, ll, vp, vp]
+    L.ona_probe_gather_rate.argtypes = [vp, ll, vp, vp]
     L.ona_apply_swaps.argtypes = [vp, ci, ci, ci, vp]
     L.ona_export_fitness_dev.argtypes = [vp, ci, ci, vp]
     L.ona_apply_edits.argtypes = [vp, ci, ci, ci, vp]
@@ -370,6 +371,12 @@ class Engine:
         xy = np.empty((count, iters, 2), np.int32)
         self._check(self.L.ona_mt_proposals(self.h, int(n1), int(n2), count, int(iters), _ptr(st), _ptr(xy)))
         return xy, st
+
+    def probe_gather_rate(self, table_bytes):
+        """measurement aid: scattered 32-byte-sector reads per second from an L2-resident table."""
+        r, ms = C.c_double(), C.c_double()
+        self._check(self.L.ona_probe_gather_rate(self.h, int(table_bytes), C.byref(r), C.byref(ms)))
+        return r.value, ms.value
 
     def hill_climb_batched(self, iters=None, xy=None, seed=0, objs=None, first=0, count=None):
         """throughput hill climb: rounds of 1024 proposals scored at once, a conflict-free accepted

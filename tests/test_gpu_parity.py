@@ -821,6 +821,12 @@ def test_mt_proposal_stream_on_device(mid, mt_golden, swap_delta_walk):
         xy2, after2 = e.mt_proposals(n1, n2, 5, after)      # and the states are resumable
         for p in range(9):
             assert np.array_equal(xy2[p], port.mt_xy_stream(after[p], n1, n2, 5)[0])
+    # a long stream (481 state refills): only the last proposals and the end state are compared in full
+    states = np.stack([port.mt_state(s) for s in (5, 6, 7)])
+    xy, after = e.mt_proposals(6000, 8000, 150001, states)
+    for p in range(3):
+        xo, so = port.mt_xy_stream(states[p], 6000, 8000, 150001)
+        assert np.array_equal(xy[p], xo) and np.array_equal(after[p], so)
     # the climb
     P, iters = 5, 7001
     aln, _ = synth.random_population(pair, P, seed=11)
