@@ -711,6 +711,7 @@ __device__ __forceinline__ void undo_accumulators(const Scalars& after, const Sc
 //           from `cur`;  fit_out (nullable): receives the new objectives.
 //   names: the objective list in shared memory (nullptr: read it from the kernel parameters; the
 //          indexed constant-bank load is slow on a single warp's critical path)
+template <bool STREAM = false>
 __device__ __forceinline__ bool judge_move(const DevObjectives& ob, int obj, const Scalars& cur,
                                            const double* curfit, const Scalars& nw,
                                            unsigned long long E1, double* fit_out, bool want_snd,
@@ -721,7 +722,10 @@ __device__ __forceinline__ bool judge_move(const DevObjectives& ob, int obj, con
         const int name = names ? names[j] : ob.names[j];
         const double fn = objective(name, nw, E1);
         const double fc = curfit ? curfit[j] : objective(name, cur, E1);
-        if (fit_out) fit_out[j] = fn;
+        if (fit_out) {
+            if (STREAM) __stcs(fit_out + j, fn);   // global output stream, written once: keep it out of the L1's way
+            else fit_out[j] = fn;
+        }
         if (fn < fc) any_lt = true;
         if (j == obj && fn <= fc) obj_le = true;
         if (want_snd) {

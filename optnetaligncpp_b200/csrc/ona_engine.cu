@@ -455,6 +455,8 @@ int launch_deltas_sorted(ona_engine* e, int first, int count, int K, const int* 
     if (nc) {
         int rc = set_smem(k_swap_deltas_sorted<T, true>, smem);
         if (rc) return rc;
+        static const int carve = getenv("ONA_SD_CARVEOUT") ? atoi(getenv("ONA_SD_CARVEOUT")) : -1;
+        if (carve >= 0) CU(cudaFuncSetAttribute(k_swap_deltas_sorted<T, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         k_swap_deltas_sorted<T, true><<<grid, kSortThreads, smem, e->stream>>>(
             e->g, e->S, e->G, e->ob, e->pop, first, K, xy_dev, seed, e->island_offset, obj, out, sum, e->d_flag,
             grid_x0, nc, e->nc_stride, e->nc_ic_off,
@@ -744,7 +746,8 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
         g.cq2 = g.cq1 + ncq1;
         if ((rc = upload<uint32_t>(e, pk1, &g.pk1))) return bail(rc);
         if ((rc = upload<uint32_t>(e, pk2, &g.pk2))) return bail(rc);
-        e->fast_ok = cq.size() < ((size_t)1 << 24) && max_row < 65536;
+        // (the fast walk parks a candidate's two deltas in 16 bits each: |delta| <= 2 * longest row)
+        e->fast_ok = cq.size() < ((size_t)1 << 24) && max_row < 16384;
     }
     g.W1 = (pr->n1 + 31) / 32;
     {

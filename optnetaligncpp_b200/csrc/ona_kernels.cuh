@@ -820,6 +820,9 @@ __device__ __forceinline__ void sort_pass(const int (&key)[PER], unsigned short 
 #ifndef ONA_STAGE_BULK
 #define ONA_STAGE_BULK 1     // stage the 16-bit state mirror with one cp.async.bulk instead of per-thread copies
 #endif
+#ifndef ONA_SD_STREAM_OUT
+#define ONA_SD_STREAM_OUT 1  // per-candidate outputs with streaming (evict-first) stores
+#endif
 #ifndef ONA_SD_SMEM_NAMES
 #define ONA_SD_SMEM_NAMES 1  // phase D reads the objective list from shared memory, not the parameter bank
 #endif
@@ -833,6 +836,25 @@ template <> struct XyStore<uint16_t> {           // ids < 32768: two 16-bit halv
     __device__ __forceinline__ void set(int x, int y) { v = (uint32_t)x | ((uint32_t)y << 16); }
     __device__ __forceinline__ int2 get() const { return make_int2((int)(v & 0xffffu), (int)(v >> 16)); }
 };
+// (dcons, dind) of a candidate between the phases.  The fast walk is only used on graphs without a
+// node of 16 384 or more neighbours (engine creation), where both deltas fit 16 bits: 4 KB instead of
+// 8 KB per CTA, which brings three resident CTAs under the 164 KB shared-memory carve-out (92 KB of
+// L1 instead of 60 KB for the node words, counts and signatures the kernel gathers).
+template <bool FAST> struct ResStore {
+    int2 v;
+    __device__ __forceinline__ void set(int dc, int di) { v = make_int2(dc, di); }
+    __device__ __forceinline__ int2 get() const { return v; }
+};
+#ifndef ONA_RES16
+#define ONA_RES16 1
+#endif
+#if ONA_RES16
+template <> struct ResStore<true> {
+    uint32_t v;
+    __device__ __forceinline__ void set(int dc, int di) { v = ((uint32_t)dc & 0xffffu) | ((uint32_t)di << 16); }
+    __device__ __forceinline__ int2 get() const { return make_int2((int)(short)(v & 0xffffu), (int)v >> 16); }
+};
+#endif
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(kSortThreads, FAST ? ONA_FAST_MINBLOCKS : ONA_SORT_MINBLOCKS)
 k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first, int K,
@@ -844,7 +866,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     // proposals of this pass, original order: packed to 2 x 16 bits with 16-bit ids (4 KB instead
     // of 8 KB, which the L1 gets)
     __shared__ XyStore<T> s_xy[kSortCap];
-    __shared__ int2 s_res[kSortCap];                // (dcons, dind), original order
+    __shared__ ResStore<FAST> s_res[kSortCap];      // (dcons, dind), original order
     __shared__ uint2 s_plan[FAST ? kSortCap : 1];   // fast walk: the two packed walks of every candidate
     __shared__ unsigned short s_order[kSortCap];    // sorted position -> candidate
     __shared__ unsigned short s_cnt[kSortWarps * kSortPer][kSortBins];  // per (virtual) warp histogram
@@ -904,7 +926,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             int x = 0, y = 0;
             if (i < n) {
                 if (xy) {
-                    const int2 v = __ldg(reinterpret_cast<const int2*>(xy) + (size_t)pl * K + c);
+                    const int2 v = __ldcs(reinterpret_cast<const int2*>(xy) + (size_t)pl * K + c);
                     x = v.x; y = v.y;
                     if ((unsigned)x >= (unsigned)g.n2 || (unsigned)y >= (unsigned)g.n2) {
                         atomicOr(err_flag, 1);  // reported by the host entry point as ONA_ERR_INVALID
@@ -931,7 +953,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                 if (i < n) {
                     int dc0, di0;
                     fast_delta(g, cx, nw, nc + (size_t)pl * ncs, ic_off, 0, 0, dc0, di0);
-                    s_res[i] = make_int2(dc0, di0);
+                    s_res[i].set(dc0, di0);
                     s_plan[i] = pack_fast_plan(fp);
                 }
             } else {
@@ -958,7 +980,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                     walk_fast<T>(g, s_aln, s_inv, cx, fp, lane, 32, ix, iy);
                     ix = warp_sum<int>(ix);
                     iy = warp_sum<int>(iy);
-                    const int2 base = s_res[i];
+                    const int2 base = s_res[i].get();
                     dc = base.x + ix + iy;
                     di = base.y;
                 } else {
@@ -970,7 +992,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                     seen = __reduce_or_sync(0xffffffffu, (unsigned)seen);
                     if (lane == 0) special_terms(g, cx, seen, dc, di);
                 }
-                if (lane == 0) s_res[i] = make_int2(dc, di);
+                if (lane == 0) s_res[i].set(dc, di);
                 continue;
             }
             const int pos = nhub + (u - nhub) * 32 + lane;
@@ -984,7 +1006,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                     const FastPlan fp = unpack_fast_plan(s_plan[i]);   // never a hub here: lengths fit
                     int ix, iy;
                     walk_fast<T>(g, s_aln, s_inv, cx, fp, 0, 1, ix, iy);
-                    const int2 base = s_res[i];
+                    const int2 base = s_res[i].get();
                     dc = base.x + ix + iy;
                     di = base.y;
                 } else {
@@ -993,7 +1015,7 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                     walk_plan<T>(g, s_aln, s_inv, cx, pl4, 0, 1, dc, di, seen);
                     if (seen) special_terms(g, cx, seen, dc, di);
                 }
-                s_res[i] = make_int2(dc, di);
+                s_res[i].set(dc, di);
             }
         }
         __syncthreads();
@@ -1004,23 +1026,37 @@ k_swap_deltas_sorted(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             if (i >= n) continue;
             const int c = pass + i;
             const int2 q = s_xy[i].get();
-            const int2 r = s_res[i];
+            const int2 r = s_res[i].get();
             const ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, q.x, q.y);
             const Scalars nw = apply_delta(cur, r.x, r.y, sd);
             const size_t o = (size_t)pl * K + c;
             const bool want_snd = out.snd || sum.block_best;
             double v;
-            const bool imp = judge_move(ob, obj, cur, s_curfit, nw, g.E1,
-                                        out.fit ? out.fit + o * ob.M : nullptr, want_snd, v,
-                                        ONA_SD_SMEM_NAMES ? s_names : nullptr);
+            const bool imp = judge_move<ONA_SD_STREAM_OUT != 0>(ob, obj, cur, s_curfit, nw, g.E1,
+                                                                out.fit ? out.fit + o * ob.M : nullptr, want_snd, v,
+                                                                ONA_SD_SMEM_NAMES ? s_names : nullptr);
+            // the output stream is written once and never read here: streaming stores keep it from
+            // displacing the node words, counts and signatures the L1 holds for the gathers
+#if ONA_SD_STREAM_OUT
+            if (out.cons) __stcs(out.cons + o, nw.C);
+            if (out.ind) __stcs(out.ind + o, nw.I);
+            if (out.bits) __stcs(out.bits + o, nw.bits);
+            if (out.goc) __stcs(out.goc + o, nw.goc);
+            if (out.improved) __stcs(out.improved + o, (unsigned char)(imp ? 1 : 0));
+#else
             if (out.cons) out.cons[o] = nw.C;
             if (out.ind) out.ind[o] = nw.I;
             if (out.bits) out.bits[o] = nw.bits;
             if (out.goc) out.goc[o] = nw.goc;
             if (out.improved) out.improved[o] = imp ? 1 : 0;
+#endif
             n_imp += imp ? 1 : 0;
             if (want_snd) {
+#if ONA_SD_STREAM_OUT
+                if (out.snd) __stcs(out.snd + o, v);
+#else
                 if (out.snd) out.snd[o] = v;
+#endif
                 if (v > bestv || (v == bestv && c < besti)) { bestv = v; besti = c; }  // first wins (localSearch.cpp:141)
             }
         }
