@@ -556,8 +556,12 @@ __device__ __forceinline__ void walk_fast(const DevGraph& g, const T* s_aln, con
         sg1 = p.side1 ? __ldg(g.sig1 + c.y) : __ldg(g.sig2 + c.ax);
         row1 = p.side1 ? g.adj1 + (size_t)c.y * (size_t)g.W1 : g.adj2 + (size_t)c.ax * (size_t)g.W;
     }
+// Two quads per trip, both requested before either is scored, halve the dependent L2 round trips of a
+// walk at the price of scoring a padding quad whenever a walk has an odd number of them.  It paid while
+// the kernel had 60 KB of L1 (0.4106 vs 0.4075 ms); with 92 KB one quad per trip is faster (0.3154 vs
+// 0.3230 ms), so it is off.
 #ifndef ONA_FAST_UNROLL2
-#define ONA_FAST_UNROLL2 1
+#define ONA_FAST_UNROLL2 0
 #endif
     auto quad = [&](const int4& t, bool w1) {
         const int side = w1 ? p.side1 : p.side0;
