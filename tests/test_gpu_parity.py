@@ -347,6 +347,19 @@ def test_error_behaviour():
     # empty inputs are no-ops
     e.hill_climb(iters=0)
     e.swap_deltas(np.empty((2, 0, 2), np.int32))
+    # device proposal stream: a generator position beyond 624 or an empty range is refused, zero
+    # iterations leave the states alone
+    st = np.stack([port.mt_state(1), port.mt_state(2)])
+    bad_st = st.copy()
+    bad_st[1, 624] = 625
+    with pytest.raises(engine.OnaError, match="position"):
+        e.hill_climb_mt(10, bad_st)
+    with pytest.raises(engine.OnaError):
+        e.mt_proposals(5, 1, 10, st)
+    with pytest.raises(engine.OnaError):
+        e.hill_climb_mt(10, st, objs=[0, 7])
+    _, nacc, after = e.hill_climb_mt(0, st)
+    assert np.array_equal(after, st) and not nacc.any()
 
 
 def test_forked_queue_and_per_individual_lists(mid):
