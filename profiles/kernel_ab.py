@@ -38,7 +38,10 @@ def child():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     res = {}
 
+    noflush = bool(os.environ.get("ONA_AB_NOFLUSH"))   # warm-L2 timing, to see what the cold misses cost
+
     def timed(fn, n, do_flush=True):
+        do_flush = do_flush and not noflush
         ts = []
         for i in range(n + 3):
             if do_flush:
