@@ -13,8 +13,15 @@ from optnetaligncpp_b200 import synth
 pair = bench.make_workload()
 d = tempfile.mkdtemp()
 p = synth.write_text(pair, os.path.join(d, "c2"))
-popsize, gens, hci = 200, 1, int(os.environ.get("HCI", "2000"))   # 200 children x 2 climbs x 500*hci iterations
-iters_total = popsize * gens * 2 * 500 * hci
+popsize, gens, hci = 200, 1, int(os.environ.get("HCI", "2000"))
+# steadystate.cpp:137 lets every worker start another child while fewer than popsize*generations have been
+# FINISHED, so a run with T workers makes popsize*generations + T - 1 children (215 at 16 threads, 455 at 256,
+# 1 223 at 1 024 -- confirmed by the call counts ONA_HOST_STATS prints); each child is climbed twice for
+# 500*hillclimbiters iterations (:243-253).  Runs at different --nthreads therefore do different amounts of
+# work: compare children per second, not wall-clock.
+def work(nthreads):
+    children = popsize * gens + nthreads - 1
+    return children, children * 2 * 500 * hci
 base = ["--net1", p["net1"], "--net2", p["net2"], "--total", "--s3", "--bitscores", p["sim"], "--blastsum",
         "--popsize", str(popsize), "--generations", str(gens), "--hillclimbiters", str(hci), "--nooutput", "--randseed", "1"]
 ncpu = os.cpu_count() or 1
@@ -36,13 +43,22 @@ run("reference_cpu_fixed_cost", REF, 1, fixed)
 run("gpu_engine_fixed_cost_first_process", GPU, 1, fixed)   # the first CUDA process on a fresh box pays extra
 run("gpu_engine_fixed_cost", GPU, 1, fixed)
 run("reference_cpu", REF, ncpu)
-for nt in (ncpu, 64, 256):
+for nt in (ncpu, 64, 256, 1024):
     run("gpu_engine_nthreads_%d" % nt, GPU, nt)
 for k, v in res.items():
     if "fixed_cost" in k:
         continue
     f = res["gpu_engine_fixed_cost" if k.startswith("gpu") else "reference_cpu_fixed_cost"]["wall_s"]
-    v["climb_iterations"] = iters_total
-    v["iterations_per_s_net_of_fixed_cost"] = iters_total / max(v["wall_s"] - f, 1e-9)
+    v["children"], v["climb_iterations"] = work(v["nthreads"])
+    v["children_per_s_wall"] = v["children"] / v["wall_s"]
+    v["iterations_per_s_net_of_fixed_cost"] = v["climb_iterations"] / max(v["wall_s"] - f, 1e-9)
+for k, v in res.items():
+    if k.startswith("gpu_engine_nthreads"):
+        v["children_per_s_vs_reference_cpu"] = v["children_per_s_wall"] / res["reference_cpu"]["children_per_s_wall"]
+        print("%-28s %5d children  %6.1f children/s wall (%.1fx the all-CPU build)  %.2e climb iterations/s net of start-up" % (
+            k, v["children"], v["children_per_s_wall"], v["children_per_s_vs_reference_cpu"], v["iterations_per_s_net_of_fixed_cost"]), flush=True)
+print("%-28s %5d children  %6.1f children/s wall  %.2e climb iterations/s net of start-up" % (
+    "reference_cpu", res["reference_cpu"]["children"], res["reference_cpu"]["children_per_s_wall"],
+    res["reference_cpu"]["iterations_per_s_net_of_fixed_cost"]), flush=True)
 json.dump(dict(host_threads=ncpu, popsize=popsize, generations=gens, hillclimbiters=hci, runs=res),
           open(os.path.join(ROOT, "profiles", sys.argv[1] if len(sys.argv) > 1 else "driver_walltime.json"), "w"), indent=1)
