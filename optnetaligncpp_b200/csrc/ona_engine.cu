@@ -508,11 +508,12 @@ int launch_climb_tg(ona_engine* e, int first, int count, long long iters, const 
 int launch_climb(ona_engine* e, int first, int count, long long iters, const int* xy_dev,
                  unsigned long long seed, const int* objs_dev, int force_obj,
                  unsigned char* acc_dev, long long* nacc_dev) {
-    // lanes per proposal: 8 by default; 4 (128-thread CTAs, twice as many resident individuals)
-    // when the batch is large enough to fill the SMs several times over
+    // lanes per proposal: 8 while every individual gets a resident CTA (two 256-thread CTAs per SM);
+    // beyond that 4 (128-thread CTAs, four per SM): a second, partly filled wave costs far more than
+    // the slower CTA (320 individuals: 3.7 vs 5.4 x 10^8 iterations/s, profiles/r2b_hc_group_sweep.json)
     int G = e->group;
     if (G != 4 && G != 16) G = 8;
-    if (!e->group_forced && count > 3 * e->sm_count) G = 4;
+    if (!e->group_forced && count > 2 * e->sm_count) G = 4;
     if (e->small_ids) {
         if (G == 4) return launch_climb_tg<uint16_t, 4>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
         if (G == 16) return launch_climb_tg<uint16_t, 16>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
