@@ -26,13 +26,18 @@ base = ["--net1", p["net1"], "--net2", p["net2"], "--total", "--s3", "--bitscore
         "--popsize", str(popsize), "--generations", str(gens), "--hillclimbiters", str(hci), "--nooutput", "--randseed", "1"]
 ncpu = os.cpu_count() or 1
 res = {}
-def run(tag, binary, nthreads, args=None):
-    t0 = time.perf_counter()
-    out = subprocess.run([binary] + (args or base) + ["--nthreads", str(nthreads)], capture_output=True, text=True, timeout=3000)
-    dt = time.perf_counter() - t0
-    assert out.returncode == 0, out.stderr[-500:]
-    res[tag] = dict(nthreads=nthreads, wall_s=dt)
-    print("%-28s nthreads %4d  wall %7.2f s" % (tag, nthreads, dt), flush=True)
+def run(tag, binary, nthreads, args=None, reps=1):
+    # wall-clock of a whole process; run-to-run spread is large for the GPU build (how the worker threads'
+    # calls happen to fall into batched launches), so those are repeated and the median is kept
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = subprocess.run([binary] + (args or base) + ["--nthreads", str(nthreads)], capture_output=True, text=True, timeout=3000)
+        ts.append(time.perf_counter() - t0)
+        assert out.returncode == 0, out.stderr[-500:]
+    dt = sorted(ts)[len(ts) // 2]
+    res[tag] = dict(nthreads=nthreads, wall_s=dt, wall_s_all=ts)
+    print("%-28s nthreads %4d  wall %7.2f s  %s" % (tag, nthreads, dt, ["%.2f" % t for t in ts]), flush=True)
 # fixed cost of a run (process start, loaders incl. the 384 MB dense BLAST matrix, for the GPU build
 # also CUDA context + engine creation): one child, no hill climbing
 fixed = [a for a in base]
@@ -41,10 +46,10 @@ fixed[fixed.index("--hillclimbiters") + 1] = "0"
 REF, GPU = os.path.join(ROOT, "oracle/_ref/optnetalign_ref"), os.path.join(ROOT, "optnetaligncpp_b200/host/_build/optnetalign")
 run("reference_cpu_fixed_cost", REF, 1, fixed)
 run("gpu_engine_fixed_cost_first_process", GPU, 1, fixed)   # the first CUDA process on a fresh box pays extra
-run("gpu_engine_fixed_cost", GPU, 1, fixed)
+run("gpu_engine_fixed_cost", GPU, 1, fixed, reps=3)
 run("reference_cpu", REF, ncpu)
 for nt in (ncpu, 64, 256, 1024):
-    run("gpu_engine_nthreads_%d" % nt, GPU, nt)
+    run("gpu_engine_nthreads_%d" % nt, GPU, nt, reps=3)
 for k, v in res.items():
     if "fixed_cost" in k:
         continue
