@@ -82,12 +82,15 @@ public:
             // Give concurrent callers time to join.  A launch takes as long as its slowest climb
             // whatever the batch size (one CTA per alignment, up to ~300 of them run at once), so
             // the leader waits until as many callers are queued as were around at the previous
-            // launch (those it climbed plus those left waiting), for at most ~5 % of the launch's
-            // expected duration (200 us for a 500-iteration climb, 50 ms for a 10^6-iteration one).
+            // launch (those it climbed plus those left waiting), for at most ~10-20 % of the launch's
+            // expected duration (200 us for a 500-iteration climb, 100 ms for a 10^6-iteration one).
+            // Before the first launch nothing is known about the callers: the leader waits the whole cap,
+            // so that a driver's worker threads, which all reach their first climb within a few
+            // milliseconds of each other, share a launch instead of queueing behind a launch of one.
             {
-                const long long cap_us = min<long long>(100000, max<long long>(200, r.iters / 20));
+                const long long cap_us = min<long long>(100000, max<long long>(200, r.iters / 10));
                 const auto t_end = chrono::steady_clock::now() + chrono::microseconds(cap_us);
-                while (chrono::steady_clock::now() < t_end && queue_.size() < callers_)
+                while (chrono::steady_clock::now() < t_end && (callers_ == 0 || queue_.size() < callers_))
                     cv_.wait_for(lk, chrono::microseconds(100));
             }
             vector<Request*> batch;
@@ -144,7 +147,7 @@ private:
     condition_variable cv_;
     vector<Request*> queue_;
     bool leader_ = false;
-    size_t callers_ = 1;   // callers around at the previous launch
+    size_t callers_ = 0;   // callers around at the previous launch (0: no launch yet)
 };
 
 Batcher& batcher_for(ona_host::Context& ctx) {
