@@ -100,6 +100,7 @@ struct ona_engine {
     bool small_ids = false;  // n2 < 32768: uint16 shared-memory state
     int group = 8;           // lanes per candidate in the hill-climb kernel's phase 1
     bool group_forced = false;
+    bool climb_mb5 = false;   // ONA_GROUP=45: 4 lanes per proposal with five CTAs per SM (tests, A/B runs)
     int pipe_slices = 8;     // host-buffer pipeline depth of ona_swap_deltas
     bool fast_ok = false;    // the fast swap-delta walk (node counts) is usable on this problem
     int fast_min_k = 4096;   // ... and pays from this many candidates per individual on
@@ -490,38 +491,54 @@ int launch_deltas(ona_engine* e, int first, int count, int K, const int* xy_dev,
     return launch_deltas_sorted<uint32_t>(e, first, count, K, xy_dev, seed, obj, out, sum, chunks, nc);
 }
 
-template <typename T, int G>
+template <typename T, int G, int MB = 0>
 int launch_climb_tg(ona_engine* e, int first, int count, long long iters, const int* xy_dev,
                     unsigned long long seed, const int* objs_dev, int force_obj,
                     unsigned char* acc_dev, long long* nacc_dev) {
     const size_t smem = state_smem(e);
-    int rc = set_smem(k_hill_climb<T, G>, smem);
+    int rc = set_smem(k_hill_climb<T, G, MB>, smem);
     if (rc) return rc;
-    k_hill_climb<T, G><<<count, kRound * G, smem, e->stream>>>(e->g, e->S, e->G, e->ob, e->pop, first,
-                                                              iters, xy_dev, seed, e->island_offset,
-                                                              objs_dev, force_obj, acc_dev, nacc_dev, e->d_flag);
+    k_hill_climb<T, G, MB><<<count, kRound * G, smem, e->stream>>>(e->g, e->S, e->G, e->ob, e->pop, first,
+                                                                  iters, xy_dev, seed, e->island_offset,
+                                                                  objs_dev, force_obj, acc_dev, nacc_dev, e->d_flag);
     e->launches++;
     CU(cudaGetLastError());
     return ONA_OK;
 }
 
+// Which form of the climb kernel for `count` individuals.  One CTA climbs one individual for the whole
+// call, so a launch takes as many waves as count / (CTAs resident at once), and a CTA is slower the
+// more of them share an SM.  Measured on the yeast-fly pair, iterations/s per CTA (profiles/README.md):
+//   8 lanes per proposal, 256 threads, 2 CTAs/SM : 2.04e6      4 lanes, 128 threads, 4 CTAs/SM : 1.48e6
+//   4 lanes, 128 threads, 5 CTAs/SM (96 registers): 1.20e6
+// The form with the shortest waves x time-per-wave wins: 8 lanes up to 2 x SMs individuals, then
+// 4 lanes with four or five CTAs per SM, whichever needs fewer (weighted) waves.
+struct ClimbForm { int G, MB; };
+ClimbForm pick_climb_form(const ona_engine* e, int count) {
+    int G = e->group;
+    if (G != 4 && G != 16) G = 8;
+    if (e->group_forced) return ClimbForm{G, e->climb_mb5 ? 5 : 0};
+    const int sm = e->sm_count;
+    if (count <= 2 * sm) return ClimbForm{8, 0};
+    const double t4 = std::ceil((double)count / (4.0 * sm)) / 1.48, t5 = std::ceil((double)count / (5.0 * sm)) / 1.20;
+    const bool fits5 = 5 * (state_smem(e) + 9 * 1024) <= (size_t)227 * 1024;
+    return ClimbForm{4, (fits5 && t5 < t4) ? 5 : 0};
+}
+
 int launch_climb(ona_engine* e, int first, int count, long long iters, const int* xy_dev,
                  unsigned long long seed, const int* objs_dev, int force_obj,
                  unsigned char* acc_dev, long long* nacc_dev) {
-    // lanes per proposal: 8 while every individual gets a resident CTA (two 256-thread CTAs per SM);
-    // beyond that 4 (128-thread CTAs, four per SM): a second, partly filled wave costs far more than
-    // the slower CTA (320 individuals: 3.7 vs 5.4 x 10^8 iterations/s, profiles/r2b_hc_group_sweep.json)
-    int G = e->group;
-    if (G != 4 && G != 16) G = 8;
-    if (!e->group_forced && count > 2 * e->sm_count) G = 4;
+    const ClimbForm f = pick_climb_form(e, count);
+#define ONA_CLIMB(T, G, MB) launch_climb_tg<T, G, MB>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev)
     if (e->small_ids) {
-        if (G == 4) return launch_climb_tg<uint16_t, 4>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
-        if (G == 16) return launch_climb_tg<uint16_t, 16>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
-        return launch_climb_tg<uint16_t, 8>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
+        if (f.G == 4) return f.MB == 5 ? ONA_CLIMB(uint16_t, 4, 5) : ONA_CLIMB(uint16_t, 4, 0);
+        if (f.G == 16) return ONA_CLIMB(uint16_t, 16, 0);
+        return ONA_CLIMB(uint16_t, 8, 0);
     }
-    if (G == 4) return launch_climb_tg<uint32_t, 4>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
-    if (G == 16) return launch_climb_tg<uint32_t, 16>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
-    return launch_climb_tg<uint32_t, 8>(e, first, count, iters, xy_dev, seed, objs_dev, force_obj, acc_dev, nacc_dev);
+    if (f.G == 4) return f.MB == 5 ? ONA_CLIMB(uint32_t, 4, 5) : ONA_CLIMB(uint32_t, 4, 0);
+    if (f.G == 16) return ONA_CLIMB(uint32_t, 16, 0);
+    return ONA_CLIMB(uint32_t, 8, 0);
+#undef ONA_CLIMB
 }
 
 template <typename V>
@@ -796,6 +813,7 @@ int ona_engine_create(int device, const ona_problem* pr, ona_engine** out) {
     if (const char* gs = getenv("ONA_GROUP")) {
         const int v = atoi(gs);
         if (v == 4 || v == 8 || v == 16) { e->group = v; e->group_forced = true; }
+        if (v == 45) { e->group = 4; e->group_forced = true; e->climb_mb5 = true; }
     }
     if (const char* ps = getenv("ONA_PIPE_SLICES")) e->pipe_slices = std::max(1, std::min(kPipeSlices, atoi(ps)));
     e->nc_ic_off = (pr->n1 + 7) / 8 * 8;
@@ -821,7 +839,7 @@ int ona_engine_fork(ona_engine* parent, ona_engine** out) {
     e->device = parent->device;
     e->owned = parent->owned;                 // graph layouts and score tables are shared, never copied
     e->g = parent->g; e->S = parent->S; e->G = parent->G; e->ob = parent->ob;
-    e->small_ids = parent->small_ids; e->group = parent->group; e->group_forced = parent->group_forced;
+    e->small_ids = parent->small_ids; e->group = parent->group; e->group_forced = parent->group_forced; e->climb_mb5 = parent->climb_mb5;
     e->pipe_slices = parent->pipe_slices; e->fast_ok = parent->fast_ok; e->fast_min_k = parent->fast_min_k;
     e->split_min_count = parent->split_min_count; e->nc_ic_off = parent->nc_ic_off; e->nc_stride = parent->nc_stride;
     e->use_graphs = parent->use_graphs; e->sm_count = parent->sm_count; e->smem_optin = parent->smem_optin;

@@ -1196,8 +1196,12 @@ __device__ __forceinline__ bool commit_conflicts(const DevGraph& g, const RoundS
     return commit_conflicts(g, j, bloom_or(j.n1x, j.n1y), bloom_or(j.n2x, j.n2y), i);
 }
 
-template <typename T, int G>
-__global__ void __launch_bounds__(kRound * G)
+// MB: CTAs per SM the register budget is set for (0 = the compiler's own choice: 127 registers, i.e. two
+// 256-thread or four 128-thread CTAs per SM; 5 = 96 registers, five 128-thread CTAs)
+template <int THREADS, int MB> struct ClimbBounds { static constexpr int blocks = MB; };
+template <int THREADS> struct ClimbBounds<THREADS, 0> { static constexpr int blocks = 65536 / (127 * THREADS) > 0 ? 65536 / (128 * THREADS) : 1; };
+template <typename T, int G, int MB = 0>
+__global__ void __launch_bounds__(kRound * G, ClimbBounds<kRound * G, MB>::blocks)
 k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first,
              long long iters, const int* __restrict__ xy, unsigned long long seed,
              long long island_offset, const int* __restrict__ objs, int force_obj,

@@ -768,7 +768,7 @@ def test_edit_lists_random_against_oracle():
 
 
 # ------------------------------------------------------------------ every hill-climb instantiation
-@pytest.mark.parametrize("group", ["4", "8", "16"])
+@pytest.mark.parametrize("group", ["4", "45", "8", "16"])      # 45: 4 lanes, register budget for five CTAs per SM
 @pytest.mark.parametrize("total", [True, False])
 def test_hill_climb_every_group_size(monkeypatch, group, total):
     """k_hill_climb<T, G> for G = 4 (what populations above 3 x SMs get), 8 and 16, forced through
