@@ -11,7 +11,7 @@ if os.environ.get("HC_CHILD"):
     pair = bench.make_workload()
     e = engine.Engine.from_pair(pair, bench.OBJECTIVES)
     out = {}
-    for P in (200, 296, 320, 455, 592, 700, 1024, 1223, 2048):
+    for P in [int(v) for v in os.environ.get("HC_POPS", "200,296,320,455,592,700,1024,1223,2048").split(",")]:
         aln, _ = synth.random_population(pair, P, seed=1000)
         e.resize(P); e.upload(aln); e.full_fitness(seed_mode=engine.SEED_REFCOMPAT)
         e.hill_climb(iters=500, seed=1)
@@ -23,7 +23,7 @@ if os.environ.get("HC_CHILD"):
     print("HC " + json.dumps(out))
     sys.exit(0)
 res = {}
-for grp in ("4", "8", None):
+for grp in [g if g != "auto" else None for g in os.environ.get("HC_GROUPS", "4,8,auto").split(",")]:
     env = dict(os.environ, HC_CHILD="1")
     if grp:
         env["ONA_GROUP"] = grp
