@@ -104,7 +104,10 @@ struct ona_engine {
     int pipe_slices = 8;     // host-buffer pipeline depth of ona_swap_deltas
     bool fast_ok = false;    // the fast swap-delta walk (node counts) is usable on this problem
     int fast_min_k = 4096;   // ... and pays from this many candidates per individual on
-    int split_min_count = 32;  // full fitness: from this many individuals on, one CTA per network
+    // full fitness: from this many individuals on, one CTA per network.  Below ~100 individuals the sliced
+    // kernel fills the SMs better (32 individuals: 21 us vs 48 us) even when the node counts the split
+    // kernel leaves behind have to be counted separately afterwards (profiles/r2b_ff_sweep*.json)
+    int split_min_count = 96;
     int nc_ic_off = 0, nc_stride = 0;   // layout of one individual's node counts
     bool use_graphs = true;             // replay the host-buffer pipeline of ona_swap_deltas as a CUDA graph
     std::vector<PipeGraph> graphs;
