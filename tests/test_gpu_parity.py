@@ -19,7 +19,7 @@ def swap_delta_walk(request, monkeypatch):
     candidates per individual on; ONA_FAST_MIN_K is read when an engine is created)"""
     monkeypatch.setenv("ONA_FAST_MIN_K", "-1" if request.param == "classic-walk" else "0")
     # ... and with both from-scratch kernels: edge slices over several CTAs (small batches) and one
-    # CTA per network (from 32 individuals on), which also leaves the node counts behind
+    # CTA per network (from 96 individuals on), which also leaves the node counts behind
     monkeypatch.setenv("ONA_FF_SPLIT_MIN", "1000000" if request.param == "classic-walk" else "1")
     return request.param
 
