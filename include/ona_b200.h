@@ -279,6 +279,18 @@ int ona_apply_swaps(ona_engine* e, int first, int count, int nswaps, const int* 
 #define ONA_EDIT_CROSS 3
 int ona_apply_edits(ona_engine* e, int first, int count, int nops, const int* ops);
 
+/* ---------------------------------------------------------------- GOC matrix
+ * Replaces: the pair loop of loadGOC (goc.cpp:23-50; 31.8 s on one host thread for the bundled example pair):
+ * the dense n1 x n2 matrix of double(|A n B|) / double(|A u B|) over the annotation sets loadAnnotations
+ * returns (goc.cpp:55-89), computed on the GPU and written to the caller's row-major host matrix `out`
+ * (e.g. the data() of the GOCDict a replacement loadGOC returns).  Term sets as CSR, rows sorted ascending
+ * without duplicates (std::set<int> order); present1/2[u] != 0 iff node u has an entry in the reference's
+ * map (NULL: "row non-empty"); pairs with an absent node stay 0.0, two present-but-empty sets give 0/0 = NaN
+ * as goc.cpp:47 does.  Needs no engine; values are bit-identical to the reference's. */
+int ona_goc_matrix(int device, int n1, int n2, const int* ann_rowptr1, const int* ann_terms1,
+                   const unsigned char* ann_present1, const int* ann_rowptr2, const int* ann_terms2,
+                   const unsigned char* ann_present2, double* out);
+
 /* ------------------------------------------------------------ measurement aid
  * Replaces nothing in the reference.  Measures, on the engine's GPU and stream, how many scattered
  * 4-byte reads per second (one 32-byte sector each, 8 independent loads in flight per thread, all SMs)

@@ -1405,6 +1405,53 @@ int ona_steepest_step(ona_engine* e, int slot, double* best_delta, int* best_x, 
     return ONA_OK;
 }
 
+int ona_goc_matrix(int device, int n1, int n2, const int* rp1, const int* t1, const unsigned char* present1,
+                   const int* rp2, const int* t2, const unsigned char* present2, double* out) {
+    if (n1 <= 0 || n2 <= 0 || !rp1 || !rp2 || !out) return fail(ONA_ERR_INVALID, "null argument");
+    if (n1 > 65535) return fail(ONA_ERR_INVALID, "GOC matrix: more than 65535 net1 nodes");   // one grid row per node
+    const int m1 = rp1[n1], m2 = rp2[n2];
+    if ((m1 && !t1) || (m2 && !t2)) return fail(ONA_ERR_INVALID, "annotation terms missing");
+    for (int net = 0; net < 2; ++net) {
+        const int n = net ? n2 : n1;
+        const int* rp = net ? rp2 : rp1;
+        const int* tm = net ? t2 : t1;
+        if (rp[0] != 0) return fail(ONA_ERR_INVALID, "annotation rowptr[0] != 0");
+        for (int u = 0; u < n; ++u) {
+            if (rp[u + 1] < rp[u]) return fail(ONA_ERR_INVALID, "annotation rowptr not monotone");
+            for (int k = rp[u] + 1; k < rp[u + 1]; ++k)
+                if (tm[k] <= tm[k - 1]) return fail(ONA_ERR_INVALID, "annotation rows must be sorted and unique");
+        }
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(ONA_ERR_CUDA, "no usable CUDA device (there is no CPU fallback)");
+    CU(cudaSetDevice(device));
+    int *d_rp1 = nullptr, *d_t1 = nullptr, *d_rp2 = nullptr, *d_t2 = nullptr;
+    unsigned char *d_p1 = nullptr, *d_p2 = nullptr;
+    double* d = nullptr;
+    auto release = [&]() {
+        cudaFree(d_rp1); cudaFree(d_t1); cudaFree(d_rp2); cudaFree(d_t2); cudaFree(d_p1); cudaFree(d_p2); cudaFree(d);
+    };
+    auto up = [&](const void* h, size_t bytes, void** dp) {
+        if (cudaMalloc(dp, std::max<size_t>(bytes, 4)) != cudaSuccess) return false;
+        return bytes == 0 || cudaMemcpy(*dp, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    bool ok = up(rp1, (size_t)(n1 + 1) * 4, (void**)&d_rp1) && up(t1, (size_t)m1 * 4, (void**)&d_t1) &&
+              up(rp2, (size_t)(n2 + 1) * 4, (void**)&d_rp2) && up(t2, (size_t)m2 * 4, (void**)&d_t2);
+    if (ok && present1) ok = up(present1, (size_t)n1, (void**)&d_p1);
+    if (ok && present2) ok = up(present2, (size_t)n2, (void**)&d_p2);
+    const size_t cells = (size_t)n1 * (size_t)n2;
+    ok = ok && cudaMalloc(&d, cells * sizeof(double)) == cudaSuccess;
+    if (!ok) { release(); return fail(ONA_ERR_CUDA, "device allocation or upload failed"); }
+    dim3 grid((n2 + 255) / 256, n1);
+    k_build_jaccard<<<grid, 256>>>(n1, n2, d_rp1, d_t1, d_rp2, d_t2, d_p1, d_p2, d);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemcpy(out, d, cells * sizeof(double), cudaMemcpyDeviceToHost);
+    release();
+    if (err != cudaSuccess) return fail(ONA_ERR_CUDA, cudaGetErrorString(err));
+    return ONA_OK;
+}
+
 int ona_probe_gather_rate(ona_engine* e, long long table_bytes, double* sectors_per_s, double* ms_out) {
     ENTER(e);
     if (!sectors_per_s || table_bytes < 4096 || table_bytes > (1ll << 31)) return fail(ONA_ERR_INVALID, "bad argument");

@@ -24,7 +24,7 @@ EXPORTS = [
     "ona_set_island_offset", "ona_set_objectives", "ona_pop_resize", "ona_pop_upload", "ona_pop_download",
     "ona_pop_set_counters", "ona_pop_get_counters", "ona_full_fitness", "ona_full_fitness_dev",
     "ona_swap_deltas", "ona_swap_deltas_rng", "ona_swap_deltas_dev", "ona_steepest_step", "ona_rng_proposals", "ona_hill_climb", "ona_hill_climb_lists", "ona_hill_climb_batched",
-    "ona_hill_climb_mt", "ona_mt_proposals", "ona_probe_gather_rate",
+    "ona_hill_climb_mt", "ona_mt_proposals", "ona_probe_gather_rate", "ona_goc_matrix",
     "ona_apply_swaps", "ona_apply_edits", "ona_export_fitness_dev", "ona_nsga2_rank", "ona_nsga2_rank_dev",
 ]
 
@@ -102,6 +102,7 @@ def load_library(build_if_missing=True):
     L.ona_hill_climb_mt.argtypes = [vp, ci, ci, ll, vp, vp, vp, vp]
     L.ona_mt_proposals.argtypes = [vp, ci, ci, ci, ll, vp, vp]
     L.ona_probe_gather_rate.argtypes = [vp, ll, vp, vp]
+    L.ona_goc_matrix.argtypes = [ci, ci, ci] + [vp] * 7
     L.ona_apply_swaps.argtypes = [vp, ci, ci, ci, vp]
     L.ona_export_fitness_dev.argtypes = [vp, ci, ci, vp]
     L.ona_apply_edits.argtypes = [vp, ci, ci, ci, vp]
@@ -429,6 +430,27 @@ class Engine:
             fitness_ptr, has_norm_ptr, norm_ptr, dom_rank_ptr, front_order_ptr, front_offsets_ptr)],
             C.addressof(nf), *[C.c_void_p(p) if p else None for p in (order_after_ptr, crowd_dist_ptr)]))
         return nf.value
+
+
+def goc_matrix(ann1, ann2, present1=None, present2=None, device=0):
+    """ona_goc_matrix: loadGOC's dense Jaccard matrix (goc.cpp:16-52) from two lists of sorted term arrays,
+    computed on the GPU.  present: which nodes have an entry in the reference's map (default: non-empty)."""
+    L = load_library()
+
+    def rows(ann, present):
+        rp = np.zeros(len(ann) + 1, np.int32)
+        rp[1:] = np.cumsum([len(a) for a in ann])
+        t = np.concatenate([np.asarray(a, np.int32) for a in ann]) if rp[-1] else np.zeros(0, np.int32)
+        p = np.array([len(a) > 0 for a in ann], np.uint8) if present is None else np.asarray(present, np.uint8)
+        return rp, np.ascontiguousarray(t, np.int32), np.ascontiguousarray(p)
+    rp1, t1, p1 = rows(ann1, present1)
+    rp2, t2, p2 = rows(ann2, present2)
+    out = np.empty((len(ann1), len(ann2)), np.float64)
+    rc = L.ona_goc_matrix(int(device), len(ann1), len(ann2), _ptr(rp1), _ptr(t1), _ptr(p1), _ptr(rp2), _ptr(t2),
+                          _ptr(p2), _ptr(out))
+    if rc != 0:
+        raise OnaError("ona error %d: %s" % (rc, L.ona_last_error().decode()))
+    return out
 
 
 def rng_proposals_host(seed, n1, n2, first_global, count, K, start=0):

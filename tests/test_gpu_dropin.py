@@ -33,6 +33,19 @@ def test_dropin_matches_reference(with_goc, lines):
         pair = synth.with_duplicate_lines(pair, 150, seed=8)
     d = tempfile.mkdtemp()
     paths = synth.write_text(pair, os.path.join(d, "w"))
+    if with_goc and lines == "duplicate-lines":
+        # annotation files as untidy as the reference's loader tolerates (goc.cpp:55-89): names the
+        # network does not know (they land on node 0, the last one wins), a node listed twice (the last
+        # line replaces the first), a line without terms (an empty set), an empty line, repeated terms on one line -- the replacement loadGOC / loadAnnotations
+        # (host/goc_b200.cpp, pair loop on the GPU) must give the reference's matrix value for value
+        for tag, node in (("annos1", "a7"), ("annos2", "b9")):
+            with open(paths[tag], "a") as f:
+                f.write("nobody%s 3 5 7 11\n" % tag)
+                f.write("%s 2 3 3 5 5 5\n" % node)
+                if tag == "annos1":      # (an empty set in BOTH files would put a NaN = 0/0 into the matrix, and
+                    f.write("%s\n" % (node[0] + "11"))   # the reference's ranking is undefined on NaN objectives)
+                    f.write("\n")
+                f.write("somebodyelse 1 2\n")
     seed, iters, nthreads = 77, 4000, 3
     a1 = paths.get("annos1", "-") if with_goc else "-"
     a2 = paths.get("annos2", "-") if with_goc else "-"

@@ -700,6 +700,21 @@ def test_goc_table_built_on_device_from_term_sets(mid):
     assert np.array_equal(a0, a1) and np.array_equal(c0["goc"], c1["goc"])
     for p in range(P):
         assert r1["goc"][p] == port.Aln(prob, aln[p]).counters()[3]
+    # the stand-alone form a replacement loadGOC calls (host/goc_b200.cpp): the dense host matrix itself,
+    # with nodes that have an entry but no terms (0/0 = NaN against each other, goc.cpp:47) and absent nodes
+    assert np.array_equal(engine.goc_matrix(pair.ann1, pair.ann2), G)
+    a1 = [np.array(t) for t in ([1, 5, 9], [], [5], [], [2, 3])]
+    a2 = [np.array(t) for t in ([5, 9], [], [], [1, 2, 3, 5, 9, 11])]
+    M = engine.goc_matrix(a1, a2, present1=[1, 1, 1, 0, 1], present2=[1, 1, 0, 1])
+    want = np.zeros((5, 4))
+    for i, (s1, q1) in enumerate(zip(a1, [1, 1, 1, 0, 1])):
+        for j, (s2, q2) in enumerate(zip(a2, [1, 1, 0, 1])):
+            if q1 and q2:
+                inter, union = len(set(s1) & set(s2)), len(set(s1) | set(s2))
+                want[i, j] = np.float64(inter) / np.float64(union) if union else np.nan
+    assert np.array_equal(M, want, equal_nan=True) and np.isnan(M[1, 1])
+    with pytest.raises(engine.OnaError, match="sorted"):
+        engine.goc_matrix([np.array([3, 1])], [np.array([1])])
 
 
 # ------------------------------------------------------------------ edit lists (partial operators)
