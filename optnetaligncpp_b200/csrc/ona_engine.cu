@@ -1636,14 +1636,14 @@ int ona_hill_climb_batched(ona_engine* e, int first, int count, long long iters,
         objs_dev = e->t_i0.p;
     }
     CU(e->t_l0.need((size_t)count));
-    // claim arrays (4 x n2 x u16) live in shared memory next to the staged state when they fit
+    // claim arrays (2 x n2 x u16) live in shared memory next to the staged state when they fit
     invalidate_counts(e, first, count);
-    const size_t claim_bytes = (size_t)4 * e->g.n2 * 2;
+    const size_t claim_bytes = (size_t)2 * e->g.n2 * 2;
     size_t smem = state_smem(e) + claim_bytes;
     unsigned short* claims_global = nullptr;
     if (smem + 40 * 1024 > e->smem_optin) {
         smem = state_smem(e);
-        CU(e->t_claims.need((size_t)count * 4 * e->g.n2));
+        CU(e->t_claims.need((size_t)count * 2 * e->g.n2));
         claims_global = e->t_claims.p;
     }
     if (e->small_ids) {

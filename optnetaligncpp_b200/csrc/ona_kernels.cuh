@@ -1485,6 +1485,7 @@ k_hill_climb(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, 
 //   WP_j = {x_j, y_j}, WV_j = {a_x, a_y}              what applying j writes (aln / alnInv)
 //   RP_j = N1(x_j) u N1(y_j), RV_j = N2(a_x) u N2(a_y) (only when the induced lists were walked)
 //   wminP[n] / wminV[n] = lowest accepted j writing n,  rminP[n] / rminV[n] = lowest j reading n
+//   (stored as two position-indexed arrays, see the kernel: at the base state position and image stand for each other)
 // proposal j is applied iff it is the lowest writer of everything it writes, nobody lower
 // reads what it writes, and nobody lower writes what it reads.  Applied proposals therefore
 // have disjoint write sets and untouched read sets: their integer deltas are exact and
@@ -1520,14 +1521,14 @@ __device__ __forceinline__ void for_each_neighbour(const DevGraph& g, const Quad
 }
 
 #ifndef ONA_BAT_THREADS
-#define ONA_BAT_THREADS 1024
+#define ONA_BAT_THREADS 512
 #endif
 constexpr int kBatThreads = ONA_BAT_THREADS;   // batched hill climb: one CTA per individual
 constexpr int kBatCap = 1024;                  // proposals per round
 constexpr int kBatPer = kBatCap / kBatThreads;
 
 template <typename T>
-__global__ void __launch_bounds__(kBatThreads, 1)
+__global__ void __launch_bounds__(kBatThreads, kBatThreads <= 512 ? 2 : 1)
 k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevPop pop, int first,
                      long long iters, const int* __restrict__ xy, unsigned long long seed,
                      long long island_offset, const int* __restrict__ objs,
@@ -1547,15 +1548,18 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     T *s_aln, *s_inv;
     const int pl = blockIdx.x, p = first + pl;
     State<T>::acquire(pop, p, g.n2, smem_raw, s_aln, s_inv);
-    // claim arrays: [wminP | rminP | wminV | rminV], n2 entries each; in shared memory right
-    // after the staged state when they fit, else in a per-individual global scratch
+    // claim arrays [w | r], n2 entries each, indexed by POSITION: in shared memory right after the staged
+    // state when they fit, else in a per-individual global scratch.  At the round's base state a position
+    // p and its image aln[p] stand for each other (writing aln[p] and writing alnInv[aln[p]] always come
+    // together, and a read of alnInv[v] is hit by exactly the writers of position alnInv[v]), so the
+    // image-indexed arrays of the rule above are these two looked up through alnInv: half the shared
+    // memory, which is what lets two CTAs share an SM.
     const size_t state_bytes = sizeof(T) == 2 ? (size_t)2 * pop.n2p * 2 : 0;
-    unsigned short* claims = claims_global ? claims_global + (size_t)pl * 4 * g.n2
+    unsigned short* claims = claims_global ? claims_global + (size_t)pl * 2 * g.n2
                                            : reinterpret_cast<unsigned short*>(smem_raw + state_bytes);
-    unsigned short* wminP = claims;
-    unsigned short* rminP = claims + g.n2;
-    unsigned short* wminV = claims + 2 * g.n2;
-    unsigned short* rminV = claims + 3 * g.n2;
+    unsigned short* wmin = claims;
+    unsigned short* rmin = claims + g.n2;
+    auto pos_of = [&](int v) { return (int)((uint32_t)s_inv[v] & MASK); };   // position whose image is v
 
     const int obj = objs ? objs[pl] : -1;
     const unsigned long long ikey = rng_individual_key(seed, (unsigned long long)(island_offset + p));
@@ -1572,7 +1576,7 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
         const int n = (int)min((long long)kBatCap, iters - pos);
         const Scalars cur = s_cur;
         // ---- A: proposals, work keys, sort; reset the claim arrays
-        for (int i = threadIdx.x; i < 4 * g.n2; i += kBatThreads) claims[i] = kNoClaim;
+        for (int i = threadIdx.x; i < 2 * g.n2; i += kBatThreads) claims[i] = kNoClaim;
         if (threadIdx.x < kBatCap / 32) { s_accept[threadIdx.x] = 0u; s_select[threadIdx.x] = 0u; }
         int key[kBatPer];
 #pragma unroll
@@ -1650,31 +1654,69 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
         }
         if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
-        // ---- E: accepted proposals claim what they write and read (lowest index wins)
-        for (int sp = threadIdx.x; sp < n; sp += kBatThreads) {
-            const int i = s_order[sp];
+        // ---- E: accepted proposals claim what they write and read (lowest index wins).  In sorted order
+        //      (longest lists first): the round's hubs by whole warps, lanes striding their quads, everybody
+        //      else by groups of four lanes -- one thread per proposal made the thread with the longest
+        //      lists (120 quads, each a dependent L2 load plus four shared-memory atomics) the round's
+        //      critical path: 121 k of its 250 k cycles here and 54 k more in F (profiles/README.md)
+        const int sub = lane & 3, quad_slot = threadIdx.x >> 2;
+        const unsigned sub_mask = 0xFu << (lane & 28);
+        // E1: the writes (two positions per proposal).  A read only matters where somebody writes, and
+        // only ~1 500 of the 8 000 positions are written in a round, so the read claims of E2 first look
+        // whether the position has a writer at all: four out of five shared-memory atomics never happen
+        for (int i = threadIdx.x; i < n; i += kBatThreads) {
             if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
             const int2 q = s_xy[i];
-            const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
-            const QuadPlan pl4 = make_plan(g, cx);
-            const unsigned short j = (unsigned short)i;
-            claim_min(wminP, q.x, j); claim_min(wminP, q.y, j);
-            claim_min(wminV, cx.ax, j); claim_min(wminV, cx.ay, j);
-            for_each_neighbour(g, pl4, 0, 1, [&](int l, int id) { claim_min(l < 2 ? rminP : rminV, id, j); });
+            claim_min(wmin, q.x, (unsigned short)i);
+            claim_min(wmin, q.y, (unsigned short)i);
         }
         __syncthreads();
-        // ---- F: select the conflict-free subset
-        for (int sp = threadIdx.x; sp < n; sp += kBatThreads) {
+        auto claim_read = [&](int pos, unsigned short j) {
+            if (wmin[pos] != kNoClaim) claim_min(rmin, pos, j);
+        };
+        for (int h = warp; h < nhub; h += kBatThreads / 32) {
+            const int i = s_order[h];
+            if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
+            const int2 q = s_xy[i];
+            const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
+            const QuadPlan pl4 = make_plan(g, cx);
+            const unsigned short j = (unsigned short)i;
+            for_each_neighbour(g, pl4, lane, 32, [&](int l, int id) { claim_read(l < 2 ? id : pos_of(id), j); });
+        }
+        for (int sp = nhub + quad_slot; sp < n; sp += kBatThreads / 4) {
             const int i = s_order[sp];
             if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
             const int2 q = s_xy[i];
             const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
             const QuadPlan pl4 = make_plan(g, cx);
             const unsigned short j = (unsigned short)i;
-            bool ok = wminP[q.x] == j && wminP[q.y] == j && wminV[cx.ax] == j && wminV[cx.ay] == j &&
-                      rminP[q.x] >= j && rminP[q.y] >= j && rminV[cx.ax] >= j && rminV[cx.ay] >= j;
-            for_each_neighbour(g, pl4, 0, 1, [&](int l, int id) { ok = ok && (l < 2 ? wminP : wminV)[id] >= j; });
-            if (ok) atomicOr(&s_select[i >> 5], 1u << (i & 31));
+            for_each_neighbour(g, pl4, sub, 4, [&](int l, int id) { claim_read(l < 2 ? id : pos_of(id), j); });
+        }
+        __syncthreads();
+        // ---- F: select the conflict-free subset (same division of the work)
+        for (int h = warp; h < nhub; h += kBatThreads / 32) {
+            const int i = s_order[h];
+            if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
+            const int2 q = s_xy[i];
+            const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
+            const QuadPlan pl4 = make_plan(g, cx);
+            const unsigned short j = (unsigned short)i;
+            bool ok = wmin[q.x] == j && wmin[q.y] == j && rmin[q.x] >= j && rmin[q.y] >= j;
+            for_each_neighbour(g, pl4, lane, 32, [&](int l, int id) { ok = ok && wmin[l < 2 ? id : pos_of(id)] >= j; });
+            ok = __all_sync(0xffffffffu, ok);
+            if (ok && lane == 0) atomicOr(&s_select[i >> 5], 1u << (i & 31));
+        }
+        for (int sp = nhub + quad_slot; sp < n; sp += kBatThreads / 4) {
+            const int i = s_order[sp];
+            if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
+            const int2 q = s_xy[i];
+            const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
+            const QuadPlan pl4 = make_plan(g, cx);
+            const unsigned short j = (unsigned short)i;
+            bool ok = wmin[q.x] == j && wmin[q.y] == j && rmin[q.x] >= j && rmin[q.y] >= j;
+            for_each_neighbour(g, pl4, sub, 4, [&](int l, int id) { ok = ok && wmin[l < 2 ? id : pos_of(id)] >= j; });
+            ok = (__ballot_sync(sub_mask, ok) & sub_mask) == sub_mask;   // the four lanes of this proposal agree
+            if (ok && sub == 0) atomicOr(&s_select[i >> 5], 1u << (i & 31));
         }
         __syncthreads();
         // ---- G: apply the selected proposals (disjoint writes), fold their deltas
