@@ -1520,6 +1520,26 @@ __device__ __forceinline__ void for_each_neighbour(const DevGraph& g, const Quad
     }
 }
 
+// A proposal's four quad lists in 16 bytes (list l: first quad << 8 | number of quads), so that the claim
+// and selection phases of the batched climb need not fetch the row pointers a second and third time.
+// A list of 255 or more quads, or a quad index beyond 24 bits, is marked 255: the plan is then rebuilt.
+__device__ __forceinline__ uint4 pack_quad_plan(const QuadPlan& p) {
+    const int q[4] = {p.e0, p.e1 - p.e0, p.e2 - p.e1, p.e3 - p.e2};
+    const int b[4] = {p.b0, p.b1 + p.e0, p.b2 + p.e1, p.b3 + p.e2};
+    uint32_t w[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+        w[l] = (q[l] >= 255 || (unsigned)b[l] >= (1u << 24)) ? 255u : (((uint32_t)b[l] << 8) | (uint32_t)q[l]);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ bool unpack_quad_plan(const uint4& w, QuadPlan& p) {
+    if (((w.x & 255u) == 255u) | ((w.y & 255u) == 255u) | ((w.z & 255u) == 255u) | ((w.w & 255u) == 255u)) return false;
+    const int q0 = (int)(w.x & 255u), q1 = (int)(w.y & 255u), q2 = (int)(w.z & 255u), q3 = (int)(w.w & 255u);
+    p.e0 = q0; p.e1 = q0 + q1; p.e2 = p.e1 + q2; p.e3 = p.e2 + q3;
+    p.b0 = (int)(w.x >> 8); p.b1 = (int)(w.y >> 8) - p.e0; p.b2 = (int)(w.z >> 8) - p.e1; p.b3 = (int)(w.w >> 8) - p.e2;
+    return true;
+}
+
 #ifndef ONA_BAT_THREADS
 #define ONA_BAT_THREADS 512
 #endif
@@ -1537,6 +1557,7 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int2 s_xy[kBatCap];
     __shared__ int2 s_res[kBatCap];
+    __shared__ uint4 s_plan[kBatCap];     // packed quad plans of the round's proposals (phase C -> E, F)
     __shared__ unsigned short s_order[kBatCap];
     __shared__ unsigned short s_cnt[kBatThreads / 32 * kBatPer][kSortBins];
     __shared__ unsigned int s_accept[kBatCap / 32], s_select[kBatCap / 32];
@@ -1619,6 +1640,7 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                 if (lane == 0) {
                     special_terms(g, cx, seen, dc, di);
                     s_res[i] = make_int2(dc, di);
+                    s_plan[i] = pack_quad_plan(pl4);
                 }
                 continue;
             }
@@ -1633,6 +1655,7 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                 walk_plan<T>(g, s_aln, s_inv, cx, pl4, 0, 1, dc, di, seen);
                 if (seen) special_terms(g, cx, seen, dc, di);
                 s_res[i] = make_int2(dc, di);
+                s_plan[i] = pack_quad_plan(pl4);
             }
         }
         __syncthreads();
@@ -1679,7 +1702,8 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
             const int2 q = s_xy[i];
             const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
-            const QuadPlan pl4 = make_plan(g, cx);
+            QuadPlan pl4;
+            if (!unpack_quad_plan(s_plan[i], pl4)) pl4 = make_plan(g, cx);
             const unsigned short j = (unsigned short)i;
             for_each_neighbour(g, pl4, lane, 32, [&](int l, int id) { claim_read(l < 2 ? id : pos_of(id), j); });
         }
@@ -1688,7 +1712,8 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
             const int2 q = s_xy[i];
             const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
-            const QuadPlan pl4 = make_plan(g, cx);
+            QuadPlan pl4;
+            if (!unpack_quad_plan(s_plan[i], pl4)) pl4 = make_plan(g, cx);
             const unsigned short j = (unsigned short)i;
             for_each_neighbour(g, pl4, sub, 4, [&](int l, int id) { claim_read(l < 2 ? id : pos_of(id), j); });
         }
@@ -1699,7 +1724,8 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
             const int2 q = s_xy[i];
             const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
-            const QuadPlan pl4 = make_plan(g, cx);
+            QuadPlan pl4;
+            if (!unpack_quad_plan(s_plan[i], pl4)) pl4 = make_plan(g, cx);
             const unsigned short j = (unsigned short)i;
             bool ok = wmin[q.x] == j && wmin[q.y] == j && rmin[q.x] >= j && rmin[q.y] >= j;
             for_each_neighbour(g, pl4, lane, 32, [&](int l, int id) { ok = ok && wmin[l < 2 ? id : pos_of(id)] >= j; });
@@ -1711,7 +1737,8 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
             const int2 q = s_xy[i];
             const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
-            const QuadPlan pl4 = make_plan(g, cx);
+            QuadPlan pl4;
+            if (!unpack_quad_plan(s_plan[i], pl4)) pl4 = make_plan(g, cx);
             const unsigned short j = (unsigned short)i;
             bool ok = wmin[q.x] == j && wmin[q.y] == j && rmin[q.x] >= j && rmin[q.y] >= j;
             for_each_neighbour(g, pl4, sub, 4, [&](int l, int id) { ok = ok && wmin[l < 2 ? id : pos_of(id)] >= j; });
