@@ -1560,7 +1560,7 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     __shared__ uint4 s_plan[kBatCap];     // packed quad plans of the round's proposals (phase C -> E, F)
     __shared__ unsigned short s_order[kBatCap];
     __shared__ unsigned short s_cnt[kBatThreads / 32 * kBatPer][kSortBins];
-    __shared__ unsigned int s_accept[kBatCap / 32], s_select[kBatCap / 32];
+    __shared__ unsigned int s_accept[kBatCap / 32], s_select[kBatCap / 32], s_okw[kBatCap / 32];
     __shared__ int s_nhub, s_next;
     __shared__ double red_d[32];
     __shared__ int red_i[32];
@@ -1598,7 +1598,7 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
         const Scalars cur = s_cur;
         // ---- A: proposals, work keys, sort; reset the claim arrays
         for (int i = threadIdx.x; i < 2 * g.n2; i += kBatThreads) claims[i] = kNoClaim;
-        if (threadIdx.x < kBatCap / 32) { s_accept[threadIdx.x] = 0u; s_select[threadIdx.x] = 0u; }
+        if (threadIdx.x < kBatCap / 32) { s_accept[threadIdx.x] = 0u; s_select[threadIdx.x] = 0u; s_okw[threadIdx.x] = 0u; }
         int key[kBatPer];
 #pragma unroll
         for (int j = 0; j < kBatPer; ++j) {
@@ -1671,6 +1671,10 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
                 const Scalars nw = apply_delta(cur, r.x, r.y, sd);
                 double unused;
                 acc = q.x != q.y && judge_move(ob, obj, cur, nullptr, nw, g.E1, nullptr, false, unused);
+                if (acc) {   // E1: an accepted proposal claims the two positions it writes (lowest index wins)
+                    claim_min(wmin, q.x, (unsigned short)i);
+                    claim_min(wmin, q.y, (unsigned short)i);
+                }
             }
             const unsigned m = __ballot_sync(0xffffffffu, acc);
             if (lane == 0) s_accept[i >> 5] = m;
@@ -1684,18 +1688,18 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
         //      critical path: 121 k of its 250 k cycles here and 54 k more in F (profiles/README.md)
         const int sub = lane & 3, quad_slot = threadIdx.x >> 2;
         const unsigned sub_mask = 0xFu << (lane & 28);
-        // E1: the writes (two positions per proposal).  A read only matters where somebody writes, and
-        // only ~1 500 of the 8 000 positions are written in a round, so the read claims of E2 first look
-        // whether the position has a writer at all: four out of five shared-memory atomics never happen
-        for (int i = threadIdx.x; i < n; i += kBatThreads) {
-            if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
-            const int2 q = s_xy[i];
-            claim_min(wmin, q.x, (unsigned short)i);
-            claim_min(wmin, q.y, (unsigned short)i);
-        }
-        __syncthreads();
-        auto claim_read = [&](int pos, unsigned short j) {
-            if (wmin[pos] != kNoClaim) claim_min(rmin, pos, j);
+        // (E1, the write claims, was done with the decisions above.)  A read only matters where somebody
+        // writes, and only ~1 500 of the 8 000 positions are written in a round, so the walk below first
+        // looks whether a position has a writer at all: four out of five shared-memory atomics never happen
+        // E2: ONE walk over the neighbour lists of every accepted proposal j does both things that need
+        // them: it claims the reads (only where a position has a writer), and it checks that nobody
+        // lower WRITES what j reads (the writers are complete after E1) -- bit j of s_okw
+        auto visit = [&](int pos, unsigned short j, bool& okw) {
+            const unsigned short w = wmin[pos];
+            if (w != kNoClaim) {
+                claim_min(rmin, pos, j);
+                okw = okw && w >= j;
+            }
         };
         for (int h = warp; h < nhub; h += kBatThreads / 32) {
             const int i = s_order[h];
@@ -1705,7 +1709,10 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             QuadPlan pl4;
             if (!unpack_quad_plan(s_plan[i], pl4)) pl4 = make_plan(g, cx);
             const unsigned short j = (unsigned short)i;
-            for_each_neighbour(g, pl4, lane, 32, [&](int l, int id) { claim_read(l < 2 ? id : pos_of(id), j); });
+            bool okw = true;
+            for_each_neighbour(g, pl4, lane, 32, [&](int l, int id) { visit(l < 2 ? id : pos_of(id), j, okw); });
+            okw = __all_sync(0xffffffffu, okw);
+            if (okw && lane == 0) atomicOr(&s_okw[i >> 5], 1u << (i & 31));
         }
         for (int sp = nhub + quad_slot; sp < n; sp += kBatThreads / 4) {
             const int i = s_order[sp];
@@ -1715,35 +1722,25 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             QuadPlan pl4;
             if (!unpack_quad_plan(s_plan[i], pl4)) pl4 = make_plan(g, cx);
             const unsigned short j = (unsigned short)i;
-            for_each_neighbour(g, pl4, sub, 4, [&](int l, int id) { claim_read(l < 2 ? id : pos_of(id), j); });
+            bool okw = true;
+            for_each_neighbour(g, pl4, sub, 4, [&](int l, int id) { visit(l < 2 ? id : pos_of(id), j, okw); });
+            okw = (__ballot_sync(sub_mask, okw) & sub_mask) == sub_mask;   // the four lanes of this proposal agree
+            if (okw && sub == 0) atomicOr(&s_okw[i >> 5], 1u << (i & 31));
         }
         __syncthreads();
-        // ---- F: select the conflict-free subset (same division of the work)
-        for (int h = warp; h < nhub; h += kBatThreads / 32) {
-            const int i = s_order[h];
-            if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
-            const int2 q = s_xy[i];
-            const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
-            QuadPlan pl4;
-            if (!unpack_quad_plan(s_plan[i], pl4)) pl4 = make_plan(g, cx);
-            const unsigned short j = (unsigned short)i;
-            bool ok = wmin[q.x] == j && wmin[q.y] == j && rmin[q.x] >= j && rmin[q.y] >= j;
-            for_each_neighbour(g, pl4, lane, 32, [&](int l, int id) { ok = ok && wmin[l < 2 ? id : pos_of(id)] >= j; });
-            ok = __all_sync(0xffffffffu, ok);
-            if (ok && lane == 0) atomicOr(&s_select[i >> 5], 1u << (i & 31));
-        }
-        for (int sp = nhub + quad_slot; sp < n; sp += kBatThreads / 4) {
-            const int i = s_order[sp];
-            if (!((s_accept[i >> 5] >> (i & 31)) & 1u)) continue;
-            const int2 q = s_xy[i];
-            const SwapCtx cx = make_ctx<T>(g, s_aln, q.x, q.y);
-            QuadPlan pl4;
-            if (!unpack_quad_plan(s_plan[i], pl4)) pl4 = make_plan(g, cx);
-            const unsigned short j = (unsigned short)i;
-            bool ok = wmin[q.x] == j && wmin[q.y] == j && rmin[q.x] >= j && rmin[q.y] >= j;
-            for_each_neighbour(g, pl4, sub, 4, [&](int l, int id) { ok = ok && wmin[l < 2 ? id : pos_of(id)] >= j; });
-            ok = (__ballot_sync(sub_mask, ok) & sub_mask) == sub_mask;   // the four lanes of this proposal agree
-            if (ok && sub == 0) atomicOr(&s_select[i >> 5], 1u << (i & 31));
+        // ---- F: select the conflict-free subset: what is left needs no list -- j is the lowest writer of
+        //      both of its positions and nobody lower reads them
+#pragma unroll
+        for (int jj = 0; jj < kBatPer; ++jj) {
+            const int i = jj * kBatThreads + threadIdx.x;
+            bool sel = false;
+            if (i < n && ((s_accept[i >> 5] >> (i & 31)) & 1u) && ((s_okw[i >> 5] >> (i & 31)) & 1u)) {
+                const int2 q = s_xy[i];
+                const unsigned short j = (unsigned short)i;
+                sel = wmin[q.x] == j && wmin[q.y] == j && rmin[q.x] >= j && rmin[q.y] >= j;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, sel);
+            if (lane == 0) s_select[i >> 5] = m;
         }
         __syncthreads();
         // ---- G: apply the selected proposals (disjoint writes), fold their deltas
