@@ -1565,6 +1565,8 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
     __shared__ double red_d[32];
     __shared__ int red_i[32];
     __shared__ Scalars s_cur;
+    __shared__ double s_curfit[kMaxObj];   // objectives of the round's base state
+    __shared__ int s_names[kMaxObj];
     constexpr uint32_t FLAG = Pk<T>::FLAG, MASK = Pk<T>::MASK;
     T *s_aln, *s_inv;
     const int pl = blockIdx.x, p = first + pl;
@@ -1599,6 +1601,10 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
         // ---- A: proposals, work keys, sort; reset the claim arrays
         for (int i = threadIdx.x; i < 2 * g.n2; i += kBatThreads) claims[i] = kNoClaim;
         if (threadIdx.x < kBatCap / 32) { s_accept[threadIdx.x] = 0u; s_select[threadIdx.x] = 0u; s_okw[threadIdx.x] = 0u; }
+        if (threadIdx.x < ob.M) {
+            s_names[threadIdx.x] = ob.names[threadIdx.x];
+            s_curfit[threadIdx.x] = objective(ob.names[threadIdx.x], cur, g.E1);
+        }
         int key[kBatPer];
 #pragma unroll
         for (int j = 0; j < kBatPer; ++j) {
@@ -1659,7 +1665,16 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             }
         }
         __syncthreads();
-        // ---- D: decide every proposal against the round's base objectives
+        // ---- D: decide every proposal against the round's base objectives (evaluated once per round into
+        //      shared memory); the score-table lookups of a thread's proposals are all requested before any
+        //      is judged
+        ScoreDelta sds[kBatPer];
+#pragma unroll
+        for (int j = 0; j < kBatPer; ++j) {
+            const int i = j * kBatThreads + threadIdx.x;
+            const int2 q = i < n ? s_xy[i] : make_int2(0, 0);
+            sds[j] = score_delta<T>(g, S, Gt, s_aln, q.x, q.y);
+        }
 #pragma unroll
         for (int j = 0; j < kBatPer; ++j) {
             const int i = j * kBatThreads + threadIdx.x;
@@ -1667,10 +1682,9 @@ k_hill_climb_batched(DevGraph g, DevTable S, DevTable Gt, DevObjectives ob, DevP
             if (i < n) {
                 const int2 q = s_xy[i];
                 const int2 r = s_res[i];
-                const ScoreDelta sd = score_delta<T>(g, S, Gt, s_aln, q.x, q.y);
-                const Scalars nw = apply_delta(cur, r.x, r.y, sd);
+                const Scalars nw = apply_delta(cur, r.x, r.y, sds[j]);
                 double unused;
-                acc = q.x != q.y && judge_move(ob, obj, cur, nullptr, nw, g.E1, nullptr, false, unused);
+                acc = q.x != q.y && judge_move(ob, obj, cur, s_curfit, nw, g.E1, nullptr, false, unused, s_names);
                 if (acc) {   // E1: an accepted proposal claims the two positions it writes (lowest index wins)
                     claim_min(wmin, q.x, (unsigned short)i);
                     claim_min(wmin, q.y, (unsigned short)i);
